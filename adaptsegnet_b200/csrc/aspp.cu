@@ -1,0 +1,383 @@
+// K1 / K1b: ASPP classifier head (model/deeplab_multi.py:106-121) on tcgen05.
+//
+// The four dilated 3x3 convolutions with N = 19 outputs are hostile to a direct implicit GEMM
+// (N padded 19 -> 32, and the pixel x 36*Cin im2col operand would stream ~2 GB through L2 per
+// call).  Instead the head is computed as ONE dense GEMM over the un-shifted activations
+// followed by a tiny shifted gather:
+//     Z[p, t*19+c] = sum_ci X[p, ci] * W_t[c, ci]          (M = pixels, N = 36*19 = 684 -> 688, K = Cin)
+//     y[c, p]      = bias_sum[c] + sum_t Z[p + shift_t, t*19+c]     (zero outside the image)
+// The branch sum of deeplab_multi.py:117-121 is the sum over t.  Backward:
+//     dYcol[q, t*19+c] = dy[c, q - shift_t]                 (tiny: dy has 19 channels)
+//     dX^T[ci, q]  = sum_j WpT[ci, j] * dYcol[q, j]         (M = Cin, N = pixels, K = 688; lands in NCHW)
+//     dWp[ci, j]   = sum_q X[ci, q] * dYcolT[j, q]          (M = Cin, N = 688, K = pixels; split-K)
+// All three GEMMs have dense, tensor-core-friendly shapes; X is read once per GEMM as bf16.
+#include "umma_host.cuh"
+
+namespace asn {
+
+
+// ---- layout kernels ------------------------------------------------------------------------
+
+// x [N][C][P] fp32 -> out [N*P][C] bf16 (64 x 64 tiles through shared memory; 256-byte reads,
+// 128-byte writes per row)
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int P) {
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const float* src = x + (int64_t)n * C * P;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    int cl = i / 64, pl = i % 64;
+    int c = c0 + cl, p = p0 + pl;
+    tile[cl][pl] = (c < C && p < P) ? __ldg(src + (int64_t)c * P + p) : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = out + (int64_t)n * P * C;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    int pl = i / 32, cp = (i % 32) * 2;
+    int p = p0 + pl, c = c0 + cp;
+    if (p < P && c + 1 < C) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(tile[cp][pl], tile[cp + 1][pl]);
+      *reinterpret_cast<__nv_bfloat162*>(dst + (int64_t)p * C + c) = v;
+    } else if (p < P && c < C) {
+      dst[(int64_t)p * C + c] = __float2bfloat16(tile[cp][pl]);
+    }
+  }
+}
+
+// x [N][C][P] fp32 -> out [C][ld] bf16, column n*P + p  (K-contiguous operand for the wgrad GEMM)
+__global__ void __launch_bounds__(256)
+nchw_to_ckp_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, int P,
+                        int64_t ld) {
+  const int64_t total = (int64_t)N * C * P;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    int p = (int)(i % P);
+    int c = (int)((i / P) % C);
+    int n = (int)(i / ((int64_t)P * C));
+    out[(int64_t)c * ld + (int64_t)n * P + p] = __float2bfloat16(__ldg(x + i));
+  }
+}
+
+struct AsppTaps {
+  int n_taps;       // 9 * n_active
+  int dh[36], dw[36];
+};
+
+// y[n][c][p] = bias_sum[c] + sum_t Z[n*P + p + shift_t][t*n_cls + c].
+// One warp owns 32 consecutive pixels; lane = class while accumulating (contiguous n_cls floats
+// per (pixel, tap)), lane = pixel while writing (coalesced NCHW rows).
+template <int MAX_CLS>
+__global__ void __launch_bounds__(256)
+aspp_gather_kernel(const float* __restrict__ Z, const float* __restrict__ bias_sum, float* __restrict__ y, int N,
+                   int H, int W, int n_cls, int NP, AsppTaps taps) {
+  __shared__ float stage[8][MAX_CLS][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = H * W;
+  const int groups_per_img = (P + 31) / 32;
+  const int g = blockIdx.x * 8 + warp;
+  if (g >= N * groups_per_img) return;
+  const int n = g / groups_per_img;
+  const int p0 = (g % groups_per_img) * 32;
+  const float b = lane < n_cls ? __ldg(bias_sum + lane) : 0.f;
+  for (int i = 0; i < 32; ++i) {
+    const int p = p0 + i;
+    float acc = b;
+    if (p < P && lane < n_cls) {
+      const int h = p / W, w = p % W;
+#pragma unroll 4
+      for (int t = 0; t < taps.n_taps; ++t) {
+        const int hh = h + taps.dh[t], ww = w + taps.dw[t];
+        if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
+          acc += __ldg(Z + ((int64_t)n * P + (int64_t)hh * W + ww) * NP + t * n_cls + lane);
+      }
+    }
+    if (lane < n_cls) stage[warp][lane][i] = acc;
+  }
+  __syncwarp();
+  if (p0 + lane < P)
+    for (int c = 0; c < n_cls; ++c) y[((int64_t)n * n_cls + c) * P + p0 + lane] = stage[warp][c][lane];
+}
+
+// dYcol[n*P + q][t*n_cls + c] = dy[n][c][q - shift_t] (0 outside), plus the transposed copy
+// dYcolT[t*n_cls + c][n*P + q].  One CTA per 32 pixels; the [32][NP] tile is staged in shared
+// memory so both outputs are written with coalesced stores.
+__global__ void __launch_bounds__(256)
+aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYcol,
+                   __nv_bfloat16* __restrict__ dYcolT, int N, int H, int W, int n_cls, int NP, int64_t ldt,
+                   AsppTaps taps) {
+  extern __shared__ __nv_bfloat16 tile[];  // [32][NP]
+  const int P = H * W;
+  const int groups_per_img = (P + 31) / 32;
+  const int n = blockIdx.x / groups_per_img;
+  const int q0 = (blockIdx.x % groups_per_img) * 32;
+  const int J = taps.n_taps * n_cls;
+  for (int idx = threadIdx.x; idx < NP * 32; idx += 256) {
+    const int j = idx >> 5, ql = idx & 31;
+    const int q = q0 + ql;
+    float v = 0.f;
+    if (j < J && q < P) {
+      const int t = j / n_cls, c = j - t * n_cls;
+      const int h = q / W - taps.dh[t], w = q % W - taps.dw[t];
+      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+        v = __ldg(dy + ((int64_t)n * n_cls + c) * P + (int64_t)h * W + w);
+    }
+    const __nv_bfloat16 bv = __float2bfloat16(v);
+    tile[ql * NP + j] = bv;
+    if (q < P) dYcolT[(int64_t)j * ldt + (int64_t)n * P + q] = bv;
+  }
+  __syncthreads();
+  // rows q0..q0+31 of dYcol are contiguous: NP*2 bytes each, NP % 8 == 0 -> 16-byte vectors
+  const int vec_per_row = NP / 8;
+  const uint4* src = reinterpret_cast<const uint4*>(tile);
+  uint4* dst = reinterpret_cast<uint4*>(dYcol + ((int64_t)n * P + q0) * NP);
+  const int rows = min(32, P - q0);
+  for (int i = threadIdx.x; i < rows * vec_per_row; i += 256) dst[i] = src[i];
+}
+
+// Wp[j][ci] (bf16, j = t*n_cls + c, rows >= J zero) and WpT[ci][j] from the fp32 OIHW branch weights
+struct WeightPtrs {
+  const float* w[4];
+};
+__global__ void __launch_bounds__(256)
+aspp_pack_kernel(WeightPtrs wp, __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* __restrict__ WpT, int n_active,
+                 int n_cls, int Cin, int NP) {
+  const int64_t total = (int64_t)NP * Cin;
+  const int J = n_active * 9 * n_cls;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int ci = (int)(i % Cin), j = (int)(i / Cin);
+    float v = 0.f;
+    if (j < J) {
+      const int t = j / n_cls, c = j - t * n_cls;
+      const int b = t / 9, k = t - b * 9;
+      v = __ldg(wp.w[b] + ((int64_t)c * Cin + ci) * 9 + k);
+    }
+    const __nv_bfloat16 bv = __float2bfloat16(v);
+    if (Wp) Wp[i] = bv;
+    if (WpT) WpT[(int64_t)ci * NP + j] = bv;
+  }
+}
+
+// dw_b[c][ci][k] = sum_s part[s][ci][(b*9+k)*n_cls + c]
+struct GradPtrs {
+  float* w[4];
+};
+__global__ void __launch_bounds__(256)
+aspp_unpack_dw_kernel(const float* __restrict__ part, int S, GradPtrs gp, int n_active, int n_cls, int Cin,
+                      int NP) {
+  const int64_t per_branch = (int64_t)n_cls * Cin * 9;
+  const int64_t total = per_branch * n_active;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int b = (int)(i / per_branch);
+    const int64_t r = i - (int64_t)b * per_branch;
+    const int k = (int)(r % 9);
+    const int ci = (int)((r / 9) % Cin);
+    const int c = (int)(r / (9 * (int64_t)Cin));
+    const int j = (b * 9 + k) * n_cls + c;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += __ldg(part + ((int64_t)s * Cin + ci) * NP + j);
+    if (gp.w[b]) gp.w[b][r] = acc;
+  }
+}
+
+// column sums over pixels of an NCHW tensor: out[o] = sum_{n,p} src[n][o][p]
+__global__ void __launch_bounds__(256)
+nchw_channel_sum_kernel(const float* __restrict__ src, float* __restrict__ out, int N, int O, int P) {
+  __shared__ double part[8];
+  const int o = blockIdx.x;
+  double acc = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const float* s = src + ((int64_t)n * O + o) * P;
+    for (int i = threadIdx.x; i < P; i += 256) acc += (double)s[i];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? part[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[o] = (float)v;
+  }
+}
+
+// ---- host orchestration --------------------------------------------------------------------
+
+static int pick_block_n(int n) {
+  const int cand[3] = {128, 176, 256};
+  int best = 256;
+  int64_t best_pad = -1;
+  for (int i = 0; i < 3; ++i) {
+    int64_t pad = round_up(n, cand[i]);
+    if (best_pad < 0 || pad < best_pad || (pad == best_pad && cand[i] > best)) {
+      best = cand[i];
+      best_pad = pad;
+    }
+  }
+  return best;
+}
+
+static int make_taps(AsppTaps& t, const int* dil, int n_active, int W) {
+  (void)W;
+  t.n_taps = 9 * n_active;
+  for (int b = 0; b < n_active; ++b)
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        t.dh[b * 9 + kh * 3 + kw] = (kh - 1) * dil[b];
+        t.dw[b * 9 + kh * 3 + kw] = (kw - 1) * dil[b];
+      }
+  return ASN_OK;
+}
+
+struct AsppWs {
+  size_t x_nhwc, z, dycol, dycolt, x_ckp, dwpart, total;
+  int NP, S;
+  int64_t ldp;
+};
+
+static AsppWs aspp_ws(int N, int Cin, int H, int W, int n_cls, int n_active) {
+  AsppWs w;
+  const int64_t P = (int64_t)N * H * W;
+  w.NP = (int)round_up((int64_t)9 * n_active * n_cls, 16);
+  w.ldp = round_up(P, 8);
+  // split-K of the wgrad GEMM: aim at two CTAs per SM
+  const int bn = pick_block_n(w.NP);
+  const int tiles = cdiv(Cin, 128) * cdiv(w.NP, bn);
+  int S = (2 * sm_count() + tiles - 1) / tiles;
+  const int k_steps = cdiv(P, 64);
+  if (S > k_steps / 4) S = k_steps / 4;
+  if (S < 1) S = 1;
+  w.S = umma::effective_split((int)P, S);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  };
+  w.x_nhwc = take((size_t)P * Cin * 2);
+  w.z = take((size_t)P * w.NP * 4);
+  w.dycol = take((size_t)P * w.NP * 2);
+  w.dycolt = take((size_t)w.NP * w.ldp * 2);
+  w.x_ckp = take((size_t)Cin * w.ldp * 2);
+  w.dwpart = take((size_t)w.S * Cin * w.NP * 4);
+  w.total = off;
+  return w;
+}
+
+}  // namespace asn
+
+using namespace asn;
+
+extern "C" int asn_aspp_np(int n_cls, int n_active) { return (int)round_up((int64_t)9 * n_active * n_cls, 16); }
+
+extern "C" int asn_aspp_pack_weights(const float* const* w_oihw, int n_active, int n_cls, int Cin, void* wp_bf16,
+                                     void* wpt_bf16, void* stream) {
+  ASN_CHECK_ARG(w_oihw && n_active >= 1 && n_active <= 4 && n_cls >= 1 && n_cls <= 32 && Cin >= 1,
+                "asn_aspp_pack_weights: bad argument");
+  WeightPtrs wp{};
+  for (int b = 0; b < n_active; ++b) {
+    ASN_CHECK_ARG(w_oihw[b], "asn_aspp_pack_weights: null branch weight %d", b);
+    wp.w[b] = w_oihw[b];
+  }
+  const int NP = asn_aspp_np(n_cls, n_active);
+  aspp_pack_kernel<<<wave_grid((int64_t)NP * Cin, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      wp, static_cast<__nv_bfloat16*>(wp_bf16), static_cast<__nv_bfloat16*>(wpt_bf16), n_active, n_cls, Cin, NP);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+extern "C" size_t asn_aspp_workspace_bytes(int N, int Cin, int H, int W, int n_cls, int n_active) {
+  return aspp_ws(N, Cin, H, W, n_cls, n_active).total;
+}
+
+static int aspp_check(int N, int Cin, int H, int W, int n_cls, int n_active, const int* dil) {
+  ASN_CHECK_ARG(N > 0 && H > 0 && W > 0, "aspp: bad shape");
+  ASN_CHECK_ARG(Cin % 8 == 0 && Cin >= 64, "aspp: Cin=%d must be a multiple of 8 and >= 64", Cin);
+  ASN_CHECK_ARG(n_cls >= 1 && n_cls <= 32, "aspp: n_cls=%d outside [1,32]", n_cls);
+  ASN_CHECK_ARG(n_active >= 1 && n_active <= 4 && dil, "aspp: n_active=%d outside [1,4]", n_active);
+  ASN_CHECK_ARG((int64_t)N * H * W < (1LL << 30), "aspp: too many pixels");
+  return ASN_OK;
+}
+
+extern "C" int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const float* bias_sum, float* y_nchw, int N,
+                            int Cin, int H, int W, int n_cls, const int* dil_host, int n_active, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  ASN_CHECK_ARG(x_nchw && wp_bf16 && bias_sum && y_nchw && workspace, "asn_aspp_fwd: null pointer");
+  int rc = aspp_check(N, Cin, H, W, n_cls, n_active, dil_host);
+  if (rc) return rc;
+  const AsppWs ws = aspp_ws(N, Cin, H, W, n_cls, n_active);
+  if (workspace_bytes < ws.total) {
+    set_error("asn_aspp_fwd: workspace %zu < %zu", workspace_bytes, ws.total);
+    return ASN_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(base + ws.x_nhwc);
+  float* Z = reinterpret_cast<float*>(base + ws.z);
+  const int P = H * W;
+  nchw_to_nhwc_bf16_kernel<<<dim3(cdiv(P, 64), cdiv(Cin, 64), N), 256, 0, st>>>(x_nchw, xn, Cin, P);
+  ASN_LAUNCH_CHECK();
+  rc = umma::gemm_tn(xn, wp_bf16, Z, N * P, ws.NP, Cin, Cin, Cin, ws.NP, 1, 0, pick_block_n(ws.NP), st);
+  if (rc) return rc;
+  AsppTaps taps;
+  make_taps(taps, dil_host, n_active, W);
+  const int groups = N * cdiv(P, 32);
+  aspp_gather_kernel<32><<<cdiv(groups, 8), 256, 0, st>>>(Z, bias_sum, y_nchw, N, H, W, n_cls, ws.NP, taps);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+extern "C" int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const float* dy_nchw, float* dx_nchw,
+                            float* const* dw_oihw, float* db, int N, int Cin, int H, int W, int n_cls,
+                            const int* dil_host, int n_active, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  ASN_CHECK_ARG(dy_nchw && workspace, "asn_aspp_bwd: null pointer");
+  ASN_CHECK_ARG(!dx_nchw || wpt_bf16, "asn_aspp_bwd: dx needs the transposed weight pack");
+  ASN_CHECK_ARG(!dw_oihw || x_nchw, "asn_aspp_bwd: dw needs x");
+  int rc = aspp_check(N, Cin, H, W, n_cls, n_active, dil_host);
+  if (rc) return rc;
+  const AsppWs ws = aspp_ws(N, Cin, H, W, n_cls, n_active);
+  if (workspace_bytes < ws.total) {
+    set_error("asn_aspp_bwd: workspace %zu < %zu", workspace_bytes, ws.total);
+    return ASN_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  __nv_bfloat16* dycol = reinterpret_cast<__nv_bfloat16*>(base + ws.dycol);
+  __nv_bfloat16* dycolt = reinterpret_cast<__nv_bfloat16*>(base + ws.dycolt);
+  const int P = H * W;
+  AsppTaps taps;
+  make_taps(taps, dil_host, n_active, W);
+  if (dx_nchw || dw_oihw) {
+    // padding columns [N*P, ldp) of dYcolT / Xckp are never read: the tensor maps end at N*P
+    const size_t smem = (size_t)32 * ws.NP * 2;
+    if (smem > 48 * 1024)
+      ASN_CUDA(cudaFuncSetAttribute(aspp_dycols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aspp_dycols_kernel<<<N * cdiv(P, 32), 256, smem, st>>>(dy_nchw, dycol, dycolt, N, H, W, n_cls, ws.NP, ws.ldp, taps);
+    ASN_LAUNCH_CHECK();
+  }
+  if (dx_nchw) {
+    for (int n = 0; n < N; ++n) {
+      rc = umma::gemm_tn(wpt_bf16, dycol + (int64_t)n * P * ws.NP, dx_nchw + (int64_t)n * Cin * P, Cin, P, ws.NP,
+                         ws.NP, ws.NP, P, 1, 0, 256, st);
+      if (rc) return rc;
+    }
+  }
+  if (dw_oihw) {
+    __nv_bfloat16* xk = reinterpret_cast<__nv_bfloat16*>(base + ws.x_ckp);
+    float* part = reinterpret_cast<float*>(base + ws.dwpart);
+    nchw_to_ckp_bf16_kernel<<<wave_grid((int64_t)N * Cin * P, 256, 8), 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
+    ASN_LAUNCH_CHECK();
+    rc = umma::gemm_tn(xk, dycolt, part, Cin, ws.NP, N * P, (int)ws.ldp, (int)ws.ldp, ws.NP, ws.S,
+                       (long long)Cin * ws.NP, pick_block_n(ws.NP), st);
+    if (rc) return rc;
+    GradPtrs gp{};
+    for (int b = 0; b < n_active; ++b) gp.w[b] = dw_oihw[b];
+    aspp_unpack_dw_kernel<<<wave_grid((int64_t)n_active * n_cls * Cin * 9, 256, 8), 256, 0, st>>>(
+        part, ws.S, gp, n_active, n_cls, Cin, ws.NP);
+    ASN_LAUNCH_CHECK();
+  }
+  if (db) {
+    nchw_channel_sum_kernel<<<n_cls, 256, 0, st>>>(dy_nchw, db, N, n_cls, P);
+    ASN_LAUNCH_CHECK();
+  }
+  return ASN_OK;
+}

@@ -1,0 +1,102 @@
+// Shared helpers for libasn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/asn_b200.h"
+
+namespace asn {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+#define ASN_CHECK_ARG(cond, ...)              \
+  do {                                        \
+    if (!(cond)) {                            \
+      asn::set_error(__VA_ARGS__);            \
+      return ASN_EINVAL;                      \
+    }                                         \
+  } while (0)
+
+#define ASN_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      asn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return ASN_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define ASN_LAUNCH_CHECK() ASN_CUDA(cudaGetLastError())
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// grid for a grid-stride kernel: whole waves of `ctas_per_sm` CTAs on every SM
+static inline int wave_grid(int64_t work_items, int threads, int ctas_per_sm) {
+  int64_t need = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit accesses (read-once / write-once tensors)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// bilinear source coordinate, align_corners=True, exactly the float ops ATen performs:
+// scale = (float)(in-1)/(out-1) (0 when out == 1); r = scale*dst; i0 = (int)r; lam = r - i0.
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__host__ __device__ __forceinline__ float lerp_scale(int n_in, int n_out) {
+  return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+}
+__device__ __forceinline__ Lerp lerp_at(int dst, float scale, int n_in) {
+  Lerp L;
+  float r = __fmul_rn(scale, (float)dst);  // no FMA contraction: lam must equal the oracle's
+  L.i0 = min((int)r, n_in - 1);
+  L.i1 = L.i0 + (L.i0 < n_in - 1 ? 1 : 0);
+  L.l1 = __fsub_rn(r, (float)L.i0);
+  L.l0 = __fsub_rn(1.f, L.l1);
+  return L;
+}
+
+}  // namespace asn

@@ -1,0 +1,172 @@
+// K7: 19x19 confusion matrix (compute_iou.py:15-17) -- HBM-bound integer kernel.
+//
+// Layout: label (u8 | i32 | i64) and pred (u8) are flat arrays of n_px pixels.
+// Each thread streams 16 consecutive pixels per iteration with 128-bit loads
+// (1 load of pred, 1/4/8 loads of labels), run-length-aggregates equal (a,b)
+// pairs in registers (labels are blocky, so most shared-memory atomics vanish),
+// and adds into a warp-private shared-memory histogram.  One 64-bit global
+// atomic per non-zero bin per CTA at the end.  Algorithmic bytes: 2 B/px (u8
+// labels) or 9 B/px (i64 labels, as the reference holds them).
+#include "common.cuh"
+
+namespace asn {
+
+constexpr int HIST_THREADS = 256;
+constexpr int HIST_WARPS = HIST_THREADS / 32;
+
+template <typename T>
+struct LabelLoad;  // loads 16 consecutive labels as int (-1 = invalid for any out-of-range)
+
+template <>
+struct LabelLoad<uint8_t> {
+  static __device__ __forceinline__ void load16(const uint8_t* p, int n, int* a) {
+    uint4 v = ld_stream(reinterpret_cast<const uint4*>(p));
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int x = (w[i >> 2] >> ((i & 3) * 8)) & 0xff;
+      a[i] = x < n ? x : -1;
+    }
+  }
+  static __device__ __forceinline__ int load1(const uint8_t* p, int n) {
+    int x = *p;
+    return x < n ? x : -1;
+  }
+};
+template <>
+struct LabelLoad<int32_t> {
+  static __device__ __forceinline__ void load16(const int32_t* p, int n, int* a) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[j * 4 + i] = w[i] < (uint32_t)n ? (int)w[i] : -1;
+    }
+  }
+  static __device__ __forceinline__ int load1(const int32_t* p, int n) {
+    uint32_t x = (uint32_t)*p;
+    return x < (uint32_t)n ? (int)x : -1;
+  }
+};
+template <>
+struct LabelLoad<int64_t> {
+  static __device__ __forceinline__ void load16(const int64_t* p, int n, int* a) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
+      // little endian: (x,y) = first int64, (z,w) = second; valid iff high word 0 and low < n
+      a[j * 2 + 0] = (v.y == 0u && v.x < (uint32_t)n) ? (int)v.x : -1;
+      a[j * 2 + 1] = (v.w == 0u && v.z < (uint32_t)n) ? (int)v.z : -1;
+    }
+  }
+  static __device__ __forceinline__ int load1(const int64_t* p, int n) {
+    unsigned long long x = (unsigned long long)*p;
+    return x < (unsigned long long)n ? (int)x : -1;
+  }
+};
+
+struct RunAgg {
+  int cur;
+  uint32_t cnt;
+  uint32_t ovf;
+  __device__ __forceinline__ void push(int idx, uint32_t* h, int nbins) {
+    if (idx == cur) {
+      ++cnt;
+    } else {
+      flush(h, nbins);
+      cur = idx;
+      cnt = 1;
+    }
+  }
+  __device__ __forceinline__ void flush(uint32_t* h, int nbins) {
+    if (cur >= 0 && cnt) {
+      if (cur < nbins)
+        atomicAdd(&h[cur], cnt);
+      else
+        ovf += cnt;
+    }
+    cnt = 0;
+  }
+};
+
+template <typename LabelT>
+__global__ void __launch_bounds__(HIST_THREADS)
+fast_hist_kernel(const LabelT* __restrict__ label, const uint8_t* __restrict__ pred, int64_t n_px,
+                 int n_cls, int n_sub, unsigned long long* __restrict__ hist,
+                 unsigned long long* __restrict__ overflow, int vec_ok) {
+  extern __shared__ uint32_t sh[];
+  const int nbins = n_cls * n_cls;
+  for (int i = threadIdx.x; i < nbins * n_sub; i += HIST_THREADS) sh[i] = 0;
+  __syncthreads();
+  uint32_t* myh = sh + ((threadIdx.x >> 5) % n_sub) * nbins;
+
+  RunAgg agg{-1, 0, 0};
+  const int64_t tid = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * HIST_THREADS;
+  int64_t n_vec = vec_ok ? (n_px >> 4) : 0;  // chunks of 16 pixels
+  for (int64_t c = tid; c < n_vec; c += nthreads) {
+    int a[16];
+    LabelLoad<LabelT>::load16(label + c * 16, n_cls, a);
+    uint4 pv = ld_stream(reinterpret_cast<const uint4*>(pred + c * 16));
+    uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int b = (pw[i >> 2] >> ((i & 3) * 8)) & 0xff;
+      int idx = a[i] >= 0 ? a[i] * n_cls + b : -1;
+      agg.push(idx, myh, nbins);
+    }
+  }
+  for (int64_t i = n_vec * 16 + tid; i < n_px; i += nthreads) {
+    int a = LabelLoad<LabelT>::load1(label + i, n_cls);
+    int idx = a >= 0 ? a * n_cls + (int)pred[i] : -1;
+    agg.push(idx, myh, nbins);
+  }
+  agg.flush(myh, nbins);
+  if (agg.ovf) atomicAdd(overflow, (unsigned long long)agg.ovf);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += HIST_THREADS) {
+    unsigned long long s = 0;
+    for (int k = 0; k < n_sub; ++k) s += sh[k * nbins + i];
+    if (s) atomicAdd(&hist[i], s);
+  }
+}
+
+template <typename LabelT>
+static int launch_hist(const void* label, const uint8_t* pred, int64_t n_px, int n_cls,
+                       int64_t* hist, int64_t* overflow, cudaStream_t st) {
+  const int nbins = n_cls * n_cls;
+  int n_sub = (48 * 1024) / (nbins * 4);
+  if (n_sub > HIST_WARPS) n_sub = HIST_WARPS;
+  ASN_CHECK_ARG(n_sub >= 1, "asn_fast_hist: n_cls=%d too large for the shared-memory histogram", n_cls);
+  int vec_ok = ((reinterpret_cast<uintptr_t>(label) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0;
+  // 16 px per thread-iteration; at least 4 iterations per thread before adding CTAs
+  int grid = wave_grid((n_px + 63) / 64, HIST_THREADS, 8);
+  // 32-bit shared counters: keep every CTA below 2^31 pixels
+  while ((n_px + grid - 1) / grid > (int64_t)1 << 31) grid *= 2;
+  fast_hist_kernel<LabelT><<<grid, HIST_THREADS, (size_t)n_sub * nbins * 4, st>>>(
+      static_cast<const LabelT*>(label), pred, n_px, n_cls, n_sub,
+      reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(overflow),
+      vec_ok);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+}  // namespace asn
+
+extern "C" int asn_fast_hist(const void* label, int label_dtype, const uint8_t* pred, int64_t n_px,
+                             int n_cls, int64_t* hist, int64_t* overflow, void* stream) {
+  using namespace asn;
+  ASN_CHECK_ARG(n_px >= 0 && n_cls >= 1 && n_cls <= 255, "asn_fast_hist: bad n_px/n_cls");
+  ASN_CHECK_ARG(hist && overflow, "asn_fast_hist: null output");
+  if (n_px == 0) return ASN_OK;
+  ASN_CHECK_ARG(label && pred, "asn_fast_hist: null input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (label_dtype) {
+    case ASN_LABEL_U8: return launch_hist<uint8_t>(label, pred, n_px, n_cls, hist, overflow, st);
+    case ASN_LABEL_I32: return launch_hist<int32_t>(label, pred, n_px, n_cls, hist, overflow, st);
+    case ASN_LABEL_I64: return launch_hist<int64_t>(label, pred, n_px, n_cls, hist, overflow, st);
+  }
+  set_error("asn_fast_hist: unknown label_dtype %d", label_dtype);
+  return ASN_EINVAL;
+}

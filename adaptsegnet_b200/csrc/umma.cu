@@ -1,0 +1,179 @@
+// Host side of the tcgen05 implicit-GEMM kernel: tensor-map encoding (driver entry point fetched
+// through the runtime, so libcuda is not a link-time dependency), template dispatch, and the raw
+// GEMM entry point asn_gemm_bf16_tn.
+#include "umma_host.cuh"
+
+namespace asn {
+namespace umma {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                  const uint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return ASN_ECUDA;
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) {
+    set_error("tensor map base %p is not 16-byte aligned", base);
+    return ASN_EINVAL;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) {
+      set_error("tensor map box[%d]=%u out of range", i, box[i]);
+      return ASN_EINVAL;
+    }
+  }
+  for (int i = 0; i < rank - 1; ++i) {
+    gstr[i] = strides[i];
+    if (strides[i] & 15) {
+      set_error("tensor map stride[%d]=%llu is not a multiple of 16 bytes", i, (unsigned long long)strides[i]);
+      return ASN_EINVAL;
+    }
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return ASN_ECUDA;
+  }
+  return ASN_OK;
+}
+
+int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+              uint32_t box_rows) {
+  uint64_t dims[2] = {inner, rows};
+  uint64_t strides[1] = {row_stride_bytes};
+  uint32_t box[2] = {64, box_rows};
+  return encode(m, base, 2, dims, strides, box);
+}
+
+int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+              uint32_t box1, uint32_t box2) {
+  uint32_t box[4] = {64, box1, box2, 1};
+  return encode(m, base, 4, dims, strides_bytes, box);
+}
+
+// stage counts: keep every CTA <= ~112 KB so that two are co-resident per SM
+template <int BLOCK_N>
+struct Stages {
+  static constexpr int stage = 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
+  static constexpr int fit = (112 * 1024 - 1280) / stage;
+  static constexpr int value = fit > 6 ? 6 : (fit < 2 ? 2 : fit);
+};
+
+template <int MODE, int BLOCK_N>
+static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = Stages<BLOCK_N>::value;
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  auto kern = umma_kernel<MODE, BLOCK_N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], P);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+bool block_n_supported(int mode, int block_n) {
+  switch (mode) {
+    case MODE_GEMM: return block_n == 128 || block_n == 176 || block_n == 256;
+    case MODE_CONV: return block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256;
+    case MODE_WGRAD: return block_n == 64 || block_n == 128 || block_n == 256;
+  }
+  return false;
+}
+
+int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st) {
+#define ASN_CASE(MODE, BN) \
+  if (mode == MODE && block_n == BN) return launch_t<MODE, BN>(maps, P, grid, st);
+  ASN_CASE(MODE_GEMM, 128)
+  ASN_CASE(MODE_GEMM, 176)
+  ASN_CASE(MODE_GEMM, 256)
+  ASN_CASE(MODE_CONV, 32)
+  ASN_CASE(MODE_CONV, 64)
+  ASN_CASE(MODE_CONV, 128)
+  ASN_CASE(MODE_CONV, 256)
+  ASN_CASE(MODE_WGRAD, 64)
+  ASN_CASE(MODE_WGRAD, 128)
+  ASN_CASE(MODE_WGRAD, 256)
+#undef ASN_CASE
+  set_error("umma::launch: no kernel for mode %d block_n %d", mode, block_n);
+  return ASN_EUNSUPPORTED;
+}
+
+// plain GEMM: C[M,N] = A[M,K] . B[N,K]^T  (+ split-K partials)
+int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, long long ldc,
+            int split_k, long long split_stride, int block_n, cudaStream_t st) {
+  ASN_CHECK_ARG(A && B && C, "gemm_tn: null pointer");
+  ASN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tn: bad shape %d %d %d", M, N, K);
+  ASN_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "gemm_tn: lda/ldb must be >= K and multiples of 8");
+  ASN_CHECK_ARG(block_n_supported(MODE_GEMM, block_n), "gemm_tn: unsupported block_n %d", block_n);
+  CUtensorMap maps[5];
+  int rc = encode_2d(&maps[0], A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BLOCK_M);
+  if (rc) return rc;
+  rc = encode_2d(&maps[4], B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)block_n);
+  if (rc) return rc;
+  maps[1] = maps[2] = maps[3] = maps[0];
+  Params P;
+  memset(&P, 0, sizeof(P));
+  P.M = M;
+  P.N = N;
+  P.k_steps = cdiv(K, BLOCK_K);
+  if (split_k < 1) split_k = 1;
+  if (split_k > P.k_steps) split_k = P.k_steps;
+  P.steps_per_split = cdiv(P.k_steps, split_k);
+  split_k = cdiv(P.k_steps, P.steps_per_split);
+  P.epi = EPI_F32;
+  P.out = C;
+  P.ld_out = ldc;
+  P.z_stride_out = split_stride;
+  P.slope = 1.f;
+  dim3 grid(cdiv(M, BLOCK_M), cdiv(N, block_n), split_k);
+  return launch(MODE_GEMM, block_n, maps, P, grid, st);
+}
+
+int effective_split(int K, int split_k) {
+  int k_steps = cdiv(K, BLOCK_K);
+  if (split_k < 1) split_k = 1;
+  if (split_k > k_steps) split_k = k_steps;
+  int sps = cdiv(k_steps, split_k);
+  return cdiv(k_steps, sps);
+}
+
+}  // namespace umma
+}  // namespace asn
+
+extern "C" int asn_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb,
+                                int ldc, int split_k, void* stream) {
+  using namespace asn;
+  int bn = N > 128 ? 256 : 128;
+  return umma::gemm_tn(A, B, C, M, N, K, lda, ldb, ldc, split_k, (long long)M * ldc, bn,
+                       static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,431 @@
+// tcgen05 / TMEM / TMA primitives and the one warp-specialised implicit-GEMM kernel every
+// tensor-core path of this library runs on (sm_100a only).
+//
+//   D[128 x BLOCK_N] (fp32, TMEM) += A[128 x 64] (bf16, smem) . B[BLOCK_N x 64]^T (bf16, smem)
+//
+// per k-step; A/B stages are filled by TMA (SWIZZLE_128B boxes whose inner extent is 64 bf16 =
+// 128 bytes), consumed by tcgen05.mma issued from one thread, released by tcgen05.commit.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  One output tile per CTA; two
+// CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
+// epilogue overlaps the other's main loop.
+//
+// Three operand-fetch programs share the skeleton:
+//   GEMM  : A and B are plain row-major [rows][K] matrices (K-major operands).
+//   CONV  : A rows are the pixels of a th x tw output box; k-steps walk (tap, 64-channel
+//           chunk); each step is ONE 4-D TMA box over an NHWC tensor (or a stride-2 parity
+//           view of it) at a tap-dependent offset; out-of-range pixels are zero-filled by
+//           TMA, which is the convolution's zero padding.  B = packed weights (K-major).
+//   WGRAD : the reduction runs over pixels, so both operands arrive "MN-major": each stage
+//           holds 64 pixels x {128 | BLOCK_N} channels as 64-channel TMA boxes.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace asn {
+namespace umma {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_holder), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulate
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued tcgen05 ops of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns: thread t receives lane (base_lane + t), columns c..c+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// descriptors (cute/arch/mma_sm100_desc.hpp bit layout)
+// ------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor for kind::f16: D fp32, A/B bf16, dense, no negate
+//   [4,6) c_format=1(F32) | [7,10) a_format=1(BF16) | [10,13) b_format=1 | 15 a_major | 16 b_major
+//   [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------
+enum { MODE_GEMM = 0, MODE_CONV = 1, MODE_WGRAD = 2 };
+enum {
+  EPI_F32 = 0,   // fp32 store
+  EPI_BF16 = 1   // (+bias) (LeakyReLU) (x LeakyReLU mask of `mask_src`) -> bf16 store
+};
+
+constexpr int MAX_TAPS = 16;
+constexpr int MAX_Z = 4;
+
+struct Params {
+  // ---- problem extents ----
+  int M, N;             // GEMM: logical rows / cols of the output (store masks)
+  int k_steps;          // total number of 64-wide k-steps
+  int steps_per_split;  // k-steps per blockIdx.z slice (GEMM / WGRAD split-K)
+  // ---- CONV / WGRAD pixel tiling (th*tw = 128 for CONV, 64 for WGRAD) ----
+  int tw, th, tiles_w, tiles_h;  // box and number of boxes per image
+  int c_chunks;                  // CONV: 64-channel chunks per tap (k_steps = taps*c_chunks)
+  int taps;                      // CONV: taps per z; WGRAD: total taps (blockIdx.y)
+  int tap_map[MAX_Z * MAX_TAPS]; // which A (CONV) / B (WGRAD) tensor map a tap reads
+  int tap_dh[MAX_Z * MAX_TAPS];  // box origin offset (rows) of the tap
+  int tap_dw[MAX_Z * MAX_TAPS];  // box origin offset (cols) of the tap
+  int b_rows_per_z;              // CONV: row offset of B per blockIdx.z (dgrad parity classes)
+  int a_boxes;                   // WGRAD: 64-channel boxes of A actually loaded (1 or 2)
+  // ---- epilogue ----
+  int epi;
+  void* out;                     // fp32 or bf16
+  long long ld_out;              // elements between consecutive rows (pixels)
+  long long z_stride_out;        // GEMM / WGRAD: elements between split-K partials
+  long long tap_stride_out;      // WGRAD: elements between per-tap blocks
+  int oh_ext[MAX_Z], ow_ext[MAX_Z];  // CONV: valid output extent (tile space) per z
+  int out_h, out_w;                  // CONV: full output grid
+  int sy, sx;                        // CONV: output row/col stride (dgrad: 2)
+  int oy[MAX_Z], ox[MAX_Z];          // CONV: output row/col offset per z (dgrad parity)
+  const float* bias;                 // nullable, fp32 [N]
+  float slope;                       // LeakyReLU slope applied to the result (1 = none)
+  const __nv_bfloat16* mask_src;     // nullable: multiply by (mask_src[off] > 0 ? 1 : mask_slope)
+  float mask_slope;
+};
+
+template <int BLOCK_N>
+struct TmemCols {
+  static constexpr int value = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+};
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements per k-step = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int MODE, int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+            const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+            const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  constexpr int TMEM_COLS = TmemCols<BLOCK_N>::value;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_holder = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_holder_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates ----
+  const int z = blockIdx.z;
+  int n0, m0 = 0, img = 0, oh0 = 0, ow0 = 0, wg_tap = 0;
+  int ks_begin = 0, ks_end = P.k_steps;
+  if (MODE == MODE_GEMM) {
+    m0 = blockIdx.x * BLOCK_M;
+    n0 = blockIdx.y * BLOCK_N;
+    ks_begin = z * P.steps_per_split;
+    ks_end = min(P.k_steps, ks_begin + P.steps_per_split);
+  } else if (MODE == MODE_CONV) {
+    int t = blockIdx.x;
+    ow0 = (t % P.tiles_w) * P.tw;
+    oh0 = ((t / P.tiles_w) % P.tiles_h) * P.th;
+    img = t / (P.tiles_w * P.tiles_h);
+    n0 = blockIdx.y * BLOCK_N;
+  } else {
+    // blockIdx.x = m_tile + m_tiles * n_tile  (m_tiles = ceil(M/128)), blockIdx.y = tap
+    const int m_tiles = (P.M + BLOCK_M - 1) / BLOCK_M;
+    m0 = (blockIdx.x % m_tiles) * BLOCK_M;
+    n0 = (blockIdx.x / m_tiles) * BLOCK_N;
+    wg_tap = blockIdx.y;
+    ks_begin = z * P.steps_per_split;
+    ks_end = min(P.k_steps, ks_begin + P.steps_per_split);
+  }
+  const int nsteps = ks_end - ks_begin;
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a0);
+    prefetch_tmap(&map_b);
+    if (MODE != MODE_GEMM) {
+      prefetch_tmap(&map_a1);
+      prefetch_tmap(&map_a2);
+      prefetch_tmap(&map_a3);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_holder_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const CUtensorMap* amaps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
+      for (int i = 0; i < nsteps; ++i) {
+        const int ks = ks_begin + i;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+        const uint32_t sb = sa + L::A_BYTES;
+        if (MODE == MODE_GEMM) {
+          mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
+          tma_load_2d(&map_a0, sa, full_bar(s), ks * BLOCK_K, m0);
+          tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, n0);
+        } else if (MODE == MODE_CONV) {
+          const int tap = ks / P.c_chunks, cc = ks - tap * P.c_chunks;
+          const int e = z * P.taps + tap;
+          mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
+          tma_load_4d(amaps[P.tap_map[e]], sa, full_bar(s), cc * BLOCK_K, ow0 + P.tap_dw[e], oh0 + P.tap_dh[e], img);
+          tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, z * P.b_rows_per_z + n0);
+        } else {
+          // k-step = one box of 64 pixels: A = dY channels [m0, m0+128), B = X@tap channels [n0, n0+BLOCK_N)
+          const int bx = ks % P.tiles_w, by = (ks / P.tiles_w) % P.tiles_h, im = ks / (P.tiles_w * P.tiles_h);
+          const uint32_t box_bytes = 64 * 64 * 2;
+          mbar_arrive_expect_tx(full_bar(s), (P.a_boxes + BLOCK_N / 64) * box_bytes);
+          for (int a = 0; a < P.a_boxes; ++a)
+            tma_load_4d(&map_a0, sa + a * box_bytes, full_bar(s), m0 + a * 64, bx * P.tw, by * P.th, im);
+          const CUtensorMap* bm = P.tap_map[wg_tap] == 0 ? &map_b
+                                  : P.tap_map[wg_tap] == 1 ? &map_a1
+                                  : P.tap_map[wg_tap] == 2 ? &map_a2 : &map_a3;
+#pragma unroll
+          for (int b = 0; b < BLOCK_N / 64; ++b)
+            tma_load_4d(bm, sb + b * box_bytes, full_bar(s), n0 + b * 64, bx * P.tw + P.tap_dw[wg_tap],
+                        by * P.th + P.tap_dh[wg_tap], im);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = MODE == MODE_WGRAD ? make_idesc(BLOCK_M, BLOCK_N, 1, 1)
+                                                    : make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+      for (int i = 0; i < nsteps; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+        const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          uint64_t da, db;
+          if (MODE == MODE_WGRAD) {
+            // MN-major, SW128: 64-channel chunks LBO = 64 px * 128 B apart, 8-pixel groups SBO = 1 KB apart;
+            // advancing K by 16 pixels = 2 KB
+            da = make_smem_desc(sa + k * 2048, 8192, 1024);
+            db = make_smem_desc(sb + k * 2048, 8192, 1024);
+          } else {
+            // K-major, SW128: 8-row groups SBO = 1 KB apart; advancing K by 16 elements = 32 B inside the row
+            da = make_smem_desc(sa + k * 32, 16, 1024);
+            db = make_smem_desc(sb + k * 32, 16, 1024);
+          }
+          mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+      }
+      mma_commit(tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;        // accumulator row owned by this thread
+    if (nsteps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    bool row_ok;
+    long long row_off;
+    if (MODE == MODE_GEMM) {
+      row_ok = (m0 + r) < P.M;
+      row_off = (long long)z * P.z_stride_out + (long long)(m0 + r) * P.ld_out;
+    } else if (MODE == MODE_CONV) {
+      const int dy = r / P.tw, dx = r - dy * P.tw;
+      const int oh = oh0 + dy, ow = ow0 + dx;
+      row_ok = oh < P.oh_ext[z] && ow < P.ow_ext[z];
+      const int fh = oh * P.sy + P.oy[z], fw = ow * P.sx + P.ox[z];
+      row_off = (((long long)img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
+    } else {
+      row_ok = (m0 + r) < P.M;
+      row_off = (long long)z * P.z_stride_out + (long long)wg_tap * P.tap_stride_out +
+                (long long)(m0 + r) * P.ld_out;
+    }
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      float v[16];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
+      if (nsteps > 0) {
+        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      const int n = n0 + c;
+      if (!row_ok || n >= P.N) continue;
+      if (P.epi == EPI_F32) {
+        float* dst = reinterpret_cast<float*>(P.out) + row_off + n;
+        if (n + 16 <= P.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = v[i];
+        }
+      } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + row_off + n;
+        const bool full = n + 16 <= P.N;
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += (full || n + i < P.N) ? __ldg(P.bias + n + i) : 0.f;
+        }
+        if (P.slope != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * P.slope;
+        }
+        if (P.mask_src) {
+          const __nv_bfloat16* ms = P.mask_src + row_off + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (full || n + i < P.N) v[i] *= (__bfloat162float(ms[i]) > 0.f ? 1.f : P.mask_slope);
+        }
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+          for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = __float2bfloat16(v[i]);
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_d, TMEM_COLS);
+  }
+}
+
+}  // namespace umma
+}  // namespace asn

@@ -1,0 +1,211 @@
+// K2 / K2b / K9: bilinear resize with align_corners=True (model/deeplab_multi.py:188-189,
+// evaluate_cityscapes.py:153,163,168-169).  HBM-bound: the forward is a pure 16-byte
+// streaming write of the full-resolution tensor (the low-res source stays in L1/L2), the
+// backward a pure streaming read.  Float op order follows ATen's upsample_bilinear2d so
+// that the fused argmax resolves near-ties like the reference.
+#include "common.cuh"
+
+namespace asn {
+
+constexpr int UP_THREADS = 256;
+
+// one thread = VEC consecutive output columns of one output row
+template <int VEC>
+__global__ void __launch_bounds__(UP_THREADS)
+upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int h, int w, int H,
+                    int W, float sh, float sw) {
+  const int wv = (W + VEC - 1) / VEC;
+  const int64_t total = (int64_t)NC * H * wv;
+  for (int64_t i = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * UP_THREADS) {
+    int xv = (int)(i % wv);
+    int64_t row = i / wv;
+    int Y = (int)(row % H);
+    int nc = (int)(row / H);
+    Lerp ly = lerp_at(Y, sh, h);
+    const float* r0 = x + ((int64_t)nc * h + ly.i0) * w;
+    const float* r1 = x + ((int64_t)nc * h + ly.i1) * w;
+    float out[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      int X = xv * VEC + k;
+      Lerp lx = lerp_at(min(X, W - 1), sw, w);
+      out[k] = ly.l0 * (lx.l0 * __ldg(r0 + lx.i0) + lx.l1 * __ldg(r0 + lx.i1)) +
+               ly.l1 * (lx.l0 * __ldg(r1 + lx.i0) + lx.l1 * __ldg(r1 + lx.i1));
+    }
+    float* dst = y + row * W + (int64_t)xv * VEC;
+    if (VEC == 4) {
+      st_stream(reinterpret_cast<float4*>(dst), make_float4(out[0], out[1], out[2], out[3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (xv * VEC + k < W) dst[k] = out[k];
+    }
+  }
+}
+
+// backward pass 1: collapse the width.  One CTA per full-res row (nc, Y): the row is staged
+// in shared memory with coalesced 16-byte loads, then thread j sums the (<= ~2/scale) columns
+// whose x0 or x1 is j.  T[nc, Y, j] (N*C*H*w floats) is the workspace.
+__global__ void __launch_bounds__(UP_THREADS)
+upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int w, int W, float sw,
+                      int vec_ok) {
+  extern __shared__ float row[];
+  const int64_t r = blockIdx.x;
+  const float* src = dy + r * W;
+  if (vec_ok) {
+    for (int i = threadIdx.x; i < W / 4; i += UP_THREADS)
+      reinterpret_cast<float4*>(row)[i] = ld_stream(reinterpret_cast<const float4*>(src) + i);
+  } else {
+    for (int i = threadIdx.x; i < W; i += UP_THREADS) row[i] = src[i];
+  }
+  __syncthreads();
+  const float inv = sw > 0.f ? 1.f / sw : 0.f;
+  for (int j = threadIdx.x; j < w; j += UP_THREADS) {
+    // candidate columns: source coordinate in (j-1, j+1); widen by 2 and re-test exactly
+    int lo = sw > 0.f ? max(0, (int)floorf((float)(j - 1) * inv) - 2) : 0;
+    int hi = sw > 0.f ? min(W - 1, (int)ceilf((float)(j + 1) * inv) + 2) : W - 1;
+    float acc = 0.f;
+    for (int X = lo; X <= hi; ++X) {
+      Lerp lx = lerp_at(X, sw, w);
+      float v = row[X];
+      if (lx.i0 == j) acc += lx.l0 * v;
+      if (lx.i1 == j) acc += lx.l1 * v;
+    }
+    T[r * w + j] = acc;
+  }
+}
+
+// backward pass 2: collapse the height.  thread = (nc, i, j), j fastest -> coalesced reads of T.
+__global__ void __launch_bounds__(UP_THREADS)
+upsample_bwd_h_kernel(const float* __restrict__ T, float* __restrict__ dx, int NC, int h, int w, int H,
+                      float sh) {
+  const int64_t total = (int64_t)NC * h * w;
+  const float inv = sh > 0.f ? 1.f / sh : 0.f;
+  for (int64_t idx = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * UP_THREADS) {
+    int j = (int)(idx % w);
+    int i = (int)((idx / w) % h);
+    int nc = (int)(idx / ((int64_t)w * h));
+    int lo = sh > 0.f ? max(0, (int)floorf((float)(i - 1) * inv) - 2) : 0;
+    int hi = sh > 0.f ? min(H - 1, (int)ceilf((float)(i + 1) * inv) + 2) : H - 1;
+    float acc = 0.f;
+    const float* base = T + (int64_t)nc * H * w + j;
+    for (int Y = lo; Y <= hi; ++Y) {
+      Lerp ly = lerp_at(Y, sh, h);
+      float wgt = (ly.i0 == i ? ly.l0 : 0.f) + (ly.i1 == i ? ly.l1 : 0.f);
+      if (wgt != 0.f) acc += wgt * __ldg(base + (int64_t)Y * w);
+    }
+    dx[idx] = acc;
+  }
+}
+
+// K9: thread = 4 consecutive output pixels; interpolate all C channels, keep the first maximum.
+__global__ void __launch_bounds__(UP_THREADS)
+upsample_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred, int N, int C, int h,
+                       int w, int H, int W, float sh, float sw) {
+  const int wv = (W + 3) / 4;
+  const int64_t total = (int64_t)N * H * wv;
+  for (int64_t i = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * UP_THREADS) {
+    int xv = (int)(i % wv);
+    int64_t row = i / wv;
+    int Y = (int)(row % H);
+    int n = (int)(row / H);
+    Lerp ly = lerp_at(Y, sh, h);
+    Lerp lx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lx[k] = lerp_at(min(xv * 4 + k, W - 1), sw, w);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int arg[4] = {0, 0, 0, 0};
+    for (int c = 0; c < C; ++c) {
+      const float* r0 = x + (((int64_t)n * C + c) * h + ly.i0) * w;
+      const float* r1 = x + (((int64_t)n * C + c) * h + ly.i1) * w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // explicit IEEE mul/add (no FMA contraction): bit-identical to the numpy oracle
+        float top = __fadd_rn(__fmul_rn(lx[k].l0, __ldg(r0 + lx[k].i0)), __fmul_rn(lx[k].l1, __ldg(r0 + lx[k].i1)));
+        float bot = __fadd_rn(__fmul_rn(lx[k].l0, __ldg(r1 + lx[k].i0)), __fmul_rn(lx[k].l1, __ldg(r1 + lx[k].i1)));
+        float v = __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
+        // strict '>' keeps the first maximum (np.argmax); NaN handling: numpy treats the
+        // first NaN as the maximum
+        if (v > best[k] || (v != v && best[k] == best[k])) {
+          best[k] = v;
+          arg[k] = c;
+        }
+      }
+    }
+    uint8_t* dst = pred + row * W + (int64_t)xv * 4;
+    if ((W & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(dst) =
+          (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (xv * 4 + k < W) dst[k] = (uint8_t)arg[k];
+    }
+  }
+}
+
+}  // namespace asn
+
+using namespace asn;
+
+extern "C" int asn_upsample_bilinear_fwd(const float* x, int N, int C, int h, int w, float* y, int H,
+                                         int W, void* stream) {
+  ASN_CHECK_ARG(x && y, "asn_upsample_bilinear_fwd: null pointer");
+  ASN_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "asn_upsample_bilinear_fwd: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
+  bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  if (vec) {
+    int64_t items = (int64_t)N * C * H * (W / 4);
+    upsample_fwd_kernel<4><<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
+  } else {
+    int64_t items = (int64_t)N * C * H * W;
+    upsample_fwd_kernel<1><<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
+  }
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+extern "C" size_t asn_upsample_bwd_workspace_bytes(int N, int C, int H, int W, int h, int w) {
+  (void)W; (void)h;
+  return (size_t)N * C * H * w * sizeof(float);
+}
+
+extern "C" int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, int W, float* dx, int h,
+                                         int w, void* workspace, size_t workspace_bytes, void* stream) {
+  ASN_CHECK_ARG(dy && dx && workspace, "asn_upsample_bilinear_bwd: null pointer");
+  ASN_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "asn_upsample_bilinear_bwd: bad shape");
+  if (workspace_bytes < asn_upsample_bwd_workspace_bytes(N, C, H, W, h, w)) {
+    set_error("asn_upsample_bilinear_bwd: workspace too small");
+    return ASN_EWORKSPACE;
+  }
+  ASN_CHECK_ARG((size_t)W * 4 <= 200 * 1024, "asn_upsample_bilinear_bwd: row of %d floats exceeds shared memory", W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
+  float* T = static_cast<float*>(workspace);
+  int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+  size_t smem = (size_t)W * 4;
+  if (smem > 48 * 1024)
+    ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  upsample_bwd_w_kernel<<<(unsigned)((int64_t)N * C * H), UP_THREADS, smem, st>>>(dy, T, w, W, sw, vec_ok);
+  ASN_LAUNCH_CHECK();
+  int64_t items = (int64_t)N * C * h * w;
+  upsample_bwd_h_kernel<<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(T, dx, N * C, h, w, H, sh);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+extern "C" int asn_upsample_argmax_u8(const float* x, int N, int C, int h, int w, uint8_t* pred, int H,
+                                      int W, void* stream) {
+  ASN_CHECK_ARG(x && pred, "asn_upsample_argmax_u8: null pointer");
+  ASN_CHECK_ARG(N > 0 && C > 0 && C <= 256 && h > 0 && w > 0 && H > 0 && W > 0, "asn_upsample_argmax_u8: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
+  int64_t items = (int64_t)N * H * ((W + 3) / 4);
+  upsample_argmax_kernel<<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, pred, N, C, h, w, H, W, sh, sw);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}

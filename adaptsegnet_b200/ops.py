@@ -1,0 +1,429 @@
+"""torch-facing operators over the C ABI (include/asn_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every
+arithmetic op below is a call into libasn_b200.so on the current CUDA stream.  CPU tensors
+are rejected -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+GAN_BCE, GAN_MSE = 0, 1
+_LABEL_CODE = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}
+
+# kernels launched through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype=None, name: str = "tensor") -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.AsnError(f"{name} must be a CUDA tensor: adaptsegnet_b200 has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def precision_mode() -> str:
+    """'bf16' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core FFMA, 1e-4 mode)."""
+    m = os.environ.get("ASN_PRECISION", "bf16").lower()
+    if m not in ("bf16", "fp32"):
+        raise ValueError("ASN_PRECISION must be bf16 or fp32")
+    return m
+
+
+# --------------------------------------------------------------------------------------
+# K7 fast_hist
+# --------------------------------------------------------------------------------------
+def fast_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: torch.Tensor | None = None):
+    """compute_iou.py:15-17 on the device.  Returns (hist int64 [n,n], overflow int64 [1])."""
+    label = _req(label, None, "label")
+    pred = _req(pred, torch.uint8, "pred")
+    if label.dtype not in _LABEL_CODE:
+        raise TypeError(f"label dtype {label.dtype} not supported (uint8, int32, int64)")
+    if label.numel() != pred.numel():
+        raise ValueError("label and pred must have the same number of pixels")
+    if hist is None:
+        hist = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=label.device)
+    overflow = torch.zeros(1, dtype=torch.int64, device=label.device)
+    lib = _lib.load()
+    check(lib.asn_fast_hist(label.data_ptr(), _LABEL_CODE[label.dtype], pred.data_ptr(), label.numel(), n_cls,
+                            hist.data_ptr(), overflow.data_ptr(), _stream()), "asn_fast_hist")
+    _count()
+    return hist, overflow
+
+
+# --------------------------------------------------------------------------------------
+# K2 upsample
+# --------------------------------------------------------------------------------------
+def upsample_fwd_raw(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    x = _req(x, torch.float32, "x")
+    N, Cc, h, w = x.shape
+    y = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.load().asn_upsample_bilinear_fwd(x.data_ptr(), N, Cc, h, w, y.data_ptr(), H, W, _stream()),
+          "asn_upsample_bilinear_fwd")
+    _count()
+    return y
+
+
+def upsample_bwd_raw(dy: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    dy = _req(dy, torch.float32, "dy")
+    N, Cc, H, W = dy.shape
+    lib = _lib.load()
+    dx = torch.empty((N, Cc, h, w), dtype=torch.float32, device=dy.device)
+    nbytes = lib.asn_upsample_bwd_workspace_bytes(N, Cc, H, W, h, w)
+    ws = _ws(nbytes, dy.device)
+    check(lib.asn_upsample_bilinear_bwd(dy.data_ptr(), N, Cc, H, W, dx.data_ptr(), h, w, ws.data_ptr(), nbytes,
+                                        _stream()), "asn_upsample_bilinear_bwd")
+    _count(2)
+    return dx
+
+
+class _Upsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        ctx.hw = (x.shape[2], x.shape[3])
+        return upsample_fwd_raw(x, H, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return upsample_bwd_raw(dy, *ctx.hw), None, None
+
+
+def upsample_bilinear(x: torch.Tensor, size) -> torch.Tensor:
+    """nn.Upsample(size=size, mode='bilinear', align_corners=True)(x) -- model/deeplab_multi.py:188-189."""
+    return _Upsample.apply(x, int(size[0]), int(size[1]))
+
+
+def upsample_argmax(x: torch.Tensor, size) -> torch.Tensor:
+    """evaluate_cityscapes.py:153,163,168-169 fused: uint8 [N,H,W] class ids, first max wins."""
+    x = _req(x, torch.float32, "x")
+    N, Cc, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    pred = torch.empty((N, H, W), dtype=torch.uint8, device=x.device)
+    check(_lib.load().asn_upsample_argmax_u8(x.data_ptr(), N, Cc, h, w, pred.data_ptr(), H, W, _stream()),
+          "asn_upsample_argmax_u8")
+    _count()
+    return pred
+
+
+# --------------------------------------------------------------------------------------
+# K3 softmax cross entropy
+# --------------------------------------------------------------------------------------
+class _SoftmaxCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, y, ignore_label, mask_negative, weight, size_average):
+        z = _req(z, torch.float32, "predict")
+        y = _req(y, torch.int64, "target")
+        N, Cc, H, W = z.shape
+        stats = torch.empty(4, dtype=torch.int64, device=z.device)
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        wptr = _req(weight, torch.float32, "weight").data_ptr() if weight is not None else None
+        check(_lib.load().asn_softmax_ce_fwd(z.data_ptr(), y.data_ptr(), N, Cc, H, W, ignore_label,
+                                             int(mask_negative), wptr, int(size_average), stats.data_ptr(),
+                                             loss.data_ptr(), _stream()), "asn_softmax_ce_fwd")
+        _count(2)
+        ctx.save_for_backward(z, y, stats, weight if weight is not None else torch.empty(0, device=z.device))
+        ctx.cfg = (ignore_label, int(mask_negative), weight is not None, int(size_average))
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, gloss, _gstats):
+        z, y, stats, weight = ctx.saved_tensors
+        ignore_label, mask_negative, has_w, size_average = ctx.cfg
+        N, Cc, H, W = z.shape
+        dz = torch.empty_like(z)
+        g = _req(gloss.to(torch.float32), torch.float32, "grad")
+        check(_lib.load().asn_softmax_ce_bwd(z.data_ptr(), y.data_ptr(), N, Cc, H, W, ignore_label, mask_negative,
+                                             weight.data_ptr() if has_w else None, size_average, stats.data_ptr(),
+                                             g.data_ptr(), dz.data_ptr(), _stream()), "asn_softmax_ce_bwd")
+        _count()
+        return dz, None, None, None, None, None
+
+
+def softmax_cross_entropy(z, y, ignore_label=255, mask_negative=False, weight=None, size_average=True,
+                          return_stats=False):
+    """Fused log-softmax + NLL over (N,C,H,W) logits with an ignore label.
+
+    torch.nn.CrossEntropyLoss(ignore_index=255) as used at train_gta2cityscapes_multi.py:599-600
+    (mask_negative=False) and utils/loss.py:7-36 (mask_negative=True).  stats[2] is the exact
+    valid-pixel count, stats[3] the number of out-of-range targets (loss is nan if non-zero).
+    """
+    loss, stats = _SoftmaxCE.apply(z, y, int(ignore_label), bool(mask_negative), weight, bool(size_average))
+    if os.environ.get("ASN_STRICT_LABELS") == "1" and int(stats[3].item()) != 0:
+        raise IndexError("Target out of bounds")  # what torch raises for the reference
+    return (loss, stats) if return_stats else loss
+
+
+# --------------------------------------------------------------------------------------
+# K4 softmax over channels
+# --------------------------------------------------------------------------------------
+class _Softmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        z = _req(z, torch.float32, "input")
+        N, Cc, H, W = z.shape
+        p = torch.empty_like(z)
+        check(_lib.load().asn_softmax_fwd(z.data_ptr(), N, Cc, H, W, p.data_ptr(), _stream()), "asn_softmax_fwd")
+        _count()
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        (p,) = ctx.saved_tensors
+        dp = _req(dp, torch.float32, "grad")
+        N, Cc, H, W = p.shape
+        dz = torch.empty_like(p)
+        check(_lib.load().asn_softmax_bwd(p.data_ptr(), dp.data_ptr(), N, Cc, H, W, dz.data_ptr(), _stream()),
+              "asn_softmax_bwd")
+        _count()
+        return dz
+
+
+def softmax_channels(z: torch.Tensor) -> torch.Tensor:
+    """F.softmax(z) with the legacy implicit dim (= 1 for 4-D), train_gta2cityscapes_multi.py:617-618."""
+    if z.dim() != 4:
+        raise ValueError("softmax_channels expects (N,C,H,W)")
+    return _Softmax.apply(z)
+
+
+# --------------------------------------------------------------------------------------
+# K6 adversarial losses against a constant label
+# --------------------------------------------------------------------------------------
+class _GanLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target, kind):
+        x = _req(x, torch.float32, "input")
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        need = x.requires_grad
+        dx = torch.empty_like(x) if need else None
+        check(_lib.load().asn_gan_loss_fwd_bwd(x.data_ptr(), x.numel(), float(target), int(kind), 1.0,
+                                               loss.data_ptr(), dx.data_ptr() if need else None, _stream()),
+              "asn_gan_loss_fwd_bwd")
+        _count()
+        if need:
+            ctx.save_for_backward(dx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None, None
+
+
+def gan_loss(x: torch.Tensor, target: float, kind: int = GAN_BCE) -> torch.Tensor:
+    """BCEWithLogitsLoss()(x, full_like(x, target)) (kind=GAN_BCE) or MSELoss() (GAN_MSE) without
+    materialising the target tensor (train_gta2cityscapes_multi.py:620-624)."""
+    return _GanLoss.apply(x, float(target), int(kind))
+
+
+# --------------------------------------------------------------------------------------
+# fp32 convolutions on CUDA cores
+# --------------------------------------------------------------------------------------
+def conv2d_fwd_f32(x, w, bias, stride, pad, dil, lrelu_slope=1.0, out=None, accumulate=False):
+    x = _req(x, torch.float32, "x")
+    w = _req(w, torch.float32, "w")
+    N, Cc, H, W = x.shape
+    O, _, KH, KW = w.shape
+    OH = (H + 2 * pad - dil * (KH - 1) - 1) // stride + 1
+    OW = (W + 2 * pad - dil * (KW - 1) - 1) // stride + 1
+    if out is None:
+        out = torch.empty((N, O, OH, OW), dtype=torch.float32, device=x.device)
+    b = _req(bias, torch.float32, "bias") if bias is not None else None
+    check(_lib.load().asn_conv2d_fwd_f32(x.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
+                                         out.data_ptr(), N, Cc, H, W, O, KH, KW, stride, pad, dil,
+                                         float(lrelu_slope), int(accumulate), _stream()), "asn_conv2d_fwd_f32")
+    _count()
+    return out
+
+
+def conv2d_dgrad_f32(dy, w, x_shape, stride, pad, dil, out=None, accumulate=False):
+    dy = _req(dy, torch.float32, "dy")
+    w = _req(w, torch.float32, "w")
+    N, Cc, H, W = x_shape
+    O, _, KH, KW = w.shape
+    if out is None:
+        out = torch.empty(tuple(x_shape), dtype=torch.float32, device=dy.device)
+    check(_lib.load().asn_conv2d_dgrad_f32(dy.data_ptr(), w.data_ptr(), out.data_ptr(), N, Cc, H, W, O, KH, KW,
+                                           stride, pad, dil, int(accumulate), _stream()), "asn_conv2d_dgrad_f32")
+    _count()
+    return out
+
+
+def conv2d_wgrad_f32(x, dy, w_shape, stride, pad, dil, want_bias=True):
+    x = _req(x, torch.float32, "x")
+    dy = _req(dy, torch.float32, "dy")
+    N, Cc, H, W = x.shape
+    O, _, KH, KW = w_shape
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    db = torch.empty((O,), dtype=torch.float32, device=x.device) if want_bias else None
+    check(_lib.load().asn_conv2d_wgrad_f32(x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                                           db.data_ptr() if want_bias else None, N, Cc, H, W, O, KH, KW, stride,
+                                           pad, dil, _stream()), "asn_conv2d_wgrad_f32")
+    _count(3)
+    return dw, db
+
+
+def lrelu_bwd_f32(dy, post, slope):
+    dy = _req(dy, torch.float32, "dy")
+    post = _req(post, torch.float32, "post")
+    dx = torch.empty_like(dy)
+    check(_lib.load().asn_lrelu_bwd_f32(dy.data_ptr(), post.data_ptr(), dx.data_ptr(), dy.numel(), float(slope),
+                                        _stream()), "asn_lrelu_bwd_f32")
+    _count()
+    return dx
+
+
+# --------------------------------------------------------------------------------------
+# raw tcgen05 GEMM (tests / microbenchmarks)
+# --------------------------------------------------------------------------------------
+def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, split_k: int = 1) -> torch.Tensor:
+    """C[M,N] fp32 = A[M,K] @ B[N,K]^T for bf16 row-major A, B (K % 8 == 0)."""
+    a = _req(a, torch.bfloat16, "A")
+    b = _req(b, torch.bfloat16, "B")
+    M, K = a.shape
+    Nn, K2 = b.shape
+    assert K == K2
+    lib = _lib.load()
+    c = torch.empty((max(split_k, 1), M, Nn), dtype=torch.float32, device=a.device)
+    check(lib.asn_gemm_bf16_tn(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K, K, K, Nn, split_k, _stream()),
+          "asn_gemm_bf16_tn")
+    _count()
+    return c
+
+
+# --------------------------------------------------------------------------------------
+# K1 ASPP classifier head
+# --------------------------------------------------------------------------------------
+class AsppWeightPack:
+    """bf16 GEMM-layout shadow of the four fp32 OIHW branch weights (asn_aspp_pack_weights).
+    Re-packed when the parameters' version counters change (i.e. after optimizer.step())."""
+
+    def __init__(self):
+        self.key = None
+        self.wp = self.wpt = self.bias_sum = None
+
+    def get(self, weights, biases, n_active):
+        key = tuple((w.data_ptr(), w._version) for w in list(weights) + list(biases)) + (n_active,)
+        if key != self.key:
+            lib = _lib.load()
+            w0 = weights[0]
+            n_cls, cin = w0.shape[0], w0.shape[1]
+            NP = lib.asn_aspp_np(n_cls, n_active)
+            self.wp = torch.empty((NP, cin), dtype=torch.bfloat16, device=w0.device)
+            self.wpt = torch.empty((cin, NP), dtype=torch.bfloat16, device=w0.device)
+            ws = [_req(w.detach(), torch.float32, "weight") for w in weights[:n_active]]
+            check(lib.asn_aspp_pack_weights(_lib.ptr_array([w.data_ptr() for w in ws]), n_active, n_cls, cin,
+                                            self.wp.data_ptr(), self.wpt.data_ptr(), _stream()),
+                  "asn_aspp_pack_weights")
+            _count()
+            with torch.no_grad():
+                self.bias_sum = torch.stack([b.detach() for b in biases[:n_active]]).sum(0).contiguous()
+            self.key = key
+        return self.wp, self.wpt, self.bias_sum
+
+
+class _AsppHeadTC(torch.autograd.Function):
+    """bf16 tcgen05 path: asn_aspp_fwd / asn_aspp_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, pack, dils, n_active, *params):
+        nb = len(params) // 2
+        weights, biases = params[:nb], params[nb:]
+        x = _req(x, torch.float32, "x")
+        wp, wpt, bias_sum = pack.get(weights, biases, n_active)
+        N, cin, H, W = x.shape
+        n_cls = weights[0].shape[0]
+        lib = _lib.load()
+        nbytes = lib.asn_aspp_workspace_bytes(N, cin, H, W, n_cls, n_active)
+        ws = _ws(nbytes, x.device)
+        y = torch.empty((N, n_cls, H, W), dtype=torch.float32, device=x.device)
+        check(lib.asn_aspp_fwd(x.data_ptr(), wp.data_ptr(), bias_sum.data_ptr(), y.data_ptr(), N, cin, H, W, n_cls,
+                               _lib.int_array(dils), n_active, ws.data_ptr(), nbytes, _stream()), "asn_aspp_fwd")
+        _count(3)
+        ctx.save_for_backward(x, wpt)
+        ctx.cfg = (tuple(dils), n_active, nb, n_cls, tuple(w.shape for w in weights))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wpt = ctx.saved_tensors
+        dils, n_active, nb, n_cls, wshapes = ctx.cfg
+        dy = _req(dy, torch.float32, "dy")
+        N, cin, H, W = x.shape
+        lib = _lib.load()
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[4:4 + nb])
+        need_b = any(ctx.needs_input_grad[4 + nb:])
+        nbytes = lib.asn_aspp_workspace_bytes(N, cin, H, W, n_cls, n_active)
+        ws = _ws(nbytes, x.device)
+        dx = torch.empty_like(x) if need_x else None
+        dws = [torch.empty(wshapes[i], dtype=torch.float32, device=x.device) for i in range(n_active)] if need_w else None
+        db = torch.empty((n_cls,), dtype=torch.float32, device=x.device) if need_b else None
+        check(lib.asn_aspp_bwd(x.data_ptr(), wpt.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_x else None,
+                               _lib.ptr_array([t.data_ptr() for t in dws]) if need_w else None,
+                               db.data_ptr() if need_b else None, N, cin, H, W, n_cls, _lib.int_array(dils),
+                               n_active, ws.data_ptr(), nbytes, _stream()), "asn_aspp_bwd")
+        _count(1 + (N if need_x else 0) + (3 if need_w else 0) + (1 if need_b else 0))
+        gw = [(dws[i] if (need_w and i < n_active) else None) for i in range(nb)]
+        # inactive branches (early-return variants) receive no gradient
+        gb = [(db if (need_b and i < n_active) else None) for i in range(nb)]
+        return (dx, None, None, None, *gw, *gb)
+
+
+class _AsppHeadF32(torch.autograd.Function):
+    """fp32 CUDA-core path (ASN_PRECISION=fp32): branch-by-branch direct convolution."""
+
+    @staticmethod
+    def forward(ctx, x, dils, n_active, *params):
+        nb = len(params) // 2
+        weights, biases = params[:nb], params[nb:]
+        x = _req(x, torch.float32, "x")
+        y = None
+        for i in range(n_active):
+            y = conv2d_fwd_f32(x, weights[i], biases[i], 1, dils[i], dils[i], 1.0, out=y, accumulate=i > 0)
+        ctx.save_for_backward(x, *weights)
+        ctx.cfg = (tuple(dils), n_active, nb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *weights = ctx.saved_tensors
+        dils, n_active, nb = ctx.cfg
+        dy = _req(dy, torch.float32, "dy")
+        dx = None
+        gw, gb = [None] * nb, [None] * nb
+        for i in range(n_active):
+            if ctx.needs_input_grad[0]:
+                dx = conv2d_dgrad_f32(dy, weights[i], x.shape, 1, dils[i], dils[i], out=dx, accumulate=i > 0)
+            if ctx.needs_input_grad[3 + i] or ctx.needs_input_grad[3 + nb + i]:
+                gw[i], gb[i] = conv2d_wgrad_f32(x, dy, weights[i].shape, 1, dils[i], dils[i], True)
+        return (dx, None, None, *gw, *gb)
+
+
+def aspp_head(x, weights, biases, dilations, n_active, pack: AsppWeightPack | None = None):
+    """sum_{b < n_active} conv_b(x) -- Classifier_Module.forward, model/deeplab_multi.py:117-121."""
+    if precision_mode() == "fp32":
+        return _AsppHeadF32.apply(x, tuple(dilations), n_active, *weights, *biases)
+    pack = pack if pack is not None else AsppWeightPack()
+    return _AsppHeadTC.apply(x, pack, tuple(dilations), n_active, *weights, *biases)

@@ -1,0 +1,210 @@
+/*
+ * asn_b200.h -- C ABI of libasn_b200.so: the B200 (sm_100a) implementation of the
+ * AdaptSegNet output-space-adaptation hot path.
+ *
+ * The reference (sahngmin/AdaptSegNet) has no FFI of its own: its hot path is a set
+ * of torch.nn / numpy calls made from three Python files plus one free function
+ * (SURVEY.md section 8b).  Each entry point below replaces the arithmetic behind one of
+ * those call sites; the citation after "replaces:" is the reference file:line.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless it says host.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises, nothing allocates: scratch comes in as (workspace, workspace_bytes),
+ *     sized by the matching asn_*_workspace_bytes().
+ *   - return 0 on success, a negative ASN_E* code on failure; asn_last_error() returns a
+ *     thread-local message for the last failure.
+ *   - activations fp32 NCHW contiguous at the boundary (what the reference's modules
+ *     exchange); bf16 / NHWC staging layouts are internal.
+ */
+#ifndef ASN_B200_H_
+#define ASN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ASN_API __attribute__((visibility("default")))
+#else
+#define ASN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASN_ABI_VERSION 1
+
+enum {
+  ASN_OK = 0,
+  ASN_EINVAL = -1,      /* bad argument (shape, alignment, null pointer) */
+  ASN_EWORKSPACE = -2,  /* workspace too small */
+  ASN_ECUDA = -3,       /* a CUDA runtime / driver call failed */
+  ASN_EUNSUPPORTED = -4 /* configuration outside what the kernels cover */
+};
+
+/* precision of the convolution paths */
+enum {
+  ASN_PREC_BF16 = 0, /* bf16 operands, fp32 accumulate on tcgen05 tensor cores (default) */
+  ASN_PREC_FP32 = 1  /* fp32 FFMA on CUDA cores: the 1e-4 "fp32 mode" of the north star */
+};
+
+enum { ASN_LABEL_U8 = 0, ASN_LABEL_I32 = 1, ASN_LABEL_I64 = 2 };
+enum { ASN_GAN_BCE = 0, ASN_GAN_MSE = 1 };
+
+ASN_API int asn_abi_version(void);
+ASN_API const char* asn_last_error(void);
+/* number of SMs of the current device (grids are sized from it) */
+ASN_API int asn_sm_count(int* out_host);
+
+/* ------------------------------------------------------------------------------------
+ * K7  confusion matrix.  replaces: compute_iou.py:15-17 (fast_hist), accumulate :57
+ *   hist[n_cls*a+b] += 1 for every pixel with 0 <= a < n_cls.  `hist` (n_cls*n_cls int64)
+ *   is ACCUMULATED into (zero it for a fresh matrix).  Like np.bincount in the reference, a
+ *   prediction b >= n_cls under a valid label lands at the flat index n_cls*a+b; indices
+ *   >= n_cls^2 (where the reference's reshape raises ValueError) are counted in
+ *   *overflow instead.  Integer arithmetic, bit-exact, order independent.
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_fast_hist(const void* label, int label_dtype, const uint8_t* pred, int64_t n_px,
+                  int n_cls, int64_t* hist, int64_t* overflow, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2 / K2b / K9  bilinear resize, align_corners=True.
+ *   replaces: model/deeplab_multi.py:188-189, evaluate_cityscapes.py:153 (nn.Upsample)
+ *   and its autograd; asn_upsample_argmax_u8 replaces evaluate_cityscapes.py:163,168-169
+ *   (interp -> cpu -> transpose -> np.argmax -> uint8; first maximum wins).
+ *   bwd is the gather-form adjoint: no atomics, deterministic.  workspace for bwd:
+ *   N*C*H*w floats (asn_upsample_bwd_workspace_bytes).
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_upsample_bilinear_fwd(const float* x, int N, int C, int h, int w, float* y, int H, int W,
+                              void* stream);
+ASN_API size_t asn_upsample_bwd_workspace_bytes(int N, int C, int H, int W, int h, int w);
+ASN_API int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, int W, float* dx, int h, int w,
+                              void* workspace, size_t workspace_bytes, void* stream);
+ASN_API int asn_upsample_argmax_u8(const float* x, int N, int C, int h, int w, uint8_t* pred, int H, int W,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  softmax + cross entropy with ignore label over (N,C,H,W) logits.
+ *   replaces: torch.nn.CrossEntropyLoss(ignore_index=255) train_gta2cityscapes_multi.py:248,
+ *   359,546 applied :282,407,599-600, and utils/loss.py:7-36 (CrossEntropy2d; mask_negative=1
+ *   adds its `target >= 0` mask, class_weight its `weight`, size_average its flag).
+ *   stats (device, 4 x 8 bytes, written by fwd):
+ *     [0] double  sum_i w_i * nll_i          [1] double  sum_i w_i   (valid pixels)
+ *     [2] int64   n_valid (exact)            [3] int64   n_bad: labels neither ignored nor in
+ *                                                         [0,C) -- torch raises for those
+ *   loss (device float): size_average ? stats0/stats1 : stats0   (0/0 = nan as the reference).
+ *   bwd: dz = gscale * (softmax(z) - onehot(y)) * w_y * valid / (size_average ? stats1 : 1);
+ *   gscale is a device float (upstream gradient), may be NULL (= 1).
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_softmax_ce_fwd(const float* z, const int64_t* y, int N, int C, int H, int W, int ignore_label,
+                       int mask_negative, const float* class_weight, int size_average, void* stats,
+                       float* loss, void* stream);
+ASN_API int asn_softmax_ce_bwd(const float* z, const int64_t* y, int N, int C, int H, int W, int ignore_label,
+                       int mask_negative, const float* class_weight, int size_average,
+                       const void* stats, const float* gscale, float* dz, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  softmax over dim 1 of (N,C,H,W).  replaces: F.softmax(pred) (implicit dim = 1)
+ *   train_gta2cityscapes_multi.py:423,442,454,617-618,645-646,665-666 and its autograd.
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_softmax_fwd(const float* z, int N, int C, int H, int W, float* p, void* stream);
+ASN_API int asn_softmax_bwd(const float* p, const float* dp, int N, int C, int H, int W, float* dz,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K6  adversarial loss against a constant target (the reference builds the target tensor on
+ *   the CPU each call).  replaces: BCEWithLogitsLoss / MSELoss
+ *   train_gta2cityscapes_multi.py:356,358,543,545 applied :425,444,456,620-624,648-650,668-670.
+ *   loss (device float) = mean(...); dx (nullable) = grad_scale * dloss/dx.
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_gan_loss_fwd_bwd(const float* x, int64_t n, float target, int kind, float grad_scale,
+                         float* loss, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * generic fp32 convolution on CUDA cores (ASN_PREC_FP32 path of K1 / K5 and the on-device
+ * cross-check of the tensor-core kernels).  NCHW fp32, OIHW weights, zero padding.
+ *   fwd : y = conv(x, w) + bias, optional LeakyReLU (slope; pass 1.0f for none);
+ *         accumulate != 0 adds into y (used to sum the ASPP branches).
+ *   dgrad: dx (+)= conv_transpose(dy, w);  wgrad: dw = corr(x, dy), db = sum dy (db nullable).
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_conv2d_fwd_f32(const float* x, const float* w, const float* bias, float* y, int N, int C,
+                       int H, int W, int O, int KH, int KW, int stride, int pad, int dil,
+                       float lrelu_slope, int accumulate, void* stream);
+ASN_API int asn_conv2d_dgrad_f32(const float* dy, const float* w, float* dx, int N, int C, int H, int W,
+                         int O, int KH, int KW, int stride, int pad, int dil, int accumulate,
+                         void* stream);
+ASN_API int asn_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int N, int C, int H,
+                         int W, int O, int KH, int KW, int stride, int pad, int dil, void* stream);
+/* dx = dy * (post > 0 ? 1 : slope): LeakyReLU backward from the stored post-activation
+ * (replaces the autograd of model/discriminator.py:23,25,27,29). */
+ASN_API int asn_lrelu_bwd_f32(const float* dy, const float* post, float* dx, int64_t n, float slope,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K1 / K1b  ASPP classifier head on tcgen05 (bf16 operands, fp32 accumulate).
+ *   replaces: Classifier_Module.forward model/deeplab_multi.py:117-121 (n_active = 4) and the
+ *   early-return variants model/deeplab.py:112-116, model/deeplab_vgg.py:17-21 (n_active = 2),
+ *   plus their autograd.
+ *   Formulation: with T = 9*n_active taps and NP = round_up(T*n_cls, 16)
+ *     fwd  : Z[px, NP]   = Xnhwc[px, Cin] . Wp[NP, Cin]^T      (dense GEMM, no im2col of X)
+ *            y[c, p]     = bias_sum[c] + sum_t Z[p + shift_t, t*n_cls + c]   (gather-sum)
+ *     dgrad: dX[Cin, px] = WpT[Cin, NP] . dYcol[px, NP]^T ,  dYcol[q, t*n_cls+c] = dy[c, q - shift_t]
+ *     wgrad: dWp[Cin,NP] = Xnchw[Cin, px] . dYcolT[NP, px]^T   (split-K over pixels)
+ *   asn_aspp_pack_weights builds Wp (bf16 [NP][Cin]) and WpT (bf16 [Cin][NP]) from the four
+ *   fp32 OIHW weights; call it after every optimizer step.
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_aspp_np(int n_cls, int n_active); /* NP */
+ASN_API int asn_aspp_pack_weights(const float* const* w_oihw /* host array of n_branches device ptrs */,
+                          int n_active, int n_cls, int Cin, void* wp_bf16, void* wpt_bf16,
+                          void* stream);
+ASN_API size_t asn_aspp_workspace_bytes(int N, int Cin, int H, int W, int n_cls, int n_active);
+ASN_API int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const float* bias_sum, float* y_nchw,
+                 int N, int Cin, int H, int W, int n_cls, const int* dil_host, int n_active,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* any of dx / dw / db may be NULL (skipped).  dw: host array of n_active device ptrs (OIHW fp32,
+ * overwritten); db: device [n_cls] = sum over pixels of dy (identical for every active branch). */
+ASN_API int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const float* dy_nchw, float* dx_nchw,
+                 float* const* dw_oihw, float* db, int N, int Cin, int H, int W, int n_cls,
+                 const int* dil_host, int n_active, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5 / K5b / K8  FCDiscriminator on tcgen05 (bf16 NHWC activations internally).
+ *   replaces: FCDiscriminator.forward model/discriminator.py:21-34 and its autograd:
+ *   conv1..conv4 (k4 s2 p1 + bias + LeakyReLU 0.2) as implicit GEMMs whose im2col tiles are
+ *   TMA boxes over stride-2 "parity views" of the NHWC activation; classifier (512 -> 1) is a
+ *   CUDA-core reduction.  Requires ndf % 64 == 0 (reference default ndf = 64), C_in <= 32.
+ *   Weights are packed once per optimizer step by asn_fcd_pack_weights into `wpack`.
+ *   The forward keeps its bf16 activations in `acts` (asn_fcd_acts_bytes) for the backward.
+ *   bwd: dx (nullable: D-step, input detached) and/or dparams (nullable: G-step, parameters
+ *   frozen) -- host array of 10 device pointers {conv1.w, conv1.b, ..., classifier.w,
+ *   classifier.b}, fp32, same shapes as the parameters, overwritten.
+ * ---------------------------------------------------------------------------------- */
+ASN_API size_t asn_fcd_wpack_bytes(int n_cls, int ndf);
+ASN_API int asn_fcd_pack_weights(const float* const* params_host /* 10 device ptrs, w/b per layer */,
+                         int n_cls, int ndf, void* wpack, void* stream);
+ASN_API size_t asn_fcd_acts_bytes(int N, int n_cls, int ndf, int H, int W);
+ASN_API size_t asn_fcd_workspace_bytes(int N, int n_cls, int ndf, int H, int W);
+/* x_is_logits != 0 fuses the channel softmax (K4) into the input pack. */
+ASN_API int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpack, void* acts, float* out,
+                int N, int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes,
+                void* stream);
+ASN_API int asn_fcd_bwd(const float* dout, const void* wpack, const void* acts, float* dx_nchw,
+                float* const* dparams_host, int N, int n_cls, int ndf, int H, int W,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * raw tcgen05 GEMM (exposed for tests / benchmarking of the tensor-core core):
+ *   C[M,N] (fp32, row major, ldc) = A[M,K] . B[N,K]^T, A and B bf16 row major (K contiguous),
+ *   lda/ldb in elements and multiples of 8.  split_k > 1 writes split_k partial matrices
+ *   C + s*M*ldc.
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb,
+                     int ldc, int split_k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASN_B200_H_ */
