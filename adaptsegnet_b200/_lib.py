@@ -49,7 +49,7 @@ SIGNATURES = {
     "asn_fcd_workspace_bytes": (c_size_t, [c_int] * 5),
     "asn_fcd_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_size_t, c_void_p]),
-    "asn_fcd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, PP, c_int, c_int, c_int, c_int, c_int,
+    "asn_fcd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PP, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_size_t, c_void_p]),
     "asn_gemm_bf16_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),

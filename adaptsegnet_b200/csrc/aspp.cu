@@ -199,6 +199,12 @@ nchw_channel_sum_kernel(const float* __restrict__ src, float* __restrict__ out, 
   }
 }
 
+int channel_sum_nchw(const float* src, float* out, int N, int O, int P, cudaStream_t st) {
+  nchw_channel_sum_kernel<<<O, 256, 0, st>>>(src, out, N, O, P);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
 // ---- host orchestration --------------------------------------------------------------------
 
 static int pick_block_n(int n) {

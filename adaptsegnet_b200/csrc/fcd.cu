@@ -1,0 +1,754 @@
+// K5 / K5b / K8: FCDiscriminator (model/discriminator.py:5-34) on tcgen05.
+//
+// Activations are bf16 NHWC.  A 4x4 stride-2 pad-1 convolution reads input pixel
+// (2*oh - 1 + kh, 2*ow - 1 + kw); writing kh - 1 = 2*a + r (r = row parity, a in {-1,0,0,1})
+// turns every tap into a unit-stride box over one of four "parity views" of the input
+// (base + (r_h*W + r_w)*C, strides doubled), so one TMA box per (tap, 64-channel chunk) is the
+// im2col tile of a 128-pixel output box, with the zero padding supplied by TMA's out-of-bounds
+// fill.  conv1 (19 input channels) pads channels to 32 and W by one zero column on each side so
+// that two horizontally adjacent taps form one 128-byte row (8 k-steps of 64).
+//   forward  conv l : MODE_CONV, epilogue = bias + LeakyReLU(0.2) -> bf16 NHWC (input of l+1)
+//   dgrad    conv l : 4 output-parity classes (blockIdx.z), each a 2x2-tap stride-1 conv over
+//                     dPre_l; epilogue multiplies by the LeakyReLU mask of A_{l-1}
+//   wgrad    conv l : MODE_WGRAD (pixels are the reduction), one CTA column per tap, split-K
+//   classifier (512 -> 1) and its gradients: CUDA-core reductions (GEMV-shaped).
+#include "umma_host.cuh"
+
+namespace asn {
+
+int channel_sum_nchw(const float* src, float* out, int N, int O, int P, cudaStream_t st);  // aspp.cu
+
+constexpr float FCD_SLOPE = 0.2f;  // model/discriminator.py:16
+
+struct FcdPlan {
+  int N, n_cls, ndf;
+  int H[6], W[6], C[6];  // level 0 = packed input (C = 32), 1..4 conv outputs, 5 = classifier output
+  int W0p;               // padded width of the packed input (W + 2 rounded up to even)
+  // acts (bf16 elements offsets in bytes)
+  size_t act_off[5], acts_total;
+  // wpack
+  size_t wf_off[5], wd_off[5], bias_off[5], wc_off, bc_off, wpack_total;  // index 1..4
+  // workspace
+  size_t dpre_off[5], da0_off, part_off, dbpart_off, ws_total;
+  int split[5];          // wgrad split-K per layer
+  size_t part_bytes;
+};
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static void pick_tile(int OH, int OW, int px, int* th, int* tw) {
+  int64_t best = -1;
+  for (int h = 1; h <= px; h *= 2) {
+    int w = px / h;
+    if (w > 256 || h > 256) continue;
+    int64_t area = (int64_t)cdiv(OH, h) * h * cdiv(OW, w) * w;
+    if (best < 0 || area < best || (area == best && w > *tw)) {
+      best = area;
+      *th = h;
+      *tw = w;
+    }
+  }
+}
+
+static int wgrad_taps(int l) { return l == 1 ? 8 : 16; }
+static int wgrad_n(const FcdPlan& p, int l) { return l == 1 ? 64 : p.C[l - 1]; }
+
+static int make_plan(FcdPlan& p, int N, int n_cls, int ndf, int H, int W) {
+  ASN_CHECK_ARG(N > 0 && n_cls >= 1 && n_cls <= 32, "fcd: n_cls=%d outside [1,32]", n_cls);
+  ASN_CHECK_ARG(ndf >= 64 && ndf % 64 == 0 && ndf <= 256, "fcd: ndf=%d must be a multiple of 64 (<= 256)", ndf);
+  ASN_CHECK_ARG(H >= 32 && W >= 32, "fcd: input %dx%d smaller than the 32x32 receptive stride", H, W);
+  p.N = N; p.n_cls = n_cls; p.ndf = ndf;
+  p.H[0] = H; p.W[0] = W; p.C[0] = 32;
+  for (int l = 1; l <= 5; ++l) {
+    p.H[l] = (p.H[l - 1] + 2 - 4) / 2 + 1;
+    p.W[l] = (p.W[l - 1] + 2 - 4) / 2 + 1;
+    p.C[l] = l == 5 ? 1 : ndf << (l - 1);
+  }
+  p.W0p = (int)round_up(W + 2, 2);
+  size_t off = 0;
+  p.act_off[0] = off; off += align256((size_t)N * H * p.W0p * 32 * 2);
+  for (int l = 1; l <= 4; ++l) { p.act_off[l] = off; off += align256((size_t)N * p.H[l] * p.W[l] * p.C[l] * 2); }
+  p.acts_total = off;
+  off = 0;
+  for (int l = 1; l <= 4; ++l) {
+    const size_t kf = l == 1 ? 8 * 64 : (size_t)16 * p.C[l - 1];           // forward K
+    p.wf_off[l] = off; off += align256((size_t)p.C[l] * kf * 2);
+    const size_t rows = l == 1 ? 32 : p.C[l - 1];                           // dgrad rows per parity class
+    p.wd_off[l] = off; off += align256((size_t)4 * rows * 4 * p.C[l] * 2);
+    p.bias_off[l] = off; off += align256((size_t)p.C[l] * 4);
+  }
+  p.wc_off = off; off += align256((size_t)16 * p.C[4] * 4);
+  p.bc_off = off; off += 256;
+  p.wpack_total = off;
+  off = 0;
+  for (int l = 1; l <= 4; ++l) { p.dpre_off[l] = off; off += align256((size_t)N * p.H[l] * p.W[l] * p.C[l] * 2); }
+  p.da0_off = off; off += align256((size_t)N * H * p.W0p * 32 * 2);
+  p.part_bytes = 0;
+  for (int l = 1; l <= 4; ++l) {
+    int th = 1, tw = 64;
+    pick_tile(p.H[l], p.W[l], 64, &th, &tw);
+    const int k_steps = N * cdiv(p.H[l], th) * cdiv(p.W[l], tw);
+    const int nn = wgrad_n(p, l);
+    const int bn = nn >= 256 ? 256 : nn;
+    const int ctas = cdiv(p.C[l], 128) * cdiv(nn, bn) * wgrad_taps(l);
+    int S = (2 * sm_count() + ctas - 1) / ctas;
+    if (S > k_steps / 2) S = k_steps / 2;
+    if (S < 1) S = 1;
+    const int sps = cdiv(k_steps, S);
+    p.split[l] = cdiv(k_steps, sps);
+    const size_t bytes = (size_t)p.split[l] * wgrad_taps(l) * p.C[l] * nn * 4;
+    if (bytes > p.part_bytes) p.part_bytes = bytes;
+  }
+  p.part_off = off; off += align256(p.part_bytes);
+  p.dbpart_off = off; off += align256((size_t)256 * 2048 * 4);
+  p.ws_total = off;
+  return ASN_OK;
+}
+
+// kh (or kw) - 1 = 2*a + r
+__host__ __device__ inline int tap_a(int k) { return k == 0 ? -1 : (k == 3 ? 1 : 0); }
+__host__ __device__ inline int tap_r(int k) { return (k == 0 || k == 2) ? 1 : 0; }
+
+// ---- input pack: fp32 NCHW (probabilities or logits) -> bf16 [N][H][W0p][32] ------------------
+__global__ void __launch_bounds__(256)
+fcd_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a0, int N, int C, int H, int W,
+                      int W0p, int softmax) {
+  const int64_t total = (int64_t)N * H * W0p;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int wp = (int)(i % W0p);
+    const int h = (int)((i / W0p) % H);
+    const int n = (int)(i / ((int64_t)W0p * H));
+    const int w = wp - 1;
+    float v[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = 0.f;
+    if (w >= 0 && w < W) {
+      const float* src = x + ((int64_t)n * C * H + h) * W + w;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) v[c] = __ldg(src + (int64_t)c * H * W);
+      if (softmax) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < C) m = fmaxf(m, v[c]);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < C) { v[c] = expf(v[c] - m); s += v[c]; }
+        const float inv = 1.f / s;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] *= inv;
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(a0 + i * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 hh = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// dA0 bf16 [N][H][W0p][32] -> dx fp32 NCHW; with logits given, the channel-softmax backward is fused:
+// dz = p * (g - sum_c p*g), p = softmax(x).
+__global__ void __launch_bounds__(256)
+fcd_unpack_dx_kernel(const __nv_bfloat16* __restrict__ da0, const float* __restrict__ logits,
+                     float* __restrict__ dx, int N, int C, int H, int W, int W0p) {
+  const int64_t total = (int64_t)N * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const int n = (int)(i / ((int64_t)W * H));
+    const uint4* src = reinterpret_cast<const uint4*>(da0 + (((int64_t)n * H + h) * W0p + w + 1) * 32);
+    float g[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u = __ldg(src + q);
+      uint32_t pk[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 hh = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+        g[q * 8 + 2 * j] = __low2float(hh);
+        g[q * 8 + 2 * j + 1] = __high2float(hh);
+      }
+    }
+    const int64_t base = ((int64_t)n * C * H + h) * W + w;
+    if (logits) {
+      float z[32];
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) { z[c] = __ldg(logits + base + (int64_t)c * H * W); m = fmaxf(m, z[c]); }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) { z[c] = expf(z[c] - m); s += z[c]; }
+      const float inv = 1.f / s;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) { z[c] *= inv; dot += z[c] * g[c]; }
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) g[c] = z[c] * (g[c] - dot);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < C) dx[base + (int64_t)c * H * W] = g[c];
+  }
+}
+
+// ---- weight packing ---------------------------------------------------------------------------
+struct FcdParamPtrs {
+  const float* w[5];
+  const float* b[5];
+};
+
+// forward pack  Wf_l[co][k]:  l >= 2: k = (kh*4+kw)*Cin + ci ; l == 1: k = (kh*2+pw)*64 + kwl*32 + c, kw = 2*pw + kwl
+// dgrad pack    Wd_l[z=(rh,rw)][ci][k], k = (th*2+tw)*Cout + co with kh = kh(rh, th), kw = kw(rw, tw):
+//               rh = 0 -> kh in {1,3}, rh = 1 -> kh in {0,2}
+__global__ void __launch_bounds__(256)
+fcd_pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, __nv_bfloat16* __restrict__ wf,
+                     __nv_bfloat16* __restrict__ wd, float* __restrict__ bias, int l, int Cout, int Cin_real,
+                     int Cin_rows) {
+  const int Kf = l == 1 ? 512 : 16 * Cin_real;
+  const int64_t nf = (int64_t)Cout * Kf;
+  const int Kd = 4 * Cout;
+  const int64_t nd = (int64_t)4 * Cin_rows * Kd;
+  const int64_t total = nf + nd + Cout;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    if (i < nf) {
+      const int co = (int)(i / Kf), k = (int)(i % Kf);
+      int ci, kh, kw;
+      if (l == 1) {
+        const int t = k / 64, r = k % 64;
+        kh = t / 2;
+        kw = (t % 2) * 2 + r / 32;
+        ci = r % 32;
+      } else {
+        const int t = k / Cin_real;
+        ci = k % Cin_real;
+        kh = t / 4;
+        kw = t % 4;
+      }
+      float v = ci < Cin_real ? __ldg(w + (((int64_t)co * Cin_real + ci) * 4 + kh) * 4 + kw) : 0.f;
+      wf[i] = __float2bfloat16(v);
+    } else if (i < nf + nd) {
+      const int64_t j = i - nf;
+      const int k = (int)(j % Kd);
+      const int ci = (int)((j / Kd) % Cin_rows);
+      const int z = (int)(j / ((int64_t)Kd * Cin_rows));
+      const int rh = z / 2, rw = z % 2;
+      const int t = k / Cout, co = k % Cout;
+      const int th = t / 2, tw = t % 2;
+      const int kh = rh == 0 ? (th == 0 ? 1 : 3) : (th == 0 ? 0 : 2);
+      const int kw = rw == 0 ? (tw == 0 ? 1 : 3) : (tw == 0 ? 0 : 2);
+      float v = ci < Cin_real ? __ldg(w + (((int64_t)co * Cin_real + ci) * 4 + kh) * 4 + kw) : 0.f;
+      wd[j] = __float2bfloat16(v);
+    } else {
+      const int co = (int)(i - nf - nd);
+      bias[co] = __ldg(b + co);
+    }
+  }
+}
+
+// classifier weights [1][C][4][4] -> fp32 [16][C]
+__global__ void __launch_bounds__(256)
+fcd_pack_cls_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wc,
+                    float* __restrict__ bc, int C) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < 16 * C; i += gridDim.x * 256) {
+    const int t = i / C, c = i % C;
+    wc[i] = __ldg(w + (int64_t)c * 16 + t);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) bc[0] = __ldg(b);
+}
+
+// ---- classifier (N = 1 output channel): CUDA-core reductions ------------------------------------
+// out[n][oh][ow] = bc + sum_{kh,kw,c} A4[n][2oh-1+kh][2ow-1+kw][c] * wc[kh*4+kw][c]; one warp per output
+__global__ void __launch_bounds__(256)
+fcd_cls_fwd_kernel(const __nv_bfloat16* __restrict__ a4, const float* __restrict__ wc, const float* __restrict__ bc,
+                   float* __restrict__ out, int N, int H4, int W4, int C, int H5, int W5) {
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N * H5 * W5) return;
+  const int ow = warp % W5, oh = (warp / W5) % H5, n = warp / (W5 * H5);
+  float acc = 0.f;
+  for (int kh = 0; kh < 4; ++kh) {
+    const int ih = 2 * oh - 1 + kh;
+    if ((unsigned)ih >= (unsigned)H4) continue;
+    for (int kw = 0; kw < 4; ++kw) {
+      const int iw = 2 * ow - 1 + kw;
+      if ((unsigned)iw >= (unsigned)W4) continue;
+      const __nv_bfloat16* src = a4 + (((int64_t)n * H4 + ih) * W4 + iw) * C;
+      const float* wt = wc + (kh * 4 + kw) * C;
+      for (int c = lane * 2; c < C; c += 64) {
+        __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + c);
+        acc = fmaf(__low2float(v), __ldg(wt + c), acc);
+        acc = fmaf(__high2float(v), __ldg(wt + c + 1), acc);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[warp] = acc + __ldg(bc);
+}
+
+// dPre4[n][ih][iw][c] = mask(A4) * sum_{kh,kw valid} dout[n][oh][ow] * wc[kh*4+kw][c]
+__global__ void __launch_bounds__(256)
+fcd_cls_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ wc,
+                     const __nv_bfloat16* __restrict__ a4, __nv_bfloat16* __restrict__ dpre4, int N, int H4, int W4,
+                     int C, int H5, int W5) {
+  const int64_t total = (int64_t)N * H4 * W4 * (C / 2);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int c = (int)(i % (C / 2)) * 2;
+    const int64_t px = i / (C / 2);
+    const int iw = (int)(px % W4), ih = (int)((px / W4) % H4), n = (int)(px / ((int64_t)W4 * H4));
+    float g0 = 0.f, g1 = 0.f;
+    for (int kh = (ih + 1) & 1; kh < 4; kh += 2) {
+      const int oh = (ih + 1 - kh) / 2;
+      if (ih + 1 - kh < 0 || oh >= H5) continue;
+      for (int kw = (iw + 1) & 1; kw < 4; kw += 2) {
+        const int ow = (iw + 1 - kw) / 2;
+        if (iw + 1 - kw < 0 || ow >= W5) continue;
+        const float d = __ldg(dout + ((int64_t)n * H5 + oh) * W5 + ow);
+        g0 = fmaf(d, __ldg(wc + (kh * 4 + kw) * C + c), g0);
+        g1 = fmaf(d, __ldg(wc + (kh * 4 + kw) * C + c + 1), g1);
+      }
+    }
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(a4 + px * C + c);
+    g0 *= __low2float(a) > 0.f ? 1.f : FCD_SLOPE;
+    g1 *= __high2float(a) > 0.f ? 1.f : FCD_SLOPE;
+    *reinterpret_cast<__nv_bfloat162*>(dpre4 + px * C + c) = __floats2bfloat162_rn(g0, g1);
+  }
+}
+
+// dwc[0][c][kh][kw] = sum_{n,oh,ow} dout * A4[n][2oh-1+kh][2ow-1+kw][c]
+__global__ void __launch_bounds__(256)
+fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a4, float* __restrict__ dw,
+                     int N, int H4, int W4, int C, int H5, int W5) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= 16 * C) return;
+  const int c = i % C, t = i / C;
+  const int kh = t / 4, kw = t % 4;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n)
+    for (int oh = 0; oh < H5; ++oh) {
+      const int ih = 2 * oh - 1 + kh;
+      if ((unsigned)ih >= (unsigned)H4) continue;
+      for (int ow = 0; ow < W5; ++ow) {
+        const int iw = 2 * ow - 1 + kw;
+        if ((unsigned)iw >= (unsigned)W4) continue;
+        acc = fmaf(__ldg(dout + ((int64_t)n * H5 + oh) * W5 + ow),
+                   __bfloat162float(a4[(((int64_t)n * H4 + ih) * W4 + iw) * C + c]), acc);
+      }
+    }
+  dw[(int64_t)c * 16 + t] = acc;
+}
+
+// ---- reductions over pixels -------------------------------------------------------------------
+// partial[r][c] = sum over the r-th slice of rows of src[row][c] (bf16 [P][C]); then db[c] = sum_r
+__global__ void __launch_bounds__(256)
+fcd_colsum_partial_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int64_t P, int C,
+                          int rows_per_cta) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(P, r0 + rows_per_cta);
+  const int pairs = C / 2;
+  const int tpr = pairs < 256 ? pairs : 256;
+  const int nsub = 256 / tpr;
+  const int sub = threadIdx.x / tpr;
+  if (sub >= nsub) return;
+  for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int64_t r = r0 + sub; r < r1; r += nsub) {
+      __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * C + cp * 2);
+      a0 += __low2float(v);
+      a1 += __high2float(v);
+    }
+    float* dst = partial + ((int64_t)blockIdx.x * nsub + sub) * C + cp * 2;
+    dst[0] = a0;
+    dst[1] = a1;
+  }
+}
+__global__ void __launch_bounds__(256)
+fcd_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int R, int C) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) acc += partial[(int64_t)r * C + c];
+  out[c] = acc;
+}
+
+// dW_l[co][ci][kh][kw] = sum_z part[z][tap][co][col]
+__global__ void __launch_bounds__(256)
+fcd_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int l, int Cout, int Cin_real,
+                        int Ncols) {
+  const int taps = l == 1 ? 8 : 16;
+  const int64_t total = (int64_t)Cout * Cin_real * 16;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int kw = (int)(i % 4), kh = (int)((i / 4) % 4);
+    const int ci = (int)((i / 16) % Cin_real);
+    const int co = (int)(i / ((int64_t)16 * Cin_real));
+    int tap, col;
+    if (l == 1) {
+      tap = kh * 2 + kw / 2;
+      col = (kw % 2) * 32 + ci;
+    } else {
+      tap = kh * 4 + kw;
+      col = ci;
+    }
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += __ldg(part + (((int64_t)s * taps + tap) * Cout + co) * Ncols + col);
+    dw[i] = acc;
+  }
+}
+
+// ---- tcgen05 launches ---------------------------------------------------------------------------
+static int block_n_for(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : 32)); }
+
+// parity view (rh, rw) of an NHWC tensor [N][Hin][Win][C]
+static int encode_parity(CUtensorMap* m, const __nv_bfloat16* base, int N, int Hin, int Win, int C, int rh, int rw,
+                         int th, int tw) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)((Win - rw + 1) / 2), (uint64_t)((Hin - rh + 1) / 2), (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)2 * C * 2, (uint64_t)2 * Win * C * 2, (uint64_t)Hin * Win * C * 2};
+  return umma::encode_4d(m, base + ((int64_t)rh * Win + rw) * C, dims, str, tw, th);
+}
+// pair view (row parity rh) of the packed input [N][H][W0p][32] seen as [N][H][W0p/2][64]
+static int encode_pair(CUtensorMap* m, const __nv_bfloat16* base, int N, int H, int W0p, int rh, int th, int tw) {
+  uint64_t dims[4] = {64, (uint64_t)(W0p / 2), (uint64_t)((H - rh + 1) / 2), (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)64 * 2, (uint64_t)2 * W0p * 32 * 2, (uint64_t)H * W0p * 32 * 2};
+  return umma::encode_4d(m, base + (int64_t)rh * W0p * 32, dims, str, tw, th);
+}
+static int encode_plain(CUtensorMap* m, const __nv_bfloat16* base, int N, int H, int W, int C, int th, int tw) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  return umma::encode_4d(m, base, dims, str, tw, th);
+}
+
+static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv_bfloat16* wf, const float* bias,
+                    __nv_bfloat16* out, cudaStream_t st) {
+  using namespace umma;
+  const int OH = p.H[l], OW = p.W[l], Cout = p.C[l];
+  int th = 1, tw = 128;
+  pick_tile(OH, OW, 128, &th, &tw);
+  CUtensorMap maps[5];
+  Params P;
+  memset(&P, 0, sizeof(P));
+  int rc;
+  if (l == 1) {
+    for (int r = 0; r < 2; ++r)
+      if ((rc = encode_pair(&maps[r], in, p.N, p.H[0], p.W0p, r, th, tw))) return rc;
+    maps[2] = maps[3] = maps[0];
+    P.c_chunks = 1;
+    P.taps = 8;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int pw = 0; pw < 2; ++pw) {
+        P.tap_map[kh * 2 + pw] = tap_r(kh);
+        P.tap_dh[kh * 2 + pw] = tap_a(kh);
+        P.tap_dw[kh * 2 + pw] = pw;
+      }
+  } else {
+    const int Cin = p.C[l - 1];
+    for (int rh = 0; rh < 2; ++rh)
+      for (int rw = 0; rw < 2; ++rw)
+        if ((rc = encode_parity(&maps[rh * 2 + rw], in, p.N, p.H[l - 1], p.W[l - 1], Cin, rh, rw, th, tw))) return rc;
+    P.c_chunks = Cin / 64;
+    P.taps = 16;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        P.tap_map[kh * 4 + kw] = tap_r(kh) * 2 + tap_r(kw);
+        P.tap_dh[kh * 4 + kw] = tap_a(kh);
+        P.tap_dw[kh * 4 + kw] = tap_a(kw);
+      }
+  }
+  const int K = P.taps * P.c_chunks * 64;
+  const int bn = block_n_for(Cout);
+  if ((rc = encode_2d(&maps[4], wf, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)bn))) return rc;
+  P.M = 0;
+  P.N = Cout;
+  P.k_steps = P.taps * P.c_chunks;
+  P.steps_per_split = P.k_steps;
+  P.tw = tw; P.th = th;
+  P.tiles_w = cdiv(OW, tw); P.tiles_h = cdiv(OH, th);
+  P.b_rows_per_z = 0;
+  P.epi = EPI_BF16;
+  P.out = out;
+  P.ld_out = Cout;
+  P.oh_ext[0] = OH; P.ow_ext[0] = OW;
+  P.out_h = OH; P.out_w = OW;
+  P.sy = P.sx = 1;
+  P.bias = bias;
+  P.slope = FCD_SLOPE;
+  P.mask_src = nullptr;
+  P.mask_slope = 1.f;
+  dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(Cout, bn), 1);
+  return launch(MODE_CONV, bn, maps, P, grid, st);
+}
+
+// dIn (= dPre_{l-1} after the LeakyReLU mask, or dA0 for l == 1) from dPre_l
+static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* wd,
+                      const __nv_bfloat16* act_in, __nv_bfloat16* din, cudaStream_t st) {
+  using namespace umma;
+  const int Hin = p.H[l - 1], Win = p.W[l - 1], Hout = p.H[l], Wout = p.W[l], Cout = p.C[l];
+  const int rows = l == 1 ? 32 : p.C[l - 1];
+  const int eh = (Hin + 1) / 2, ew = (Win + 1) / 2;  // largest parity class
+  int th = 1, tw = 128;
+  pick_tile(eh, ew, 128, &th, &tw);
+  CUtensorMap maps[5];
+  int rc;
+  if ((rc = encode_plain(&maps[0], dpre, p.N, Hout, Wout, Cout, th, tw))) return rc;
+  maps[1] = maps[2] = maps[3] = maps[0];
+  const int K = 4 * Cout;
+  const int bn = block_n_for(rows);
+  if ((rc = encode_2d(&maps[4], wd, (uint64_t)K, (uint64_t)4 * rows, (uint64_t)K * 2, (uint32_t)bn))) return rc;
+  Params P;
+  memset(&P, 0, sizeof(P));
+  P.N = rows;
+  P.c_chunks = Cout / 64;
+  P.taps = 4;
+  P.k_steps = 4 * P.c_chunks;
+  P.steps_per_split = P.k_steps;
+  P.tw = tw; P.th = th;
+  P.tiles_w = cdiv(ew, tw); P.tiles_h = cdiv(eh, th);
+  for (int z = 0; z < 4; ++z) {
+    const int rh = z / 2, rw = z % 2;
+    for (int t = 0; t < 4; ++t) {
+      const int thh = t / 2, tww = t % 2;
+      // rh = 0: kh in {1,3} -> oh = i, i-1 ; rh = 1: kh in {0,2} -> oh = i+1, i
+      P.tap_map[z * 4 + t] = 0;
+      P.tap_dh[z * 4 + t] = rh == 0 ? (thh == 0 ? 0 : -1) : (thh == 0 ? 1 : 0);
+      P.tap_dw[z * 4 + t] = rw == 0 ? (tww == 0 ? 0 : -1) : (tww == 0 ? 1 : 0);
+    }
+    P.oh_ext[z] = (Hin - rh + 1) / 2;
+    P.ow_ext[z] = (Win - rw + 1) / 2;
+    P.oy[z] = rh;
+    P.ox[z] = rw + (l == 1 ? 1 : 0);  // packed input: pixel w lives at padded column w + 1
+  }
+  P.b_rows_per_z = rows;
+  P.epi = EPI_BF16;
+  P.out = din;
+  P.ld_out = rows;
+  P.out_h = Hin;
+  P.out_w = l == 1 ? p.W0p : Win;
+  P.sy = P.sx = 2;
+  P.bias = nullptr;
+  P.slope = 1.f;
+  P.mask_src = l == 1 ? nullptr : act_in;
+  P.mask_slope = FCD_SLOPE;
+  dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(rows, bn), 4);
+  return launch(MODE_CONV, bn, maps, P, grid, st);
+}
+
+static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* act_in, float* part,
+                      float* dw, cudaStream_t st) {
+  using namespace umma;
+  const int Hout = p.H[l], Wout = p.W[l], Cout = p.C[l];
+  int th = 1, tw = 64;
+  pick_tile(Hout, Wout, 64, &th, &tw);
+  CUtensorMap maps[5];
+  int rc;
+  if ((rc = encode_plain(&maps[0], dpre, p.N, Hout, Wout, Cout, th, tw))) return rc;
+  Params P;
+  memset(&P, 0, sizeof(P));
+  const int nn = wgrad_n(p, l);
+  if (l == 1) {
+    if ((rc = encode_pair(&maps[4], act_in, p.N, p.H[0], p.W0p, 0, th, tw))) return rc;
+    if ((rc = encode_pair(&maps[1], act_in, p.N, p.H[0], p.W0p, 1, th, tw))) return rc;
+    maps[2] = maps[3] = maps[1];
+    P.taps = 8;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int pw = 0; pw < 2; ++pw) {
+        P.tap_map[kh * 2 + pw] = tap_r(kh);
+        P.tap_dh[kh * 2 + pw] = tap_a(kh);
+        P.tap_dw[kh * 2 + pw] = pw;
+      }
+  } else {
+    const int Cin = p.C[l - 1];
+    CUtensorMap pm[4];
+    for (int rh = 0; rh < 2; ++rh)
+      for (int rw = 0; rw < 2; ++rw)
+        if ((rc = encode_parity(&pm[rh * 2 + rw], act_in, p.N, p.H[l - 1], p.W[l - 1], Cin, rh, rw, th, tw))) return rc;
+    maps[4] = pm[0]; maps[1] = pm[1]; maps[2] = pm[2]; maps[3] = pm[3];
+    P.taps = 16;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        P.tap_map[kh * 4 + kw] = tap_r(kh) * 2 + tap_r(kw);
+        P.tap_dh[kh * 4 + kw] = tap_a(kh);
+        P.tap_dw[kh * 4 + kw] = tap_a(kw);
+      }
+  }
+  const int bn = nn >= 256 ? 256 : nn;
+  P.M = Cout;
+  P.N = nn;
+  P.tw = tw; P.th = th;
+  P.tiles_w = cdiv(Wout, tw); P.tiles_h = cdiv(Hout, th);
+  P.k_steps = p.N * P.tiles_h * P.tiles_w;
+  P.steps_per_split = cdiv(P.k_steps, p.split[l]);
+  const int S = cdiv(P.k_steps, P.steps_per_split);
+  P.a_boxes = Cout <= 64 ? 1 : 2;
+  P.epi = EPI_F32;
+  P.out = part;
+  P.ld_out = nn;
+  P.tap_stride_out = (long long)Cout * nn;
+  P.z_stride_out = (long long)P.taps * Cout * nn;
+  P.slope = 1.f;
+  dim3 grid(cdiv(Cout, 128) * cdiv(nn, bn), P.taps, S);
+  if ((rc = launch(MODE_WGRAD, bn, maps, P, grid, st))) return rc;
+  const int cin_real = l == 1 ? p.n_cls : p.C[l - 1];
+  fcd_wgrad_reduce_kernel<<<wave_grid((int64_t)Cout * cin_real * 16, 256, 8), 256, 0, st>>>(part, dw, S, l, Cout,
+                                                                                             cin_real, nn);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+static int col_sum(const __nv_bfloat16* src, float* partial, float* out, int64_t P, int C, cudaStream_t st) {
+  const int tpr = C / 2 < 256 ? C / 2 : 256;   // threads per row
+  const int sub = 256 / tpr;                    // row subsets per CTA
+  int64_t ctas = 2 * (int64_t)sm_count();
+  if (ctas > (P + 63) / 64) ctas = (P + 63) / 64;
+  const int64_t cap = (int64_t)256 * 2048 / ((int64_t)sub * C);  // partial buffer: 512K floats
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  const int rows_per_cta = (int)((P + ctas - 1) / ctas);
+  ctas = (P + rows_per_cta - 1) / rows_per_cta;
+  fcd_colsum_partial_kernel<<<(unsigned)ctas, 256, 0, st>>>(src, partial, P, C, rows_per_cta);
+  ASN_LAUNCH_CHECK();
+  fcd_colsum_final_kernel<<<cdiv(C, 256), 256, 0, st>>>(partial, out, (int)ctas * sub, C);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+}  // namespace asn
+
+using namespace asn;
+
+extern "C" size_t asn_fcd_wpack_bytes(int n_cls, int ndf) {
+  FcdPlan p;
+  if (make_plan(p, 1, n_cls, ndf, 64, 64)) return 0;
+  return p.wpack_total;
+}
+extern "C" size_t asn_fcd_acts_bytes(int N, int n_cls, int ndf, int H, int W) {
+  FcdPlan p;
+  if (make_plan(p, N, n_cls, ndf, H, W)) return 0;
+  return p.acts_total;
+}
+extern "C" size_t asn_fcd_workspace_bytes(int N, int n_cls, int ndf, int H, int W) {
+  FcdPlan p;
+  if (make_plan(p, N, n_cls, ndf, H, W)) return 0;
+  return p.ws_total;
+}
+
+extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, int ndf, void* wpack, void* stream) {
+  ASN_CHECK_ARG(params_host && wpack, "asn_fcd_pack_weights: null pointer");
+  FcdPlan p;
+  int rc = make_plan(p, 1, n_cls, ndf, 64, 64);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(wpack);
+  for (int l = 1; l <= 4; ++l) {
+    const float* w = params_host[2 * (l - 1)];
+    const float* b = params_host[2 * (l - 1) + 1];
+    ASN_CHECK_ARG(w && b, "asn_fcd_pack_weights: null parameter %d", l);
+    const int cin_real = l == 1 ? n_cls : p.C[l - 1];
+    const int rows = l == 1 ? 32 : p.C[l - 1];
+    const int64_t total = (int64_t)p.C[l] * (l == 1 ? 512 : 16 * cin_real) + (int64_t)16 * rows * p.C[l] + p.C[l];
+    fcd_pack_conv_kernel<<<wave_grid(total, 256, 8), 256, 0, st>>>(
+        w, b, reinterpret_cast<__nv_bfloat16*>(base + p.wf_off[l]), reinterpret_cast<__nv_bfloat16*>(base + p.wd_off[l]),
+        reinterpret_cast<float*>(base + p.bias_off[l]), l, p.C[l], cin_real, rows);
+    ASN_LAUNCH_CHECK();
+  }
+  ASN_CHECK_ARG(params_host[8] && params_host[9], "asn_fcd_pack_weights: null classifier parameter");
+  fcd_pack_cls_kernel<<<cdiv(16 * p.C[4], 256), 256, 0, st>>>(params_host[8], params_host[9],
+                                                               reinterpret_cast<float*>(base + p.wc_off),
+                                                               reinterpret_cast<float*>(base + p.bc_off), p.C[4]);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpack, void* acts, float* out, int N,
+                           int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  ASN_CHECK_ARG(x_nchw && wpack && acts && out, "asn_fcd_fwd: null pointer");
+  FcdPlan p;
+  int rc = make_plan(p, N, n_cls, ndf, H, W);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* wb = static_cast<const uint8_t*>(wpack);
+  uint8_t* ab = static_cast<uint8_t*>(acts);
+  __nv_bfloat16* A[5];
+  for (int l = 0; l <= 4; ++l) A[l] = reinterpret_cast<__nv_bfloat16*>(ab + p.act_off[l]);
+  fcd_pack_input_kernel<<<wave_grid((int64_t)N * H * p.W0p, 256, 8), 256, 0, st>>>(x_nchw, A[0], N, n_cls, H, W, p.W0p,
+                                                                                   x_is_logits);
+  ASN_LAUNCH_CHECK();
+  for (int l = 1; l <= 4; ++l) {
+    rc = conv_fwd(p, l, A[l - 1], reinterpret_cast<const __nv_bfloat16*>(wb + p.wf_off[l]),
+                  reinterpret_cast<const float*>(wb + p.bias_off[l]), A[l], st);
+    if (rc) return rc;
+  }
+  const int n_out = N * p.H[5] * p.W[5];
+  fcd_cls_fwd_kernel<<<cdiv((int64_t)n_out * 32, 256), 256, 0, st>>>(
+      A[4], reinterpret_cast<const float*>(wb + p.wc_off), reinterpret_cast<const float*>(wb + p.bc_off), out, N, p.H[4],
+      p.W[4], p.C[4], p.H[5], p.W[5]);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void* wpack, const void* acts,
+                           float* dx_nchw, float* const* dparams_host, int N, int n_cls, int ndf, int H, int W,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  ASN_CHECK_ARG(dout && wpack && acts && workspace, "asn_fcd_bwd: null pointer");
+  FcdPlan p;
+  int rc = make_plan(p, N, n_cls, ndf, H, W);
+  if (rc) return rc;
+  if (workspace_bytes < p.ws_total) {
+    set_error("asn_fcd_bwd: workspace %zu < %zu", workspace_bytes, p.ws_total);
+    return ASN_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* wb = static_cast<const uint8_t*>(wpack);
+  const uint8_t* ab = static_cast<const uint8_t*>(acts);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const __nv_bfloat16* A[5];
+  for (int l = 0; l <= 4; ++l) A[l] = reinterpret_cast<const __nv_bfloat16*>(ab + p.act_off[l]);
+  __nv_bfloat16* dPre[5];
+  for (int l = 1; l <= 4; ++l) dPre[l] = reinterpret_cast<__nv_bfloat16*>(ws + p.dpre_off[l]);
+  __nv_bfloat16* dA0 = reinterpret_cast<__nv_bfloat16*>(ws + p.da0_off);
+  float* part = reinterpret_cast<float*>(ws + p.part_off);
+  float* dbpart = reinterpret_cast<float*>(ws + p.dbpart_off);
+  const float* wc = reinterpret_cast<const float*>(wb + p.wc_off);
+
+  // classifier
+  fcd_cls_dgrad_kernel<<<wave_grid((int64_t)N * p.H[4] * p.W[4] * (p.C[4] / 2), 256, 8), 256, 0, st>>>(
+      dout, wc, A[4], dPre[4], N, p.H[4], p.W[4], p.C[4], p.H[5], p.W[5]);
+  ASN_LAUNCH_CHECK();
+  if (dparams_host) {
+    ASN_CHECK_ARG(dparams_host[8] && dparams_host[9], "asn_fcd_bwd: null classifier gradient");
+    fcd_cls_wgrad_kernel<<<cdiv(16 * p.C[4], 256), 256, 0, st>>>(dout, A[4], dparams_host[8], N, p.H[4], p.W[4], p.C[4],
+                                                                  p.H[5], p.W[5]);
+    ASN_LAUNCH_CHECK();
+    if ((rc = channel_sum_nchw(dout, dparams_host[9], N, 1, p.H[5] * p.W[5], st))) return rc;
+  }
+  for (int l = 4; l >= 1; --l) {
+    if (dparams_host) {
+      float* dw = dparams_host[2 * (l - 1)];
+      float* db = dparams_host[2 * (l - 1) + 1];
+      ASN_CHECK_ARG(dw && db, "asn_fcd_bwd: null gradient pointer for layer %d", l);
+      if ((rc = conv_wgrad(p, l, dPre[l], A[l - 1], part, dw, st))) return rc;
+      if ((rc = col_sum(dPre[l], dbpart, db, (int64_t)N * p.H[l] * p.W[l], p.C[l], st))) return rc;
+    }
+    if (l > 1 || dx_nchw) {
+      rc = conv_dgrad(p, l, dPre[l], reinterpret_cast<const __nv_bfloat16*>(wb + p.wd_off[l]), A[l - 1],
+                      l == 1 ? dA0 : dPre[l - 1], st);
+      if (rc) return rc;
+    }
+  }
+  if (dx_nchw) {
+    fcd_unpack_dx_kernel<<<wave_grid((int64_t)N * H * W, 256, 8), 256, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls, H, W,
+                                                                                p.W0p);
+    ASN_LAUNCH_CHECK();
+  }
+  return ASN_OK;
+}

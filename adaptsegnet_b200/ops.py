@@ -427,3 +427,125 @@ def aspp_head(x, weights, biases, dilations, n_active, pack: AsppWeightPack | No
         return _AsppHeadF32.apply(x, tuple(dilations), n_active, *weights, *biases)
     pack = pack if pack is not None else AsppWeightPack()
     return _AsppHeadTC.apply(x, pack, tuple(dilations), n_active, *weights, *biases)
+
+
+# --------------------------------------------------------------------------------------
+# K5 FCDiscriminator
+# --------------------------------------------------------------------------------------
+FCD_LAYERS = ("conv1", "conv2", "conv3", "conv4", "classifier")
+LRELU_SLOPE = 0.2  # model/discriminator.py:16
+
+
+class FcdWeightPack:
+    """bf16 implicit-GEMM shadows of the discriminator's fp32 OIHW parameters
+    (asn_fcd_pack_weights); rebuilt when a parameter's version counter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, params, n_cls, ndf):
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            lib = _lib.load()
+            nbytes = lib.asn_fcd_wpack_bytes(n_cls, ndf)
+            if nbytes == 0:
+                raise _lib.AsnError(f"FCDiscriminator(num_classes={n_cls}, ndf={ndf}) is outside the tensor-core "
+                                    "path (needs num_classes <= 32, ndf a multiple of 64); use ASN_PRECISION=fp32")
+            self.buf = _ws(nbytes, params[0].device)
+            ps = [_req(p.detach(), torch.float32, "parameter") for p in params]
+            check(lib.asn_fcd_pack_weights(_lib.ptr_array([p.data_ptr() for p in ps]), n_cls, ndf,
+                                           self.buf.data_ptr(), _stream()), "asn_fcd_pack_weights")
+            _count(5)
+            self.key = key
+        return self.buf
+
+
+class _FcdTC(torch.autograd.Function):
+    """tcgen05 path: asn_fcd_fwd / asn_fcd_bwd.  params = (conv1.w, conv1.b, ..., classifier.w, classifier.b)"""
+
+    @staticmethod
+    def forward(ctx, x, pack, x_is_logits, *params):
+        x = _req(x, torch.float32, "x")
+        N, n_cls, H, W = x.shape
+        ndf = params[0].shape[0]
+        lib = _lib.load()
+        wpack = pack.get(params, n_cls, ndf)
+        acts = _ws(lib.asn_fcd_acts_bytes(N, n_cls, ndf, H, W), x.device)
+        if acts.numel() <= 16:
+            raise _lib.AsnError(f"FCDiscriminator input {H}x{W} is outside the tensor-core path (needs >= 32x32)")
+        oh, ow = H, W
+        for _ in range(5):
+            oh, ow = (oh + 2 - 4) // 2 + 1, (ow + 2 - 4) // 2 + 1
+        out = torch.empty((N, 1, oh, ow), dtype=torch.float32, device=x.device)
+        check(lib.asn_fcd_fwd(x.data_ptr(), int(x_is_logits), wpack.data_ptr(), acts.data_ptr(), out.data_ptr(), N,
+                              n_cls, ndf, H, W, None, 0, _stream()), "asn_fcd_fwd")
+        _count(6)
+        ctx.save_for_backward(x if x_is_logits else torch.empty(0, device=x.device), wpack, acts)
+        ctx.cfg = (N, n_cls, ndf, H, W, bool(x_is_logits), tuple(p.shape for p in params))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wpack, acts = ctx.saved_tensors
+        N, n_cls, ndf, H, W, x_is_logits, pshapes = ctx.cfg
+        dout = _req(dout, torch.float32, "dout")
+        lib = _lib.load()
+        need_x = ctx.needs_input_grad[0]
+        need_p = any(ctx.needs_input_grad[3:])
+        nbytes = lib.asn_fcd_workspace_bytes(N, n_cls, ndf, H, W)
+        ws = _ws(nbytes, dout.device)
+        dx = torch.empty((N, n_cls, H, W), dtype=torch.float32, device=dout.device) if need_x else None
+        dps = [torch.empty(s, dtype=torch.float32, device=dout.device) for s in pshapes] if need_p else None
+        check(lib.asn_fcd_bwd(dout.data_ptr(), x.data_ptr() if x_is_logits else None, wpack.data_ptr(),
+                              acts.data_ptr(), dx.data_ptr() if need_x else None,
+                              _lib.ptr_array([t.data_ptr() for t in dps]) if need_p else None, N, n_cls, ndf, H, W,
+                              ws.data_ptr(), nbytes, _stream()), "asn_fcd_bwd")
+        _count(1 + (3 if need_p else 0) + 4 * (4 if need_p else 0) + 4 + (1 if need_x else 0))
+        return (dx, None, None, *(dps if need_p else [None] * len(pshapes)))
+
+
+class _FcdF32(torch.autograd.Function):
+    """fp32 CUDA-core path (ASN_PRECISION=fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        h = _req(x, torch.float32, "x")
+        acts = []
+        for i in range(4):
+            h = conv2d_fwd_f32(h, params[2 * i], params[2 * i + 1], 2, 1, 1, LRELU_SLOPE)
+            acts.append(h)
+        out = conv2d_fwd_f32(h, params[8], params[9], 2, 1, 1, 1.0)
+        ctx.save_for_backward(x, *acts, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = ctx.saved_tensors
+        x, acts, params = saved[0], list(saved[1:5]), saved[5:]
+        need_x = ctx.needs_input_grad[0]
+        need_p = any(ctx.needs_input_grad[1:])
+        inputs = [x] + acts
+        g = _req(dout, torch.float32, "dout")
+        grads = [None] * 10
+        for li in range(4, -1, -1):
+            w = params[2 * li]
+            if li < 4:
+                g = lrelu_bwd_f32(g, acts[li], LRELU_SLOPE)
+            if need_p:
+                grads[2 * li], grads[2 * li + 1] = conv2d_wgrad_f32(inputs[li], g, w.shape, 2, 1, 1, True)
+            if li > 0 or need_x:
+                g = conv2d_dgrad_f32(g, w, inputs[li].shape, 2, 1, 1)
+        return (g if need_x else None, *grads)
+
+
+def fcd_forward(x, params, pack: FcdWeightPack | None = None, x_is_logits: bool = False):
+    """FCDiscriminator.forward (model/discriminator.py:21-34).  With x_is_logits the channel softmax
+    F.softmax(x) of train_gta2cityscapes_multi.py:617-618 is fused into the input pack (bf16 path)."""
+    params = tuple(params)
+    if precision_mode() == "fp32":
+        if x_is_logits:
+            x = softmax_channels(x)
+        return _FcdF32.apply(x, *params)
+    pack = pack if pack is not None else FcdWeightPack()
+    return _FcdTC.apply(x, pack, bool(x_is_logits), *params)

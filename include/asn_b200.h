@@ -178,7 +178,9 @@ ASN_API int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const float*
  *   CUDA-core reduction.  Requires ndf % 64 == 0 (reference default ndf = 64), C_in <= 32.
  *   Weights are packed once per optimizer step by asn_fcd_pack_weights into `wpack`.
  *   The forward keeps its bf16 activations in `acts` (asn_fcd_acts_bytes) for the backward.
- *   bwd: dx (nullable: D-step, input detached) and/or dparams (nullable: G-step, parameters
+ *   bwd: x_logits (nullable): when the forward ran with x_is_logits, pass the same logits and
+ *   dx is the gradient w.r.t. them (softmax backward fused).
+ *   dx (nullable: D-step, input detached) and/or dparams (nullable: G-step, parameters
  *   frozen) -- host array of 10 device pointers {conv1.w, conv1.b, ..., classifier.w,
  *   classifier.b}, fp32, same shapes as the parameters, overwritten.
  * ---------------------------------------------------------------------------------- */
@@ -191,7 +193,7 @@ ASN_API size_t asn_fcd_workspace_bytes(int N, int n_cls, int ndf, int H, int W);
 ASN_API int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpack, void* acts, float* out,
                 int N, int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes,
                 void* stream);
-ASN_API int asn_fcd_bwd(const float* dout, const void* wpack, const void* acts, float* dx_nchw,
+ASN_API int asn_fcd_bwd(const float* dout, const float* x_logits, const void* wpack, const void* acts, float* dx_nchw,
                 float* const* dparams_host, int N, int n_cls, int ndf, int H, int W,
                 void* workspace, size_t workspace_bytes, void* stream);
 
