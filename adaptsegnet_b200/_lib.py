@@ -47,6 +47,7 @@ SIGNATURES = {
     "asn_fcd_pack_weights": (c_int, [PP, c_int, c_int, c_void_p, c_void_p]),
     "asn_fcd_acts_bytes": (c_size_t, [c_int] * 5),
     "asn_fcd_workspace_bytes": (c_size_t, [c_int] * 5),
+    "asn_fcd_act_layout": (c_int, [c_int] * 5 + [C.POINTER(c_int64)]),
     "asn_fcd_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_size_t, c_void_p]),
     "asn_fcd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PP, c_int, c_int, c_int, c_int, c_int,

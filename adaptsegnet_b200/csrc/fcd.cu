@@ -641,6 +641,20 @@ extern "C" size_t asn_fcd_workspace_bytes(int N, int n_cls, int ndf, int H, int 
   return p.ws_total;
 }
 
+extern "C" int asn_fcd_act_layout(int N, int n_cls, int ndf, int H, int W, int64_t* out_host) {
+  ASN_CHECK_ARG(out_host, "asn_fcd_act_layout: null pointer");
+  FcdPlan p;
+  int rc = make_plan(p, N, n_cls, ndf, H, W);
+  if (rc) return rc;
+  for (int l = 0; l <= 4; ++l) {
+    out_host[4 * l + 0] = (int64_t)p.act_off[l];
+    out_host[4 * l + 1] = p.H[l];
+    out_host[4 * l + 2] = l == 0 ? p.W0p : p.W[l];
+    out_host[4 * l + 3] = p.C[l];
+  }
+  return ASN_OK;
+}
+
 extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, int ndf, void* wpack, void* stream) {
   ASN_CHECK_ARG(params_host && wpack, "asn_fcd_pack_weights: null pointer");
   FcdPlan p;

@@ -539,6 +539,28 @@ class _FcdF32(torch.autograd.Function):
         return (g if need_x else None, *grads)
 
 
+def fcd_saved_activations(out: torch.Tensor):
+    """The post-LeakyReLU activations conv1..conv4 the forward saved for its backward, as fp32 NCHW
+    tensors (inspection / tests: backward parity is defined on the saved activations, exactly as
+    autograd defines it for the reference)."""
+    fn = out.grad_fn
+    if fn is None:
+        raise ValueError("output has no autograd history")
+    saved = fn.saved_tensors
+    if type(fn).__name__.startswith("_FcdF32"):
+        return [t.detach().clone() for t in saved[1:5]]
+    _x, _wpack, acts = saved
+    N, n_cls, ndf, H, W = fn.cfg[:5]
+    lay = (C.c_int64 * 20)()
+    check(_lib.load().asn_fcd_act_layout(N, n_cls, ndf, H, W, lay), "asn_fcd_act_layout")
+    res = []
+    for l in range(1, 5):
+        off, h, w, c = lay[4 * l], lay[4 * l + 1], lay[4 * l + 2], lay[4 * l + 3]
+        a = acts[off:off + N * h * w * c * 2].view(torch.bfloat16).view(N, h, w, c)
+        res.append(a.permute(0, 3, 1, 2).float().contiguous())
+    return res
+
+
 def fcd_forward(x, params, pack: FcdWeightPack | None = None, x_is_logits: bool = False):
     """FCDiscriminator.forward (model/discriminator.py:21-34).  With x_is_logits the channel softmax
     F.softmax(x) of train_gta2cityscapes_multi.py:617-618 is fused into the input pack (bf16 path)."""

@@ -189,6 +189,9 @@ ASN_API int asn_fcd_pack_weights(const float* const* params_host /* 10 device pt
                          int n_cls, int ndf, void* wpack, void* stream);
 ASN_API size_t asn_fcd_acts_bytes(int N, int n_cls, int ndf, int H, int W);
 ASN_API size_t asn_fcd_workspace_bytes(int N, int n_cls, int ndf, int H, int W);
+/* layout of `acts` for inspection / tests: out_host[4*l + {0,1,2,3}] = {byte offset, H_l, W_l, C_l} of
+ * the bf16 NHWC activation of level l = 0..4 (level 0 = packed input [N][H][W0p][32], W_0 = W0p). */
+ASN_API int asn_fcd_act_layout(int N, int n_cls, int ndf, int H, int W, int64_t* out_host);
 /* x_is_logits != 0 fuses the channel softmax (K4) into the input pack. */
 ASN_API int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpack, void* acts, float* out,
                 int N, int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes,
