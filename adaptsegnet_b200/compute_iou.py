@@ -1,0 +1,38 @@
+"""Confusion matrix / IoU behind the reference's ``compute_iou.py`` surface (fast_hist, per_class_iu)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def fast_hist(a, b, n):
+    """compute_iou.py:15-17.  numpy in -> numpy int64 (n, n) out, like the reference; CUDA tensors in ->
+    CUDA int64 tensor out (no host round trip).  The counting runs on the device either way."""
+    as_numpy = not isinstance(a, torch.Tensor)
+    if as_numpy:
+        a = np.ascontiguousarray(a)
+        b = np.ascontiguousarray(b)
+        if a.dtype not in (np.uint8, np.int32, np.int64):
+            a = a.astype(np.int64)
+        lab = torch.from_numpy(a.reshape(-1)).cuda(non_blocking=True)
+        prd = torch.from_numpy(b.astype(np.uint8, copy=False).reshape(-1)).cuda(non_blocking=True)
+    else:
+        lab, prd = a.reshape(-1), b.reshape(-1)
+    hist, overflow = ops.fast_hist(lab, prd, int(n))
+    if as_numpy:
+        if int(overflow.item()):
+            # np.bincount would return more than n*n bins and the reference's reshape raises
+            raise ValueError(f"cannot reshape array into shape ({n},{n})")
+        return hist.cpu().numpy()
+    return hist
+
+
+def per_class_iu(hist):
+    """compute_iou.py:20-21 (float64, 0/0 -> nan)."""
+    if isinstance(hist, torch.Tensor):
+        hist = hist.cpu().numpy()
+    hist = np.asarray(hist, dtype=np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))

@@ -1,0 +1,181 @@
+"""One AdaptSegNet training iteration on the new modules.
+
+The reference's loops live inside ``main()`` of train_gta2cityscapes_multi.py and cannot be called
+(SURVEY.md Q2); this module restates them operation for operation -- multi-level :560-683,
+single-level :373-464 -- on top of the drop-in modules, so the order of forwards, backwards,
+``requires_grad`` toggles, loss scalings and optimizer steps is the reference's.  Differences, all
+outside the arithmetic: the GAN target is a scalar instead of a CPU-built tensor (Q15), the losses
+stay on the device (no ``.item()`` sync per loss, Q16) and, under data parallelism, gradients are
+averaged once per optimizer right before ``step()``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .model.deeplab_multi import DeeplabMulti
+from .model.discriminator import FCDiscriminator
+from .utils.loss import GANLoss, SegCrossEntropy
+
+SOURCE_LABEL = 0  # train_gta2cityscapes_multi.py:364-365
+TARGET_LABEL = 1
+
+
+@dataclass
+class TrainConfig:
+    """defaults of train_gta2cityscapes_multi.py:24-69 (GAN / level as the BASELINE configs name them)"""
+    num_classes: int = 19
+    learning_rate: float = 2.5e-4
+    momentum: float = 0.9
+    weight_decay: float = 0.0005
+    learning_rate_D: float = 1e-4
+    power: float = 0.9
+    num_steps: int = 250000
+    iter_size: int = 1
+    lambda_seg: float = 0.1
+    lambda_adv_target1: float = 0.0002
+    lambda_adv_target2: float = 0.001
+    gan: str = "Vanilla"
+    level: str = "multi-level"  # or "single-level"
+    fuse_softmax: bool = True   # D(softmax(pred)) with the softmax fused into D's input pack
+
+
+def lr_poly(base_lr, it, max_iter, power):
+    """train_gta2cityscapes_multi.py:162-163"""
+    return base_lr * ((1 - float(it) / max_iter) ** power)
+
+
+class FlatGrads:
+    """All gradients of one optimizer as views into one flat fp32 buffer, so that data-parallel
+    averaging is a single NCCL all-reduce per optimizer per iteration."""
+
+    def __init__(self, params):
+        seen, uniq = set(), []
+        for p in params:
+            if id(p) not in seen and p.requires_grad:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        total = sum(p.numel() for p in uniq)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=uniq[0].device)
+        off = 0
+        for p in uniq:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+
+
+class AdaptSegTrainer:
+    """Holds G (DeeplabMulti), D1/D2 (FCDiscriminator), their optimizers and runs iterations."""
+
+    def __init__(self, cfg: TrainConfig | None = None, device="cuda", model=None, model_D1=None, model_D2=None):
+        self.cfg = cfg = cfg or TrainConfig()
+        self.device = torch.device(device)
+        self.multi = cfg.level == "multi-level"
+        self.model = (model or DeeplabMulti(cfg.num_classes)).to(self.device).train()
+        self.model_D2 = (model_D2 or FCDiscriminator(cfg.num_classes)).to(self.device).train()
+        self.model_D1 = (model_D1 or FCDiscriminator(cfg.num_classes)).to(self.device).train() if self.multi else None
+        # optimizers exactly as train...:532-540 (the duplicated trunk parameters included, Q11)
+        self.optimizer = torch.optim.SGD(self.model.optim_parameters(cfg), lr=cfg.learning_rate,
+                                         momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+        self.optimizer_D2 = torch.optim.Adam(self.model_D2.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
+        self.optimizer_D1 = (torch.optim.Adam(self.model_D1.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
+                             if self.multi else None)
+        self.bce_loss = GANLoss(cfg.gan)
+        self.seg_loss = SegCrossEntropy(ignore_index=255)
+        self.flat_G = FlatGrads(self.model.parameters())
+        self.flat_D2 = FlatGrads(self.model_D2.parameters())
+        self.flat_D1 = FlatGrads(self.model_D1.parameters()) if self.multi else None
+
+    # ---- pieces of the loop ------------------------------------------------------------------
+    def _adjust_lr(self, i_iter):
+        cfg = self.cfg
+        lr = lr_poly(cfg.learning_rate, i_iter, cfg.num_steps, cfg.power)
+        self.optimizer.param_groups[0]["lr"] = lr
+        self.optimizer.param_groups[1]["lr"] = lr * 10
+        lr_d = lr_poly(cfg.learning_rate_D, i_iter, cfg.num_steps, cfg.power)
+        for opt in (self.optimizer_D1, self.optimizer_D2):
+            if opt is not None:
+                opt.param_groups[0]["lr"] = lr_d
+
+    def _d_out(self, D, pred):
+        if self.cfg.fuse_softmax:
+            return D(pred, from_logits=True)
+        return D(ops.softmax_channels(pred))
+
+    @staticmethod
+    def _set_requires_grad(module, flag):
+        if module is not None:
+            for p in module.parameters():
+                p.requires_grad = flag
+
+    def step(self, src_images, src_labels, tgt_images, i_iter=0, group=None, do_optimizer_step=True):
+        """One iteration.  Returns the dict of (device) loss scalars the reference prints.
+        ``do_optimizer_step=False`` leaves the accumulated gradients in place (parity tests)."""
+        cfg = self.cfg
+        it = cfg.iter_size
+        self.flat_G.zero()
+        self.flat_D2.zero()
+        if self.multi:
+            self.flat_D1.zero()
+        self._adjust_lr(i_iter)
+        out = {}
+        # ---------------- train G: discriminators frozen (train...:583-587) ----------------
+        self._set_requires_grad(self.model_D1, False)
+        self._set_requires_grad(self.model_D2, False)
+        pred1, pred2 = self.model(src_images)
+        loss_seg2 = self.seg_loss(pred2, src_labels)
+        if self.multi:
+            loss_seg1 = self.seg_loss(pred1, src_labels)
+            loss = loss_seg2 + cfg.lambda_seg * loss_seg1
+            out["loss_seg1"] = loss_seg1.detach() / it
+        else:
+            loss = loss_seg2
+        (loss / it).backward()
+        out["loss_seg2"] = loss_seg2.detach() / it
+
+        pred_target1, pred_target2 = self.model(tgt_images)
+        loss_adv2 = self.bce_loss(self._d_out(self.model_D2, pred_target2), SOURCE_LABEL)
+        loss = cfg.lambda_adv_target2 * loss_adv2
+        if self.multi:
+            loss_adv1 = self.bce_loss(self._d_out(self.model_D1, pred_target1), SOURCE_LABEL)
+            loss = cfg.lambda_adv_target1 * loss_adv1 + loss
+            out["loss_adv_target1"] = loss_adv1.detach() / it
+        (loss / it).backward()
+        out["loss_adv_target2"] = loss_adv2.detach() / it
+
+        # ---------------- train D (train...:635-679) ----------------
+        self._set_requires_grad(self.model_D1, True)
+        self._set_requires_grad(self.model_D2, True)
+        levels = [(self.model_D2, pred2, pred_target2, "loss_D2")]
+        if self.multi:
+            levels.insert(0, (self.model_D1, pred1, pred_target1, "loss_D1"))
+        for D, p_src, p_tgt, name in levels:
+            l_src = self.bce_loss(self._d_out(D, p_src.detach()), SOURCE_LABEL) / it / 2
+            l_src.backward()
+            l_tgt = self.bce_loss(self._d_out(D, p_tgt.detach()), TARGET_LABEL) / it / 2
+            l_tgt.backward()
+            out[name] = l_src.detach() + l_tgt.detach()
+
+        # ---------------- data-parallel averaging, then the three optimizer steps ----------------
+        self.flat_G.all_reduce_mean(group)
+        self.flat_D2.all_reduce_mean(group)
+        if self.multi:
+            self.flat_D1.all_reduce_mean(group)
+        if do_optimizer_step:
+            self.optimizer.step()
+            if self.multi:
+                self.optimizer_D1.step()
+            self.optimizer_D2.step()
+        return out

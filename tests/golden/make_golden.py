@@ -244,7 +244,40 @@ def gold_argmax():
     save("argmax", x=x.numpy(), pred=output)
 
 
+def gold_step():
+    """whole multi-level / single-level iteration (train_gta2cityscapes_multi.py:560-683, :373-464) driven
+    through oracle/torch_ref.RefTrainer's restated loop with the REFERENCE's own modules injected."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import torch_ref as TR
+    from model.deeplab_multi import DeeplabMulti
+
+    out = {}
+    for level, gan in (("multi-level", "Vanilla"), ("single-level", "LS")):
+        tag = "multi" if level == "multi-level" else "single"
+        G = TR.seeded_init_(DeeplabMulti(19), SEED)
+        D1 = TR.seeded_init_(FCDiscriminator(19), SEED + 1)
+        D2 = TR.seeded_init_(FCDiscriminator(19), SEED + 2)
+        tr = TR.RefTrainer(level=level, gan=gan, model=G, model_D1=D1, model_D2=D2)
+        src, lab, tgt = TR.synthetic_batch(SEED, (129, 257), (97, 193))
+        losses = tr.step(src, lab, tgt, i_iter=0, do_optimizer_step=False)
+        for k, v in losses.items():
+            out[f"{tag}_{k}"] = v
+        for name, mod in (("G", G), ("D1", D1), ("D2", D2)):
+            if name == "D1" and level != "multi-level":
+                continue
+            for pn, p in mod.named_parameters():
+                if p.grad is None:
+                    continue
+                gnp = p.grad.numpy().astype(np.float64)
+                if pn.startswith(("layer5", "layer6")) or name != "G" or pn == "conv1.weight" \
+                        or pn.endswith("layer4.2.conv3.weight"):
+                    out[f"{tag}_{name}_{pn}_l2"] = np.sqrt((gnp ** 2).sum())
+                    out[f"{tag}_{name}_{pn}_head"] = gnp.reshape(-1)[:32].astype(np.float32)
+        print(tag, losses)
+    save("step", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["aspp", "upsample", "ce", "softmax", "fcd", "ganloss", "hist", "argmax"]
+    which = sys.argv[1:] or ["aspp", "upsample", "ce", "softmax", "fcd", "ganloss", "hist", "argmax", "step"]
     for name in which:
         globals()["gold_" + name]()
