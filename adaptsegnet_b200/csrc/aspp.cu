@@ -319,13 +319,19 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const floa
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(base + ws.x_nhwc);
   float* Z = reinterpret_cast<float*>(base + ws.z);
   const int P = H * W;
-  nchw_to_nhwc_bf16_kernel<<<dim3(cdiv(P, 64), cdiv(Cin, 64), N), 256, 0, st>>>(x_nchw, xn, Cin, P);
-  ASN_LAUNCH_CHECK();
-  rc = umma::gemm_tn(xn, wp_bf16, Z, N * P, ws.NP, Cin, Cin, Cin, ws.NP, 1, 0, pick_block_n(ws.NP), st);
+  {
+    prof::Scope ps("aspp_x_to_nhwc_bf16", 0, 6.0 * N * P * Cin, st);
+    nchw_to_nhwc_bf16_kernel<<<dim3(cdiv(P, 64), cdiv(Cin, 64), N), 256, 0, st>>>(x_nchw, xn, Cin, P);
+    ASN_LAUNCH_CHECK();
+  }
+  // algorithmic flops: 2 * px * (9*n_active*n_cls) * Cin  (N padding not counted)
+  rc = umma::gemm_tn(xn, wp_bf16, Z, N * P, ws.NP, Cin, Cin, Cin, ws.NP, 1, 0, pick_block_n(ws.NP), st,
+                     "aspp_fwd_gemm", 2.0 * N * P * (9.0 * n_active * n_cls) * Cin);
   if (rc) return rc;
   AsppTaps taps;
   make_taps(taps, dil_host, n_active, W);
   const int groups = N * cdiv(P, 32);
+  prof::Scope ps("aspp_gather", 0, 4.0 * N * P * (9.0 * n_active * n_cls + n_cls), st);
   aspp_gather_kernel<32><<<cdiv(groups, 8), 256, 0, st>>>(Z, bias_sum, y_nchw, N, H, W, n_cls, ws.NP, taps);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -357,26 +363,33 @@ extern "C" int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const flo
     const size_t smem = (size_t)32 * ws.NP * 2;
     if (smem > 48 * 1024)
       ASN_CUDA(cudaFuncSetAttribute(aspp_dycols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof::Scope ps("aspp_dy_cols", 0, 4.0 * N * P * ws.NP + 4.0 * N * P * n_cls, st);
     aspp_dycols_kernel<<<N * cdiv(P, 32), 256, smem, st>>>(dy_nchw, dycol, dycolt, N, H, W, n_cls, ws.NP, ws.ldp, taps);
     ASN_LAUNCH_CHECK();
   }
   if (dx_nchw) {
     for (int n = 0; n < N; ++n) {
       rc = umma::gemm_tn(wpt_bf16, dycol + (int64_t)n * P * ws.NP, dx_nchw + (int64_t)n * Cin * P, Cin, P, ws.NP,
-                         ws.NP, ws.NP, P, 1, 0, 256, st);
+                         ws.NP, ws.NP, P, 1, 0, 256, st, "aspp_dgrad_gemm",
+                         2.0 * P * (9.0 * n_active * n_cls) * Cin);
       if (rc) return rc;
     }
   }
   if (dw_oihw) {
     __nv_bfloat16* xk = reinterpret_cast<__nv_bfloat16*>(base + ws.x_ckp);
     float* part = reinterpret_cast<float*>(base + ws.dwpart);
-    nchw_to_ckp_bf16_kernel<<<wave_grid((int64_t)N * Cin * P, 256, 8), 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
-    ASN_LAUNCH_CHECK();
+    {
+      prof::Scope ps("aspp_x_to_bf16", 0, 6.0 * N * P * Cin, st);
+      nchw_to_ckp_bf16_kernel<<<wave_grid((int64_t)N * Cin * P, 256, 8), 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
+      ASN_LAUNCH_CHECK();
+    }
     rc = umma::gemm_tn(xk, dycolt, part, Cin, ws.NP, N * P, (int)ws.ldp, (int)ws.ldp, ws.NP, ws.S,
-                       (long long)Cin * ws.NP, pick_block_n(ws.NP), st);
+                       (long long)Cin * ws.NP, pick_block_n(ws.NP), st, "aspp_wgrad_gemm",
+                       2.0 * N * P * (9.0 * n_active * n_cls) * Cin);
     if (rc) return rc;
     GradPtrs gp{};
     for (int b = 0; b < n_active; ++b) gp.w[b] = dw_oihw[b];
+    prof::Scope ps("aspp_unpack_dw", 0, 4.0 * Cin * ws.NP * (ws.S + 1), st);
     aspp_unpack_dw_kernel<<<wave_grid((int64_t)n_active * n_cls * Cin * 9, 256, 8), 256, 0, st>>>(
         part, ws.S, gp, n_active, n_cls, Cin, ws.NP);
     ASN_LAUNCH_CHECK();

@@ -13,6 +13,24 @@ namespace asn {
 void set_error(const char* fmt, ...);
 int sm_count();
 
+// Optional per-kernel timing with CUDA events on the launching stream (asn_prof_enable /
+// asn_prof_report): bench.py uses it to time the dominant kernel live inside the timed steps.
+namespace prof {
+bool enabled();
+void begin(const char* name, double flops, double bytes, cudaStream_t st);
+void end(cudaStream_t st);
+struct Scope {
+  cudaStream_t st;
+  bool on;
+  Scope(const char* name, double flops, double bytes, cudaStream_t s) : st(s), on(enabled()) {
+    if (on) begin(name, flops, bytes, st);
+  }
+  ~Scope() {
+    if (on) end(st);
+  }
+};
+}  // namespace prof
+
 #define ASN_CHECK_ARG(cond, ...)              \
   do {                                        \
     if (!(cond)) {                            \

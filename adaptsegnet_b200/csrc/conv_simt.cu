@@ -194,6 +194,7 @@ extern "C" int asn_conv2d_fwd_f32(const float* x, const float* w, const float* b
   if (rc) return rc;
   int M = N * g.OH * g.OW, K = C * KH * KW;
   dim3 grid(cdiv(M, BM), cdiv(O, BN), 1);
+  prof::Scope ps("conv_f32_fwd", 2.0 * M * O * K, 0, static_cast<cudaStream_t>(stream));
   conv_simt_kernel<MODE_FWD><<<grid, CONV_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       x, w, bias, y, g, M, O, K, K, lrelu_slope, accumulate);
   ASN_LAUNCH_CHECK();
@@ -209,6 +210,7 @@ extern "C" int asn_conv2d_dgrad_f32(const float* dy, const float* w, float* dx, 
   if (rc) return rc;
   int M = N * H * W, K = O * KH * KW;
   dim3 grid(cdiv(M, BM), cdiv(C, BN), 1);
+  prof::Scope ps("conv_f32_dgrad", 2.0 * M * C * K, 0, static_cast<cudaStream_t>(stream));
   conv_simt_kernel<MODE_DGRAD><<<grid, CONV_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       dy, w, nullptr, dx, g, M, C, K, K, 1.f, accumulate);
   ASN_LAUNCH_CHECK();
@@ -233,8 +235,11 @@ extern "C" int asn_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, 
   split = cdiv(K, kps);
   if (split > 1) ASN_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * Nn * sizeof(float), st));
   dim3 grid(cdiv(M, BM), cdiv(Nn, BN), split);
-  conv_simt_kernel<MODE_WGRAD><<<grid, CONV_THREADS, 0, st>>>(dy, x, nullptr, dw, g, M, Nn, K, kps, 1.f, 0);
-  ASN_LAUNCH_CHECK();
+  {
+    prof::Scope ps("conv_f32_wgrad", 2.0 * M * Nn * K, 0, st);
+    conv_simt_kernel<MODE_WGRAD><<<grid, CONV_THREADS, 0, st>>>(dy, x, nullptr, dw, g, M, Nn, K, kps, 1.f, 0);
+    ASN_LAUNCH_CHECK();
+  }
   if (db) {
     bias_grad_kernel<<<O, 256, 0, st>>>(dy, db, N, O, g.OH * g.OW);
     ASN_LAUNCH_CHECK();

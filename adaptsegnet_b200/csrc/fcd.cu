@@ -406,6 +406,12 @@ fcd_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, 
   }
 }
 
+// algorithmic flops of conv l (forward = dgrad = wgrad): 2 * pixels_out * Cout * 16 * Cin_real
+static double layer_flops(const FcdPlan& p, int l) {
+  const double cin = l == 1 ? p.n_cls : p.C[l - 1];
+  return 2.0 * p.N * p.H[l] * p.W[l] * p.C[l] * 16.0 * cin;
+}
+
 // ---- tcgen05 launches ---------------------------------------------------------------------------
 static int block_n_for(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : 32)); }
 
@@ -485,7 +491,8 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
   P.mask_src = nullptr;
   P.mask_slope = 1.f;
   dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(Cout, bn), 1);
-  return launch(MODE_CONV, bn, maps, P, grid, st);
+  static const char* names[5] = {"", "fcd_conv1_fwd", "fcd_conv2_fwd", "fcd_conv3_fwd", "fcd_conv4_fwd"};
+  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l));
 }
 
 // dIn (= dPre_{l-1} after the LeakyReLU mask, or dA0 for l == 1) from dPre_l
@@ -539,7 +546,8 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   P.mask_src = l == 1 ? nullptr : act_in;
   P.mask_slope = FCD_SLOPE;
   dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(rows, bn), 4);
-  return launch(MODE_CONV, bn, maps, P, grid, st);
+  static const char* names[5] = {"", "fcd_conv1_dgrad", "fcd_conv2_dgrad", "fcd_conv3_dgrad", "fcd_conv4_dgrad"};
+  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l));
 }
 
 static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* act_in, float* part,
@@ -596,7 +604,8 @@ static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   P.z_stride_out = (long long)P.taps * Cout * nn;
   P.slope = 1.f;
   dim3 grid(cdiv(Cout, 128) * cdiv(nn, bn), P.taps, S);
-  if ((rc = launch(MODE_WGRAD, bn, maps, P, grid, st))) return rc;
+  static const char* names[5] = {"", "fcd_conv1_wgrad", "fcd_conv2_wgrad", "fcd_conv3_wgrad", "fcd_conv4_wgrad"};
+  if ((rc = launch(MODE_WGRAD, bn, maps, P, grid, st, names[l], layer_flops(p, l)))) return rc;
   const int cin_real = l == 1 ? p.n_cls : p.C[l - 1];
   fcd_wgrad_reduce_kernel<<<wave_grid((int64_t)Cout * cin_real * 16, 256, 8), 256, 0, st>>>(part, dw, S, l, Cout,
                                                                                              cin_real, nn);
@@ -694,15 +703,19 @@ extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpa
   uint8_t* ab = static_cast<uint8_t*>(acts);
   __nv_bfloat16* A[5];
   for (int l = 0; l <= 4; ++l) A[l] = reinterpret_cast<__nv_bfloat16*>(ab + p.act_off[l]);
-  fcd_pack_input_kernel<<<wave_grid((int64_t)N * H * p.W0p, 256, 8), 256, 0, st>>>(x_nchw, A[0], N, n_cls, H, W, p.W0p,
-                                                                                   x_is_logits);
-  ASN_LAUNCH_CHECK();
+  {
+    prof::Scope ps("fcd_pack_input", 0, (double)N * H * W * (4.0 * n_cls + 64.0), st);
+    fcd_pack_input_kernel<<<wave_grid((int64_t)N * H * p.W0p, 256, 8), 256, 0, st>>>(x_nchw, A[0], N, n_cls, H, W,
+                                                                                     p.W0p, x_is_logits);
+    ASN_LAUNCH_CHECK();
+  }
   for (int l = 1; l <= 4; ++l) {
     rc = conv_fwd(p, l, A[l - 1], reinterpret_cast<const __nv_bfloat16*>(wb + p.wf_off[l]),
                   reinterpret_cast<const float*>(wb + p.bias_off[l]), A[l], st);
     if (rc) return rc;
   }
   const int n_out = N * p.H[5] * p.W[5];
+  prof::Scope ps("fcd_classifier_fwd", 2.0 * n_out * 16 * p.C[4], 0, st);
   fcd_cls_fwd_kernel<<<cdiv((int64_t)n_out * 32, 256), 256, 0, st>>>(
       A[4], reinterpret_cast<const float*>(wb + p.wc_off), reinterpret_cast<const float*>(wb + p.bc_off), out, N, p.H[4],
       p.W[4], p.C[4], p.H[5], p.W[5]);
@@ -760,6 +773,7 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
     }
   }
   if (dx_nchw) {
+    prof::Scope ps("fcd_unpack_dx", 0, (double)N * H * W * (64.0 + 4.0 * n_cls * (x_logits ? 2 : 1)), st);
     fcd_unpack_dx_kernel<<<wave_grid((int64_t)N * H * W, 256, 8), 256, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls, H, W,
                                                                                 p.W0p);
     ASN_LAUNCH_CHECK();

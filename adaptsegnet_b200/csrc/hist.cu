@@ -144,6 +144,7 @@ static int launch_hist(const void* label, const uint8_t* pred, int64_t n_px, int
   int grid = wave_grid((n_px + 63) / 64, HIST_THREADS, 8);
   // 32-bit shared counters: keep every CTA below 2^31 pixels
   while ((n_px + grid - 1) / grid > (int64_t)1 << 31) grid *= 2;
+  prof::Scope ps("fast_hist", 0, (double)n_px * (sizeof(LabelT) + 1), st);
   fast_hist_kernel<LabelT><<<grid, HIST_THREADS, (size_t)n_sub * nbins * 4, st>>>(
       static_cast<const LabelT*>(label), pred, n_px, n_cls, n_sub,
       reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(overflow),

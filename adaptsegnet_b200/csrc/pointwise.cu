@@ -314,6 +314,8 @@ static int launch_ce(const float* z, const int64_t* y, int N, int C, int H, int 
   const long long* yl = reinterpret_cast<const long long*>(y);
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
                    (!BWD || (reinterpret_cast<uintptr_t>(dz) & 15) == 0);
+  prof::Scope ps(BWD ? "softmax_ce_bwd" : "softmax_ce_fwd", 0,
+                 (double)N * HW * (4.0 * C * (BWD ? 2 : 1) + 8.0), st);
   if (C == 19 && vec) {
     int grid = wave_grid((int64_t)N * (HW / 4), PW_THREADS, 4);
     ce_kernel<19, 4, BWD><<<grid, PW_THREADS, 0, st>>>(z, yl, N, HW, ignore, mask_negative, cw, size_average, s, gscale, dz);
@@ -358,6 +360,7 @@ static int launch_softmax(const float* a, const float* b, float* out, int N, int
   const int HW = H * W;
   const bool vec = (HW % 4 == 0) && (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                                         reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  prof::Scope ps(BWD ? "softmax_bwd" : "softmax_fwd", 0, 4.0 * N * C * HW * (BWD ? 3 : 2), st);
   if (C == 19 && vec) {
     softmax_kernel<19, 4, BWD><<<wave_grid((int64_t)N * (HW / 4), PW_THREADS, 4), PW_THREADS, 0, st>>>(a, b, out, N, HW);
   } else if (C == 19) {
@@ -387,6 +390,7 @@ extern "C" int asn_gan_loss_fwd_bwd(const float* x, int64_t n, float target, int
   ASN_CHECK_ARG(x && loss, "asn_gan_loss_fwd_bwd: null pointer");
   ASN_CHECK_ARG(n > 0, "asn_gan_loss_fwd_bwd: empty input");
   ASN_CHECK_ARG(kind == ASN_GAN_BCE || kind == ASN_GAN_MSE, "asn_gan_loss_fwd_bwd: unknown kind %d", kind);
+  prof::Scope ps("gan_loss", 0, 8.0 * n, static_cast<cudaStream_t>(stream));
   gan_loss_kernel<<<1, GAN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, (long long)n, target, kind, grad_scale, loss, dx);
   ASN_LAUNCH_CHECK();
   return ASN_OK;

@@ -87,7 +87,8 @@ struct Stages {
 };
 
 template <int MODE, int BLOCK_N>
-static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st) {
+static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st, const char* name,
+                    double flops) {
   constexpr int STAGES = Stages<BLOCK_N>::value;
   using L = SmemLayout<BLOCK_N, STAGES>;
   auto kern = umma_kernel<MODE, BLOCK_N, STAGES>;
@@ -96,6 +97,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
     ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
+  prof::Scope ps(name, flops, 0, st);
   kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], P);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -110,9 +112,10 @@ bool block_n_supported(int mode, int block_n) {
   return false;
 }
 
-int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st) {
+int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
+           const char* prof_name, double prof_flops) {
 #define ASN_CASE(MODE, BN) \
-  if (mode == MODE && block_n == BN) return launch_t<MODE, BN>(maps, P, grid, st);
+  if (mode == MODE && block_n == BN) return launch_t<MODE, BN>(maps, P, grid, st, prof_name, prof_flops);
   ASN_CASE(MODE_GEMM, 128)
   ASN_CASE(MODE_GEMM, 176)
   ASN_CASE(MODE_GEMM, 256)
@@ -130,7 +133,8 @@ int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, di
 
 // plain GEMM: C[M,N] = A[M,K] . B[N,K]^T  (+ split-K partials)
 int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, long long ldc,
-            int split_k, long long split_stride, int block_n, cudaStream_t st) {
+            int split_k, long long split_stride, int block_n, cudaStream_t st, const char* prof_name,
+            double prof_flops) {
   ASN_CHECK_ARG(A && B && C, "gemm_tn: null pointer");
   ASN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tn: bad shape %d %d %d", M, N, K);
   ASN_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "gemm_tn: lda/ldb must be >= K and multiples of 8");
@@ -156,7 +160,7 @@ int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda
   P.z_stride_out = split_stride;
   P.slope = 1.f;
   dim3 grid(cdiv(M, BLOCK_M), cdiv(N, block_n), split_k);
-  return launch(MODE_GEMM, block_n, maps, P, grid, st);
+  return launch(MODE_GEMM, block_n, maps, P, grid, st, prof_name, prof_flops >= 0 ? prof_flops : 2.0 * M * N * K);
 }
 
 int effective_split(int K, int split_k) {

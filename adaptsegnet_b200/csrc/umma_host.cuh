@@ -14,7 +14,8 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
               uint32_t box1, uint32_t box2);
 
 // maps = {a0, a1, a2, a3, b}.  grid as documented on umma_kernel.
-int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st);
+int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
+           const char* prof_name = "umma", double prof_flops = 0);
 
 // BLOCK_N choices compiled for each mode
 bool block_n_supported(int mode, int block_n);
@@ -26,7 +27,8 @@ namespace asn {
 namespace umma {
 // C[M,N] (fp32, ldc) = A[M,K] . B[N,K]^T, bf16 K-contiguous operands; split_k partials at split_stride
 int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, long long ldc,
-            int split_k, long long split_stride, int block_n, cudaStream_t st);
+            int split_k, long long split_stride, int block_n, cudaStream_t st, const char* prof_name = "gemm_bf16_tn",
+            double prof_flops = -1.0);
 // number of z-slices gemm_tn actually launches for a requested split
 int effective_split(int K, int split_k);
 }  // namespace umma

@@ -158,6 +158,7 @@ extern "C" int asn_upsample_bilinear_fwd(const float* x, int N, int C, int h, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
   bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  prof::Scope ps("upsample_fwd", 0, 4.0 * N * C * ((double)H * W + (double)h * w), st);
   if (vec) {
     int64_t items = (int64_t)N * C * H * (W / 4);
     upsample_fwd_kernel<4><<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
@@ -190,11 +191,17 @@ extern "C" int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, i
   size_t smem = (size_t)W * 4;
   if (smem > 48 * 1024)
     ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  upsample_bwd_w_kernel<<<(unsigned)((int64_t)N * C * H), UP_THREADS, smem, st>>>(dy, T, w, W, sw, vec_ok);
-  ASN_LAUNCH_CHECK();
+  {
+    prof::Scope ps("upsample_bwd_w", 0, 4.0 * N * C * ((double)H * W + (double)H * w), st);
+    upsample_bwd_w_kernel<<<(unsigned)((int64_t)N * C * H), UP_THREADS, smem, st>>>(dy, T, w, W, sw, vec_ok);
+    ASN_LAUNCH_CHECK();
+  }
   int64_t items = (int64_t)N * C * h * w;
-  upsample_bwd_h_kernel<<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(T, dx, N * C, h, w, H, sh);
-  ASN_LAUNCH_CHECK();
+  {
+    prof::Scope ps("upsample_bwd_h", 0, 4.0 * N * C * ((double)H * w + (double)h * w), st);
+    upsample_bwd_h_kernel<<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(T, dx, N * C, h, w, H, sh);
+    ASN_LAUNCH_CHECK();
+  }
   return ASN_OK;
 }
 
@@ -205,6 +212,7 @@ extern "C" int asn_upsample_argmax_u8(const float* x, int N, int C, int h, int w
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
   int64_t items = (int64_t)N * H * ((W + 3) / 4);
+  prof::Scope ps("upsample_argmax", 0, 4.0 * N * C * h * w + (double)N * H * W, st);
   upsample_argmax_kernel<<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, pred, N, C, h, w, H, W, sh, sw);
   ASN_LAUNCH_CHECK();
   return ASN_OK;

@@ -58,6 +58,13 @@ ASN_API const char* asn_last_error(void);
 /* number of SMs of the current device (grids are sized from it) */
 ASN_API int asn_sm_count(int* out_host);
 
+/* Optional per-kernel timing (CUDA events recorded on the launching stream around every kernel of
+ * this library).  asn_prof_enable(1) clears and starts recording, asn_prof_enable(0) stops;
+ * asn_prof_report synchronises the recorded events and writes a JSON object
+ * {"kernel": {"launches", "ms", "flops", "bytes"}} (algorithmic flops / bytes); returns the size needed. */
+ASN_API int asn_prof_enable(int on);
+ASN_API int64_t asn_prof_report(char* buf_host, int64_t capacity);
+
 /* ------------------------------------------------------------------------------------
  * K7  confusion matrix.  replaces: compute_iou.py:15-17 (fast_hist), accumulate :57
  *   hist[n_cls*a+b] += 1 for every pixel with 0 <= a < n_cls.  `hist` (n_cls*n_cls int64)
