@@ -45,16 +45,28 @@ nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict_
   }
 }
 
-// x [N][C][P] fp32 -> out [C][ld] bf16, column n*P + p  (K-contiguous operand for the wgrad GEMM)
+// x [N][C][P] fp32 -> out [C][ld] bf16, column n*P + p  (K-contiguous operand for the wgrad GEMM).
+// blockIdx.y = (n, c) row; VEC = 4 pixels per thread (16-byte loads, 8-byte stores).
+template <int VEC>
 __global__ void __launch_bounds__(256)
 nchw_to_ckp_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, int P,
                         int64_t ld) {
-  const int64_t total = (int64_t)N * C * P;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    int p = (int)(i % P);
-    int c = (int)((i / P) % C);
-    int n = (int)(i / ((int64_t)P * C));
-    out[(int64_t)c * ld + (int64_t)n * P + p] = __float2bfloat16(__ldg(x + i));
+  const int n_rows = N * C;
+  const int pv = (P + VEC - 1) / VEC;
+  for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
+    const int n = row / C, c = row - n * C;
+    const float* src = x + (int64_t)row * P;
+    __nv_bfloat16* dst = out + (int64_t)c * ld + (int64_t)n * P;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < pv; i += gridDim.x * 256) {
+      if (VEC == 4) {
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(src) + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        *reinterpret_cast<uint2*>(dst + (int64_t)i * 4) = pk;
+      } else {
+        dst[i] = __float2bfloat16(__ldg(src + i));
+      }
+    }
   }
 }
 
@@ -64,38 +76,42 @@ struct AsppTaps {
 };
 
 // y[n][c][p] = bias_sum[c] + sum_t Z[n*P + p + shift_t][t*n_cls + c].
-// One warp owns 32 consecutive pixels; lane = class while accumulating (contiguous n_cls floats
-// per (pixel, tap)), lane = pixel while writing (coalesced NCHW rows).
+// A CTA owns 32 consecutive pixels; each of its 8 warps accumulates 4 of them with lane = class
+// (the n_cls floats of one (pixel, tap) are contiguous in Z, all taps of a pixel are independent
+// loads), then the CTA writes the [n_cls][32] tile as coalesced 128-byte NCHW rows.
 template <int MAX_CLS>
 __global__ void __launch_bounds__(256)
 aspp_gather_kernel(const float* __restrict__ Z, const float* __restrict__ bias_sum, float* __restrict__ y, int N,
                    int H, int W, int n_cls, int NP, AsppTaps taps) {
-  __shared__ float stage[8][MAX_CLS][33];
+  __shared__ float stage[MAX_CLS][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = H * W;
   const int groups_per_img = (P + 31) / 32;
-  const int g = blockIdx.x * 8 + warp;
-  if (g >= N * groups_per_img) return;
-  const int n = g / groups_per_img;
-  const int p0 = (g % groups_per_img) * 32;
+  const int n = blockIdx.x / groups_per_img;
+  const int p0 = (blockIdx.x - n * groups_per_img) * 32;
   const float b = lane < n_cls ? __ldg(bias_sum + lane) : 0.f;
-  for (int i = 0; i < 32; ++i) {
-    const int p = p0 + i;
+  const float* Zn = Z + (int64_t)n * P * NP + lane;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pl = warp * 4 + i;
+    const int p = p0 + pl;
     float acc = b;
     if (p < P && lane < n_cls) {
-      const int h = p / W, w = p % W;
-#pragma unroll 4
+      const int h = p / W, w = p - h * W;
+#pragma unroll 6
       for (int t = 0; t < taps.n_taps; ++t) {
         const int hh = h + taps.dh[t], ww = w + taps.dw[t];
         if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
-          acc += __ldg(Z + ((int64_t)n * P + (int64_t)hh * W + ww) * NP + t * n_cls + lane);
+          acc += __ldg(Zn + (int64_t)(hh * W + ww) * NP + t * n_cls);
       }
     }
-    if (lane < n_cls) stage[warp][lane][i] = acc;
+    if (lane < n_cls) stage[lane][pl] = acc;
   }
-  __syncwarp();
-  if (p0 + lane < P)
-    for (int c = 0; c < n_cls; ++c) y[((int64_t)n * n_cls + c) * P + p0 + lane] = stage[warp][c][lane];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n_cls * 32; idx += 256) {
+    const int c = idx >> 5, pl = idx & 31;
+    if (p0 + pl < P) y[((int64_t)n * n_cls + c) * P + p0 + pl] = stage[c][pl];
+  }
 }
 
 // dYcol[n*P + q][t*n_cls + c] = dy[n][c][q - shift_t] (0 outside), plus the transposed copy
@@ -332,7 +348,7 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const floa
   make_taps(taps, dil_host, n_active, W);
   const int groups = N * cdiv(P, 32);
   prof::Scope ps("aspp_gather", 0, 4.0 * N * P * (9.0 * n_active * n_cls + n_cls), st);
-  aspp_gather_kernel<32><<<cdiv(groups, 8), 256, 0, st>>>(Z, bias_sum, y_nchw, N, H, W, n_cls, ws.NP, taps);
+  aspp_gather_kernel<32><<<groups, 256, 0, st>>>(Z, bias_sum, y_nchw, N, H, W, n_cls, ws.NP, taps);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -380,7 +396,16 @@ extern "C" int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const flo
     float* part = reinterpret_cast<float*>(base + ws.dwpart);
     {
       prof::Scope ps("aspp_x_to_bf16", 0, 6.0 * N * P * Cin, st);
-      nchw_to_ckp_bf16_kernel<<<wave_grid((int64_t)N * Cin * P, 256, 8), 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
+      // vector path needs 16-byte aligned rows on both sides: P % 4 == 0 (then ld % 8 == 0 keeps the stores aligned)
+      const bool vec = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
+      const int rows = N * Cin;
+      if (vec) {
+        dim3 grid(cdiv(P / 4, 256) < 8 ? cdiv(P / 4, 256) : 8, rows < 32768 ? rows : 32768);
+        nchw_to_ckp_bf16_kernel<4><<<grid, 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
+      } else {
+        dim3 grid(cdiv(P, 256) < 8 ? cdiv(P, 256) : 8, rows < 32768 ? rows : 32768);
+        nchw_to_ckp_bf16_kernel<1><<<grid, 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
+      }
       ASN_LAUNCH_CHECK();
     }
     rc = umma::gemm_tn(xk, dycolt, part, Cin, ws.NP, N * P, (int)ws.ldp, (int)ws.ldp, ws.NP, ws.S,

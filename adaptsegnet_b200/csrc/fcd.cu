@@ -270,31 +270,42 @@ fcd_pack_cls_kernel(const float* __restrict__ w, const float* __restrict__ b, fl
 }
 
 // ---- classifier (N = 1 output channel): CUDA-core reductions ------------------------------------
-// out[n][oh][ow] = bc + sum_{kh,kw,c} A4[n][2oh-1+kh][2ow-1+kw][c] * wc[kh*4+kw][c]; one warp per output
-__global__ void __launch_bounds__(256)
+// out[n][oh][ow] = bc + sum_{kh,kw,c} A4[n][2oh-1+kh][2ow-1+kw][c] * wc[kh*4+kw][c].
+// One 128-thread CTA per output pixel: warp = kernel row kh, lanes stride the channels with 16-byte loads.
+__global__ void __launch_bounds__(128)
 fcd_cls_fwd_kernel(const __nv_bfloat16* __restrict__ a4, const float* __restrict__ wc, const float* __restrict__ bc,
                    float* __restrict__ out, int N, int H4, int W4, int C, int H5, int W5) {
-  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N * H5 * W5) return;
-  const int ow = warp % W5, oh = (warp / W5) % H5, n = warp / (W5 * H5);
+  __shared__ float red[4];
+  const int o = blockIdx.x;
+  const int kh = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ow = o % W5, oh = (o / W5) % H5, n = o / (W5 * H5);
   float acc = 0.f;
-  for (int kh = 0; kh < 4; ++kh) {
-    const int ih = 2 * oh - 1 + kh;
-    if ((unsigned)ih >= (unsigned)H4) continue;
+  const int ih = 2 * oh - 1 + kh;
+  if ((unsigned)ih < (unsigned)H4) {
     for (int kw = 0; kw < 4; ++kw) {
       const int iw = 2 * ow - 1 + kw;
       if ((unsigned)iw >= (unsigned)W4) continue;
       const __nv_bfloat16* src = a4 + (((int64_t)n * H4 + ih) * W4 + iw) * C;
       const float* wt = wc + (kh * 4 + kw) * C;
-      for (int c = lane * 2; c < C; c += 64) {
-        __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + c);
-        acc = fmaf(__low2float(v), __ldg(wt + c), acc);
-        acc = fmaf(__high2float(v), __ldg(wt + c + 1), acc);
+      for (int c = lane * 8; c < C; c += 256) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + c));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + c + 4));
+        const uint32_t pk[4] = {u.x, u.y, u.z, u.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+          acc = fmaf(__low2float(v), wv[2 * j], acc);
+          acc = fmaf(__high2float(v), wv[2 * j + 1], acc);
+        }
       }
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) out[warp] = acc + __ldg(bc);
+  if (lane == 0) red[kh] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) out[o] = red[0] + red[1] + red[2] + red[3] + __ldg(bc);
 }
 
 // dPre4[n][ih][iw][c] = mask(A4) * sum_{kh,kw valid} dout[n][oh][ow] * wc[kh*4+kw][c]
@@ -375,11 +386,21 @@ fcd_colsum_partial_kernel(const __nv_bfloat16* __restrict__ src, float* __restri
 }
 __global__ void __launch_bounds__(256)
 fcd_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int R, int C) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
+  // 32 channels per CTA (lane = channel -> coalesced 128-byte reads), 8 warps split the R partial rows
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int r = 0; r < R; ++r) acc += partial[(int64_t)r * C + c];
-  out[c] = acc;
+  if (c < C)
+    for (int r = warp; r < R; r += 8) acc += partial[(int64_t)r * C + c];
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    out[c] = t;
+  }
 }
 
 // dW_l[co][ci][kh][kw] = sum_z part[z][tap][co][col]
@@ -625,7 +646,7 @@ static int col_sum(const __nv_bfloat16* src, float* partial, float* out, int64_t
   ctas = (P + rows_per_cta - 1) / rows_per_cta;
   fcd_colsum_partial_kernel<<<(unsigned)ctas, 256, 0, st>>>(src, partial, P, C, rows_per_cta);
   ASN_LAUNCH_CHECK();
-  fcd_colsum_final_kernel<<<cdiv(C, 256), 256, 0, st>>>(partial, out, (int)ctas * sub, C);
+  fcd_colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(partial, out, (int)ctas * sub, C);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -716,7 +737,7 @@ extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpa
   }
   const int n_out = N * p.H[5] * p.W[5];
   prof::Scope ps("fcd_classifier_fwd", 2.0 * n_out * 16 * p.C[4], 0, st);
-  fcd_cls_fwd_kernel<<<cdiv((int64_t)n_out * 32, 256), 256, 0, st>>>(
+  fcd_cls_fwd_kernel<<<n_out, 128, 0, st>>>(
       A[4], reinterpret_cast<const float*>(wb + p.wc_off), reinterpret_cast<const float*>(wb + p.bc_off), out, N, p.H[4],
       p.W[4], p.C[4], p.H[5], p.W[5]);
   ASN_LAUNCH_CHECK();

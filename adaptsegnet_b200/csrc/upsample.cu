@@ -9,70 +9,82 @@ namespace asn {
 
 constexpr int UP_THREADS = 256;
 
-// one thread = VEC consecutive output columns of one output row
+// one thread = VEC consecutive output columns of one output row.  A CTA owns UP_ROWS consecutive
+// rows (nc, Y) and walks their column vectors with a flat 32-bit index (no 64-bit division).
+constexpr int UP_ROWS = 4;
 template <int VEC>
 __global__ void __launch_bounds__(UP_THREADS)
 upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int h, int w, int H,
                     int W, float sh, float sw) {
   const int wv = (W + VEC - 1) / VEC;
-  const int64_t total = (int64_t)NC * H * wv;
-  for (int64_t i = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * UP_THREADS) {
-    int xv = (int)(i % wv);
-    int64_t row = i / wv;
-    int Y = (int)(row % H);
-    int nc = (int)(row / H);
-    Lerp ly = lerp_at(Y, sh, h);
-    const float* r0 = x + ((int64_t)nc * h + ly.i0) * w;
-    const float* r1 = x + ((int64_t)nc * h + ly.i1) * w;
-    float out[VEC];
+  const int n_rows = NC * H;
+  for (int row0 = blockIdx.x * UP_ROWS; row0 < n_rows; row0 += gridDim.x * UP_ROWS) {
+    const int rows_here = min(UP_ROWS, n_rows - row0);
+    for (int idx = threadIdx.x; idx < rows_here * wv; idx += UP_THREADS) {
+      const int rl = idx / wv;
+      const int xv = idx - rl * wv;
+      const int row = row0 + rl;
+      const int nc = row / H;
+      const int Y = row - nc * H;
+      const Lerp ly = lerp_at(Y, sh, h);
+      const float* r0 = x + ((int64_t)nc * h + ly.i0) * w;
+      const float* r1 = x + ((int64_t)nc * h + ly.i1) * w;
+      float out[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      int X = xv * VEC + k;
-      Lerp lx = lerp_at(min(X, W - 1), sw, w);
-      out[k] = ly.l0 * (lx.l0 * __ldg(r0 + lx.i0) + lx.l1 * __ldg(r0 + lx.i1)) +
-               ly.l1 * (lx.l0 * __ldg(r1 + lx.i0) + lx.l1 * __ldg(r1 + lx.i1));
-    }
-    float* dst = y + row * W + (int64_t)xv * VEC;
-    if (VEC == 4) {
-      st_stream(reinterpret_cast<float4*>(dst), make_float4(out[0], out[1], out[2], out[3]));
-    } else {
+      for (int k = 0; k < VEC; ++k) {
+        const Lerp lx = lerp_at(min(xv * VEC + k, W - 1), sw, w);
+        out[k] = ly.l0 * (lx.l0 * __ldg(r0 + lx.i0) + lx.l1 * __ldg(r0 + lx.i1)) +
+                 ly.l1 * (lx.l0 * __ldg(r1 + lx.i0) + lx.l1 * __ldg(r1 + lx.i1));
+      }
+      float* dst = y + (int64_t)row * W + (int64_t)xv * VEC;
+      if (VEC == 4) {
+        st_stream(reinterpret_cast<float4*>(dst), make_float4(out[0], out[1], out[2], out[3]));
+      } else {
 #pragma unroll
-      for (int k = 0; k < VEC; ++k)
-        if (xv * VEC + k < W) dst[k] = out[k];
+        for (int k = 0; k < VEC; ++k)
+          if (xv * VEC + k < W) dst[k] = out[k];
+      }
     }
   }
 }
 
-// backward pass 1: collapse the width.  One CTA per full-res row (nc, Y): the row is staged
-// in shared memory with coalesced 16-byte loads, then thread j sums the (<= ~2/scale) columns
+// backward pass 1: collapse the width.  A CTA stages UPB_ROWS full-res rows (nc, Y) in shared memory
+// with coalesced 16-byte loads, then every thread sums, for one (row, j), the (<= ~2/scale) columns
 // whose x0 or x1 is j.  T[nc, Y, j] (N*C*H*w floats) is the workspace.
+constexpr int UPB_ROWS = 4;
 __global__ void __launch_bounds__(UP_THREADS)
-upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int w, int W, float sw,
+upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int n_rows, int w, int W, float sw,
                       int vec_ok) {
-  extern __shared__ float row[];
-  const int64_t r = blockIdx.x;
-  const float* src = dy + r * W;
-  if (vec_ok) {
-    for (int i = threadIdx.x; i < W / 4; i += UP_THREADS)
-      reinterpret_cast<float4*>(row)[i] = ld_stream(reinterpret_cast<const float4*>(src) + i);
-  } else {
-    for (int i = threadIdx.x; i < W; i += UP_THREADS) row[i] = src[i];
-  }
-  __syncthreads();
+  extern __shared__ float rows_sh[];  // [UPB_ROWS][W]
   const float inv = sw > 0.f ? 1.f / sw : 0.f;
-  for (int j = threadIdx.x; j < w; j += UP_THREADS) {
-    // candidate columns: source coordinate in (j-1, j+1); widen by 2 and re-test exactly
-    int lo = sw > 0.f ? max(0, (int)floorf((float)(j - 1) * inv) - 2) : 0;
-    int hi = sw > 0.f ? min(W - 1, (int)ceilf((float)(j + 1) * inv) + 2) : W - 1;
-    float acc = 0.f;
-    for (int X = lo; X <= hi; ++X) {
-      Lerp lx = lerp_at(X, sw, w);
-      float v = row[X];
-      if (lx.i0 == j) acc += lx.l0 * v;
-      if (lx.i1 == j) acc += lx.l1 * v;
+  for (int row0 = blockIdx.x * UPB_ROWS; row0 < n_rows; row0 += gridDim.x * UPB_ROWS) {
+    const int rows_here = min(UPB_ROWS, n_rows - row0);
+    const float* src = dy + (int64_t)row0 * W;
+    const int n_el = rows_here * W;  // the rows are contiguous in memory
+    if (vec_ok) {
+      for (int i = threadIdx.x; i < n_el / 4; i += UP_THREADS)
+        reinterpret_cast<float4*>(rows_sh)[i] = ld_stream(reinterpret_cast<const float4*>(src) + i);
+    } else {
+      for (int i = threadIdx.x; i < n_el; i += UP_THREADS) rows_sh[i] = src[i];
     }
-    T[r * w + j] = acc;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows_here * w; idx += UP_THREADS) {
+      const int rl = idx / w;
+      const int j = idx - rl * w;
+      const float* row = rows_sh + rl * W;
+      // candidate columns: source coordinate in (j-1, j+1); widen by 2 and re-test exactly
+      const int lo = sw > 0.f ? max(0, (int)floorf((float)(j - 1) * inv) - 2) : 0;
+      const int hi = sw > 0.f ? min(W - 1, (int)ceilf((float)(j + 1) * inv) + 2) : W - 1;
+      float acc = 0.f;
+      for (int X = lo; X <= hi; ++X) {
+        const Lerp lx = lerp_at(X, sw, w);
+        const float v = row[X];
+        if (lx.i0 == j) acc += lx.l0 * v;
+        if (lx.i1 == j) acc += lx.l1 * v;
+      }
+      T[(int64_t)(row0 + rl) * w + j] = acc;
+    }
+    __syncthreads();
   }
 }
 
@@ -159,12 +171,12 @@ extern "C" int asn_upsample_bilinear_fwd(const float* x, int N, int C, int h, in
   float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
   bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   prof::Scope ps("upsample_fwd", 0, 4.0 * N * C * ((double)H * W + (double)h * w), st);
+  const int groups = cdiv((int64_t)N * C * H, UP_ROWS);
+  const int grid = groups < 16 * sm_count() ? groups : 16 * sm_count();
   if (vec) {
-    int64_t items = (int64_t)N * C * H * (W / 4);
-    upsample_fwd_kernel<4><<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
+    upsample_fwd_kernel<4><<<grid, UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
   } else {
-    int64_t items = (int64_t)N * C * H * W;
-    upsample_fwd_kernel<1><<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
+    upsample_fwd_kernel<1><<<grid, UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
   }
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -183,17 +195,20 @@ extern "C" int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, i
     set_error("asn_upsample_bilinear_bwd: workspace too small");
     return ASN_EWORKSPACE;
   }
-  ASN_CHECK_ARG((size_t)W * 4 <= 200 * 1024, "asn_upsample_bilinear_bwd: row of %d floats exceeds shared memory", W);
+  ASN_CHECK_ARG((size_t)W * 4 * UPB_ROWS <= 200 * 1024, "asn_upsample_bilinear_bwd: rows of %d floats exceed shared memory", W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
   float* T = static_cast<float*>(workspace);
   int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
-  size_t smem = (size_t)W * 4;
+  size_t smem = (size_t)W * 4 * UPB_ROWS;
+  const int n_rows = N * C * H;
+  const int groups_w = cdiv(n_rows, UPB_ROWS);
+  const int grid_w = groups_w < 8 * sm_count() ? groups_w : 8 * sm_count();
   if (smem > 48 * 1024)
     ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     prof::Scope ps("upsample_bwd_w", 0, 4.0 * N * C * ((double)H * W + (double)H * w), st);
-    upsample_bwd_w_kernel<<<(unsigned)((int64_t)N * C * H), UP_THREADS, smem, st>>>(dy, T, w, W, sw, vec_ok);
+    upsample_bwd_w_kernel<<<grid_w, UP_THREADS, smem, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
     ASN_LAUNCH_CHECK();
   }
   int64_t items = (int64_t)N * C * h * w;
