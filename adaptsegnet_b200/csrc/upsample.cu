@@ -9,41 +9,41 @@ namespace asn {
 
 constexpr int UP_THREADS = 256;
 
-// one thread = VEC consecutive output columns of one output row.  A CTA owns UP_ROWS consecutive
-// rows (nc, Y) and walks their column vectors with a flat 32-bit index (no 64-bit division).
-constexpr int UP_ROWS = 4;
+// one thread = VEC consecutive output columns; it keeps their x-interpolation (indices + weights) in
+// registers and walks down the rows (nc, Y) assigned to its CTA row-slice, so the per-pixel work is
+// 4 gathers (L1-resident low-res rows) + 6 FMAs and the kernel stays HBM-write-bound.
 template <int VEC>
-__global__ void __launch_bounds__(UP_THREADS)
-upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int h, int w, int H,
-                    int W, float sh, float sw) {
+__global__ void upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int h, int w, int H,
+                                    int W, float sh, float sw) {
   const int wv = (W + VEC - 1) / VEC;
+  const int xv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xv >= wv) return;
+  int i0[VEC], i1[VEC];
+  float l0[VEC], l1[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const Lerp lx = lerp_at(min(xv * VEC + k, W - 1), sw, w);
+    i0[k] = lx.i0; i1[k] = lx.i1; l0[k] = lx.l0; l1[k] = lx.l1;
+  }
   const int n_rows = NC * H;
-  for (int row0 = blockIdx.x * UP_ROWS; row0 < n_rows; row0 += gridDim.x * UP_ROWS) {
-    const int rows_here = min(UP_ROWS, n_rows - row0);
-    for (int idx = threadIdx.x; idx < rows_here * wv; idx += UP_THREADS) {
-      const int rl = idx / wv;
-      const int xv = idx - rl * wv;
-      const int row = row0 + rl;
-      const int nc = row / H;
-      const int Y = row - nc * H;
-      const Lerp ly = lerp_at(Y, sh, h);
-      const float* r0 = x + ((int64_t)nc * h + ly.i0) * w;
-      const float* r1 = x + ((int64_t)nc * h + ly.i1) * w;
-      float out[VEC];
+  for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
+    const int nc = row / H;
+    const int Y = row - nc * H;
+    const Lerp ly = lerp_at(Y, sh, h);
+    const float* r0 = x + ((int64_t)nc * h + ly.i0) * w;
+    const float* r1 = x + ((int64_t)nc * h + ly.i1) * w;
+    float out[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const Lerp lx = lerp_at(min(xv * VEC + k, W - 1), sw, w);
-        out[k] = ly.l0 * (lx.l0 * __ldg(r0 + lx.i0) + lx.l1 * __ldg(r0 + lx.i1)) +
-                 ly.l1 * (lx.l0 * __ldg(r1 + lx.i0) + lx.l1 * __ldg(r1 + lx.i1));
-      }
-      float* dst = y + (int64_t)row * W + (int64_t)xv * VEC;
-      if (VEC == 4) {
-        st_stream(reinterpret_cast<float4*>(dst), make_float4(out[0], out[1], out[2], out[3]));
-      } else {
+    for (int k = 0; k < VEC; ++k)
+      out[k] = ly.l0 * (l0[k] * __ldg(r0 + i0[k]) + l1[k] * __ldg(r0 + i1[k])) +
+               ly.l1 * (l0[k] * __ldg(r1 + i0[k]) + l1[k] * __ldg(r1 + i1[k]));
+    float* dst = y + (int64_t)row * W + (int64_t)xv * VEC;
+    if (VEC == 4) {
+      st_stream(reinterpret_cast<float4*>(dst), make_float4(out[0], out[1], out[2], out[3]));
+    } else {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k)
-          if (xv * VEC + k < W) dst[k] = out[k];
-      }
+      for (int k = 0; k < VEC; ++k)
+        if (xv * VEC + k < W) dst[k] = out[k];
     }
   }
 }
@@ -55,7 +55,14 @@ constexpr int UPB_ROWS = 4;
 __global__ void __launch_bounds__(UP_THREADS)
 upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int n_rows, int w, int W, float sw,
                       int vec_ok) {
-  extern __shared__ float rows_sh[];  // [UPB_ROWS][W]
+  extern __shared__ float rows_sh[];                          // [UPB_ROWS][W] | i0[W] | l1[W]
+  int* tab_i0 = reinterpret_cast<int*>(rows_sh + UPB_ROWS * W);
+  float* tab_l1 = rows_sh + (UPB_ROWS + 1) * W;
+  for (int X = threadIdx.x; X < W; X += UP_THREADS) {          // same x-interpolation for every row
+    const Lerp lx = lerp_at(X, sw, w);
+    tab_i0[X] = lx.i0;
+    tab_l1[X] = lx.l1;
+  }
   const float inv = sw > 0.f ? 1.f / sw : 0.f;
   for (int row0 = blockIdx.x * UPB_ROWS; row0 < n_rows; row0 += gridDim.x * UPB_ROWS) {
     const int rows_here = min(UPB_ROWS, n_rows - row0);
@@ -72,15 +79,17 @@ upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int n
       const int rl = idx / w;
       const int j = idx - rl * w;
       const float* row = rows_sh + rl * W;
-      // candidate columns: source coordinate in (j-1, j+1); widen by 2 and re-test exactly
+      // candidate columns: source coordinate in (j-1, j+1); widen by 2 and test against the table
       const int lo = sw > 0.f ? max(0, (int)floorf((float)(j - 1) * inv) - 2) : 0;
       const int hi = sw > 0.f ? min(W - 1, (int)ceilf((float)(j + 1) * inv) + 2) : W - 1;
       float acc = 0.f;
       for (int X = lo; X <= hi; ++X) {
-        const Lerp lx = lerp_at(X, sw, w);
+        const int a0 = tab_i0[X];
+        const float b1 = tab_l1[X];
         const float v = row[X];
-        if (lx.i0 == j) acc += lx.l0 * v;
-        if (lx.i1 == j) acc += lx.l1 * v;
+        const int a1 = a0 + (a0 < w - 1 ? 1 : 0);
+        if (a0 == j) acc += __fsub_rn(1.f, b1) * v;
+        if (a1 == j) acc += b1 * v;
       }
       T[(int64_t)(row0 + rl) * w + j] = acc;
     }
@@ -171,12 +180,19 @@ extern "C" int asn_upsample_bilinear_fwd(const float* x, int N, int C, int h, in
   float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
   bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   prof::Scope ps("upsample_fwd", 0, 4.0 * N * C * ((double)H * W + (double)h * w), st);
-  const int groups = cdiv((int64_t)N * C * H, UP_ROWS);
-  const int grid = groups < 16 * sm_count() ? groups : 16 * sm_count();
+  const int wv = vec ? W / 4 : W;
+  // block = one row of column vectors (rounded up to warps, capped at 512 threads)
+  int threads = (int)round_up(wv < 512 ? wv : 512, 32);
+  if (wv > 512) threads = (int)round_up(cdiv(wv, cdiv(wv, 512)), 32);
+  const int gx = cdiv(wv, threads);
+  const int rows = N * C * H;
+  int gy = (8 * sm_count() * 256) / (gx * threads);  // ~8 x 256 resident threads per SM
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
   if (vec) {
-    upsample_fwd_kernel<4><<<grid, UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
+    upsample_fwd_kernel<4><<<dim3(gx, gy), threads, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
   } else {
-    upsample_fwd_kernel<1><<<grid, UP_THREADS, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
+    upsample_fwd_kernel<1><<<dim3(gx, gy), threads, 0, st>>>(x, y, N * C, h, w, H, W, sh, sw);
   }
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -195,12 +211,12 @@ extern "C" int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, i
     set_error("asn_upsample_bilinear_bwd: workspace too small");
     return ASN_EWORKSPACE;
   }
-  ASN_CHECK_ARG((size_t)W * 4 * UPB_ROWS <= 200 * 1024, "asn_upsample_bilinear_bwd: rows of %d floats exceed shared memory", W);
+  ASN_CHECK_ARG((size_t)W * 4 * (UPB_ROWS + 2) <= 200 * 1024, "asn_upsample_bilinear_bwd: rows of %d floats exceed shared memory", W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
   float* T = static_cast<float*>(workspace);
   int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
-  size_t smem = (size_t)W * 4 * UPB_ROWS;
+  size_t smem = (size_t)W * 4 * (UPB_ROWS + 2);
   const int n_rows = N * C * H;
   const int groups_w = cdiv(n_rows, UPB_ROWS);
   const int grid_w = groups_w < 8 * sm_count() ? groups_w : 8 * sm_count();
