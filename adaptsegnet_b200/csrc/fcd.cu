@@ -434,7 +434,21 @@ static double layer_flops(const FcdPlan& p, int l) {
 }
 
 // ---- tcgen05 launches ---------------------------------------------------------------------------
-static int block_n_for(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : 32)); }
+// largest BLOCK_N dividing n that still yields enough tiles to occupy most SMs of the persistent grid
+static int block_n_for(int n, long long m_tiles = 1 << 30) {
+  const int cand[4] = {256, 128, 64, 32};
+  int best = 32;
+  for (int i = 3; i >= 0; --i)
+    if (n % cand[i] == 0) {
+      best = cand[i];
+      break;
+    }
+  for (int i = 0; i < 4; ++i) {
+    if (n % cand[i]) continue;
+    if (m_tiles * (n / cand[i]) * 4 >= 3LL * sm_count() || cand[i] == best) return cand[i];
+  }
+  return best;
+}
 
 // parity view (rh, rw) of an NHWC tensor [N][Hin][Win][C]
 static int encode_parity(CUtensorMap* m, const __nv_bfloat16* base, int N, int Hin, int Win, int C, int rh, int rw,
@@ -492,7 +506,7 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
       }
   }
   const int K = P.taps * P.c_chunks * 64;
-  const int bn = block_n_for(Cout);
+  const int bn = block_n_for(Cout, (long long)p.N * cdiv(OH, th) * cdiv(OW, tw));
   if ((rc = encode_2d(&maps[4], wf, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)bn))) return rc;
   P.M = 0;
   P.N = Cout;
@@ -530,7 +544,7 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   if ((rc = encode_plain(&maps[0], dpre, p.N, Hout, Wout, Cout, th, tw))) return rc;
   maps[1] = maps[2] = maps[3] = maps[0];
   const int K = 4 * Cout;
-  const int bn = block_n_for(rows);
+  const int bn = block_n_for(rows, 4LL * p.N * cdiv(eh, th) * cdiv(ew, tw));
   if ((rc = encode_2d(&maps[4], wd, (uint64_t)K, (uint64_t)4 * rows, (uint64_t)K * 2, (uint32_t)bn))) return rc;
   Params P;
   memset(&P, 0, sizeof(P));

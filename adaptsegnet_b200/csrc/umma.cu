@@ -54,7 +54,7 @@ static int encode(CUtensorMap* m, const void* base, int rank, const uint64_t* di
     }
   }
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)", (int)r, rank,
@@ -78,12 +78,16 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
   return encode(m, base, 4, dims, strides_bytes, box);
 }
 
-// stage counts: keep every CTA <= ~112 KB so that two are co-resident per SM
+// Persistent CTAs per SM and ring depth.  BLOCK_N <= 128: two CTAs per SM (2 x 2*BLOCK_N <= 512 TMEM
+// columns, ~104 KB ring each) -- their k-steps are cheap (<= 256 MMA cycles), so one TMA-issuing
+// thread per SM cannot keep the tensor pipe fed; two producers can.  BLOCK_N > 128: one CTA per SM
+// with the whole ~192 KB ring (the double-buffered accumulator needs all 512 TMEM columns).
 template <int BLOCK_N>
 struct Stages {
+  static constexpr int ctas_per_sm = BLOCK_N <= 128 ? 2 : 1;
   static constexpr int stage = 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
-  static constexpr int fit = (112 * 1024 - 1280) / stage;
-  static constexpr int value = fit > 6 ? 6 : (fit < 2 ? 2 : fit);
+  static constexpr int fit = ((ctas_per_sm == 2 ? 104 : 196) * 1024) / stage;
+  static constexpr int value = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
 
 template <int MODE, int BLOCK_N>
@@ -97,8 +101,15 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
     ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
+  Params Pp = P;
+  Pp.grid_x = (int)grid.x;
+  Pp.grid_y = (int)grid.y;
+  Pp.grid_z = (int)grid.z;
+  const long long tiles = (long long)grid.x * grid.y * grid.z;
+  const long long slots = (long long)sm_count() * Stages<BLOCK_N>::ctas_per_sm;
+  const int ctas = (int)(tiles < slots ? tiles : slots);
   prof::Scope ps(name, flops, 0, st);
-  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], P);
+  kern<<<ctas, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], Pp);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }

@@ -6,9 +6,12 @@
 // per k-step; A/B stages are filled by TMA (SWIZZLE_128B boxes whose inner extent is 64 bf16 =
 // 128 bytes), consumed by tcgen05.mma issued from one thread, released by tcgen05.commit.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  One output tile per CTA; two
-// CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
-// epilogue overlaps the other's main loop.
+// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  The kernel is PERSISTENT: one CTA
+// (two for BLOCK_N <= 128) per SM walks the tile list (tile = blockIdx.x + i * gridDim.x); the
+// shared-memory ring (~100-190 KB, 3-5 stages) keeps streaming across tile boundaries and the accumulator is double
+// buffered in TMEM (2 x BLOCK_N columns), so the epilogue of tile i overlaps the MMAs of tile
+// i+1 and the fixed costs (TMEM allocation, barrier init, descriptor prefetch, pipeline fill)
+// are paid once per SM instead of once per tile.
 //
 // Three operand-fetch programs share the skeleton:
 //   GEMM  : A and B are plain row-major [rows][K] matrices (K-major operands).
@@ -41,6 +44,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -152,6 +158,8 @@ constexpr int MAX_TAPS = 16;
 constexpr int MAX_Z = 4;
 
 struct Params {
+  // ---- logical tile grid (walked persistently): tile -> (bx, by, bz) ----
+  int grid_x, grid_y, grid_z;
   // ---- problem extents ----
   int M, N;             // GEMM: logical rows / cols of the output (store masks)
   int k_steps;          // total number of 64-wide k-steps
@@ -181,9 +189,11 @@ struct Params {
   float mask_slope;
 };
 
+// two accumulator buffers of BLOCK_N fp32 columns each, power-of-two allocation
 template <int BLOCK_N>
 struct TmemCols {
-  static constexpr int value = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  static constexpr int value = 2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
+                               : 2 * BLOCK_N <= 256 ? 256 : 512;
 };
 
 constexpr int BLOCK_M = 128;
@@ -197,11 +207,47 @@ struct SmemLayout {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers (<= 21 x 8 B) + alignment slack
 };
 
+struct TileCoord {
+  int z, n0, m0, img, oh0, ow0, wg_tap, ks_begin, nsteps;
+};
+
+template <int MODE, int BLOCK_N>
+__device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
+  TileCoord t;
+  const int bx = tile % P.grid_x;
+  const int by = (tile / P.grid_x) % P.grid_y;
+  t.z = tile / (P.grid_x * P.grid_y);
+  t.m0 = t.img = t.oh0 = t.ow0 = t.wg_tap = 0;
+  t.ks_begin = 0;
+  int ks_end = P.k_steps;
+  if (MODE == MODE_GEMM) {
+    t.m0 = bx * BLOCK_M;
+    t.n0 = by * BLOCK_N;
+    t.ks_begin = t.z * P.steps_per_split;
+    ks_end = min(P.k_steps, t.ks_begin + P.steps_per_split);
+  } else if (MODE == MODE_CONV) {
+    t.ow0 = (bx % P.tiles_w) * P.tw;
+    t.oh0 = ((bx / P.tiles_w) % P.tiles_h) * P.th;
+    t.img = bx / (P.tiles_w * P.tiles_h);
+    t.n0 = by * BLOCK_N;
+  } else {
+    // bx = m_tile + m_tiles * n_tile  (m_tiles = ceil(M/128)), by = tap, bz = split
+    const int m_tiles = (P.M + BLOCK_M - 1) / BLOCK_M;
+    t.m0 = (bx % m_tiles) * BLOCK_M;
+    t.n0 = (bx / m_tiles) * BLOCK_N;
+    t.wg_tap = by;
+    t.ks_begin = t.z * P.steps_per_split;
+    ks_end = min(P.k_steps, t.ks_begin + P.steps_per_split);
+  }
+  t.nsteps = max(ks_end - t.ks_begin, 0);
+  return t;
+}
+
 template <int MODE, int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, (BLOCK_N <= 128 ? 2 : 1))
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
@@ -212,39 +258,15 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_holder = bar_base + 8u * (2 * STAGES + 1);
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_holder = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_holder_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates ----
-  const int z = blockIdx.z;
-  int n0, m0 = 0, img = 0, oh0 = 0, ow0 = 0, wg_tap = 0;
-  int ks_begin = 0, ks_end = P.k_steps;
-  if (MODE == MODE_GEMM) {
-    m0 = blockIdx.x * BLOCK_M;
-    n0 = blockIdx.y * BLOCK_N;
-    ks_begin = z * P.steps_per_split;
-    ks_end = min(P.k_steps, ks_begin + P.steps_per_split);
-  } else if (MODE == MODE_CONV) {
-    int t = blockIdx.x;
-    ow0 = (t % P.tiles_w) * P.tw;
-    oh0 = ((t / P.tiles_w) % P.tiles_h) * P.th;
-    img = t / (P.tiles_w * P.tiles_h);
-    n0 = blockIdx.y * BLOCK_N;
-  } else {
-    // blockIdx.x = m_tile + m_tiles * n_tile  (m_tiles = ceil(M/128)), blockIdx.y = tap
-    const int m_tiles = (P.M + BLOCK_M - 1) / BLOCK_M;
-    m0 = (blockIdx.x % m_tiles) * BLOCK_M;
-    n0 = (blockIdx.x / m_tiles) * BLOCK_N;
-    wg_tap = blockIdx.y;
-    ks_begin = z * P.steps_per_split;
-    ks_end = min(P.k_steps, ks_begin + P.steps_per_split);
-  }
-  const int nsteps = ks_end - ks_begin;
+  const int total_tiles = P.grid_x * P.grid_y * P.grid_z;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -259,7 +281,10 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), NUM_THREADS - 64);  // every epilogue thread arrives
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -269,43 +294,47 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_holder_ptr;
+  const uint32_t tmem_base = *tmem_holder_ptr;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const CUtensorMap* amaps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
-      for (int i = 0; i < nsteps; ++i) {
-        const int ks = ks_begin + i;
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        const uint32_t sb = sa + L::A_BYTES;
-        if (MODE == MODE_GEMM) {
-          mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
-          tma_load_2d(&map_a0, sa, full_bar(s), ks * BLOCK_K, m0);
-          tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, n0);
-        } else if (MODE == MODE_CONV) {
-          const int tap = ks / P.c_chunks, cc = ks - tap * P.c_chunks;
-          const int e = z * P.taps + tap;
-          mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
-          tma_load_4d(amaps[P.tap_map[e]], sa, full_bar(s), cc * BLOCK_K, ow0 + P.tap_dw[e], oh0 + P.tap_dh[e], img);
-          tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, z * P.b_rows_per_z + n0);
-        } else {
-          // k-step = one box of 64 pixels: A = dY channels [m0, m0+128), B = X@tap channels [n0, n0+BLOCK_N)
-          const int bx = ks % P.tiles_w, by = (ks / P.tiles_w) % P.tiles_h, im = ks / (P.tiles_w * P.tiles_h);
-          const uint32_t box_bytes = 64 * 64 * 2;
-          mbar_arrive_expect_tx(full_bar(s), (P.a_boxes + BLOCK_N / 64) * box_bytes);
-          for (int a = 0; a < P.a_boxes; ++a)
-            tma_load_4d(&map_a0, sa + a * box_bytes, full_bar(s), m0 + a * 64, bx * P.tw, by * P.th, im);
-          const CUtensorMap* bm = P.tap_map[wg_tap] == 0 ? &map_b
-                                  : P.tap_map[wg_tap] == 1 ? &map_a1
-                                  : P.tap_map[wg_tap] == 2 ? &map_a2 : &map_a3;
+      uint32_t it = 0;  // k-steps issued so far: the ring keeps streaming across tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile<MODE, BLOCK_N>(P, tile);
+        for (int i = 0; i < t.nsteps; ++i, ++it) {
+          const int ks = t.ks_begin + i;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
+          if (MODE == MODE_GEMM) {
+            mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
+            tma_load_2d(&map_a0, sa, full_bar(s), ks * BLOCK_K, t.m0);
+            tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.n0);
+          } else if (MODE == MODE_CONV) {
+            const int tap = ks / P.c_chunks, cc = ks - tap * P.c_chunks;
+            const int e = t.z * P.taps + tap;
+            mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
+            tma_load_4d(amaps[P.tap_map[e]], sa, full_bar(s), cc * BLOCK_K, t.ow0 + P.tap_dw[e],
+                        t.oh0 + P.tap_dh[e], t.img);
+            tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.z * P.b_rows_per_z + t.n0);
+          } else {
+            // k-step = one box of 64 pixels: A = dY channels [m0, m0+128), B = X@tap channels [n0, n0+BLOCK_N)
+            const int bx = ks % P.tiles_w, by = (ks / P.tiles_w) % P.tiles_h, im = ks / (P.tiles_w * P.tiles_h);
+            const uint32_t box_bytes = 64 * 64 * 2;
+            mbar_arrive_expect_tx(full_bar(s), (P.a_boxes + BLOCK_N / 64) * box_bytes);
+            for (int a = 0; a < P.a_boxes; ++a)
+              tma_load_4d(&map_a0, sa + a * box_bytes, full_bar(s), t.m0 + a * 64, bx * P.tw, by * P.th, im);
+            const int mi = P.tap_map[t.wg_tap];
+            const CUtensorMap* bm = mi == 0 ? &map_b : mi == 1 ? &map_a1 : mi == 2 ? &map_a2 : &map_a3;
 #pragma unroll
-          for (int b = 0; b < BLOCK_N / 64; ++b)
-            tma_load_4d(bm, sb + b * box_bytes, full_bar(s), n0 + b * 64, bx * P.tw + P.tap_dw[wg_tap],
-                        by * P.th + P.tap_dh[wg_tap], im);
+            for (int b = 0; b < BLOCK_N / 64; ++b)
+              tma_load_4d(bm, sb + b * box_bytes, full_bar(s), t.n0 + b * 64, bx * P.tw + P.tap_dw[t.wg_tap],
+                          by * P.th + P.tap_dh[t.wg_tap], im);
+          }
         }
       }
     }
@@ -314,107 +343,138 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = MODE == MODE_WGRAD ? make_idesc(BLOCK_M, BLOCK_N, 1, 1)
                                                     : make_idesc(BLOCK_M, BLOCK_N, 0, 0);
-      for (int i = 0; i < nsteps; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        const TileCoord t = decode_tile<MODE, BLOCK_N>(P, tile);
+        const uint32_t acc = tile_iter & 1;
+        const uint32_t acc_ph = (tile_iter >> 1) & 1;
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int i = 0; i < t.nsteps; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          uint64_t da, db;
-          if (MODE == MODE_WGRAD) {
-            // MN-major, SW128: 64-channel chunks LBO = 64 px * 128 B apart, 8-pixel groups SBO = 1 KB apart;
-            // advancing K by 16 pixels = 2 KB
-            da = make_smem_desc(sa + k * 2048, 8192, 1024);
-            db = make_smem_desc(sb + k * 2048, 8192, 1024);
-          } else {
-            // K-major, SW128: 8-row groups SBO = 1 KB apart; advancing K by 16 elements = 32 B inside the row
-            da = make_smem_desc(sa + k * 32, 16, 1024);
-            db = make_smem_desc(sb + k * 32, 16, 1024);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            uint64_t da, db;
+            if (MODE == MODE_WGRAD) {
+              // MN-major, SW128: 64-channel chunks LBO = 64 px * 128 B apart, 8-pixel groups SBO = 1 KB apart;
+              // advancing K by 16 pixels = 2 KB
+              da = make_smem_desc(sa + k * 2048, 8192, 1024);
+              db = make_smem_desc(sb + k * 2048, 8192, 1024);
+            } else {
+              // K-major, SW128: 8-row groups SBO = 1 KB apart; advancing K by 16 elements = 32 B inside the row
+              da = make_smem_desc(sa + k * 32, 16, 1024);
+              db = make_smem_desc(sb + k * 32, 16, 1024);
+            }
+            mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
         }
-        mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+        mma_commit(tmem_full_bar(acc));  // accumulator of this tile complete
       }
-      mma_commit(tmem_full_bar);   // accumulator complete
     }
   } else {
     // =============================== epilogue ===============================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;        // accumulator row owned by this thread
-    if (nsteps > 0) {
-      mbar_wait(tmem_full_bar, 0);
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const TileCoord t = decode_tile<MODE, BLOCK_N>(P, tile);
+      const uint32_t acc = tile_iter & 1;
+      const uint32_t acc_ph = (tile_iter >> 1) & 1;
+      mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
-    }
-    bool row_ok;
-    long long row_off;
-    if (MODE == MODE_GEMM) {
-      row_ok = (m0 + r) < P.M;
-      row_off = (long long)z * P.z_stride_out + (long long)(m0 + r) * P.ld_out;
-    } else if (MODE == MODE_CONV) {
-      const int dy = r / P.tw, dx = r - dy * P.tw;
-      const int oh = oh0 + dy, ow = ow0 + dx;
-      row_ok = oh < P.oh_ext[z] && ow < P.ow_ext[z];
-      const int fh = oh * P.sy + P.oy[z], fw = ow * P.sx + P.ox[z];
-      row_off = (((long long)img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
-    } else {
-      row_ok = (m0 + r) < P.M;
-      row_off = (long long)z * P.z_stride_out + (long long)wg_tap * P.tap_stride_out +
-                (long long)(m0 + r) * P.ld_out;
-    }
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      bool row_ok;
+      long long row_off;
+      if (MODE == MODE_GEMM) {
+        row_ok = (t.m0 + r) < P.M;
+        row_off = (long long)t.z * P.z_stride_out + (long long)(t.m0 + r) * P.ld_out;
+      } else if (MODE == MODE_CONV) {
+        const int dy = r / P.tw, dx = r - dy * P.tw;
+        const int oh = t.oh0 + dy, ow = t.ow0 + dx;
+        row_ok = oh < P.oh_ext[t.z] && ow < P.ow_ext[t.z];
+        const int fh = oh * P.sy + P.oy[t.z], fw = ow * P.sx + P.ox[t.z];
+        row_off = (((long long)t.img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
+      } else {
+        row_ok = (t.m0 + r) < P.M;
+        row_off = (long long)t.z * P.z_stride_out + (long long)t.wg_tap * P.tap_stride_out +
+                  (long long)(t.m0 + r) * P.ld_out;
+      }
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
-      float v[16];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
-      if (nsteps > 0) {
-        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-      }
-      const int n = n0 + c;
-      if (!row_ok || n >= P.N) continue;
-      if (P.epi == EPI_F32) {
-        float* dst = reinterpret_cast<float*>(P.out) + row_off + n;
-        if (n + 16 <= P.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        float v[16];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
+        if (t.nsteps > 0) {
+          tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
         } else {
-          for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = v[i];
-        }
-      } else {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + row_off + n;
-        const bool full = n + 16 <= P.N;
-        if (P.bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += (full || n + i < P.N) ? __ldg(P.bias + n + i) : 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
-        if (P.slope != 1.f) {
+        const int n = t.n0 + c;
+        if (!row_ok || n >= P.N) continue;
+        if (P.epi == EPI_F32) {
+          float* dst = reinterpret_cast<float*>(P.out) + row_off + n;
+          if (n + 16 <= P.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * P.slope;
-        }
-        if (P.mask_src) {
-          const __nv_bfloat16* ms = P.mask_src + row_off + n;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (full || n + i < P.N) v[i] *= (__bfloat162float(ms[i]) > 0.f ? 1.f : P.mask_slope);
-        }
-        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = v[i];
           }
-          reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         } else {
-          for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = __float2bfloat16(v[i]);
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + row_off + n;
+          const bool full = n + 16 <= P.N;
+          if (P.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += (full || n + i < P.N) ? __ldg(P.bias + n + i) : 0.f;
+          }
+          if (P.slope != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * P.slope;
+          }
+          if (P.mask_src) {
+            const __nv_bfloat16* ms = P.mask_src + row_off + n;
+            if (full && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
+              const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(ms));
+              const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(ms) + 1);
+              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                // bf16 > 0  <=>  sign bit clear and not zero
+                const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+                v[2 * i] *= (lo != 0u && lo < 0x8000u) ? 1.f : P.mask_slope;
+                v[2 * i + 1] *= (hi != 0u && hi < 0x8000u) ? 1.f : P.mask_slope;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (full || n + i < P.N) v[i] *= (__bfloat162float(ms[i]) > 0.f ? 1.f : P.mask_slope);
+            }
+          }
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+            for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = __float2bfloat16(v[i]);
+          }
         }
       }
+      // this thread's TMEM reads of the tile are complete (tcgen05.wait::ld in tmem_ld16): release the buffer
+      __syncwarp();
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar(acc));
     }
   }
 
@@ -423,7 +483,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_d, TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

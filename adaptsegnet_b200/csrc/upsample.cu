@@ -25,6 +25,8 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ x, float* __restri
     const Lerp lx = lerp_at(min(xv * VEC + k, W - 1), sw, w);
     i0[k] = lx.i0; i1[k] = lx.i1; l0[k] = lx.l0; l1[k] = lx.l1;
   }
+  const int base = i0[0], b1 = min(base + 1, w - 1), b2 = min(base + 2, w - 1);
+  const bool narrow = (i0[VEC - 1] - base) <= 1 && (i1[VEC - 1] - base) <= 2;
   const int n_rows = NC * H;
   for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
     const int nc = row / H;
@@ -33,10 +35,23 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ x, float* __restri
     const float* r0 = x + ((int64_t)nc * h + ly.i0) * w;
     const float* r1 = x + ((int64_t)nc * h + ly.i1) * w;
     float out[VEC];
+    if (VEC == 4 && narrow) {
+      // the 4 outputs touch at most source columns base, base+1, base+2: 6 gathers instead of 16
+      const float a0 = __ldg(r0 + base), a1 = __ldg(r0 + b1), a2 = __ldg(r0 + b2);
+      const float c0 = __ldg(r1 + base), c1 = __ldg(r1 + b1), c2 = __ldg(r1 + b2);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k)
-      out[k] = ly.l0 * (l0[k] * __ldg(r0 + i0[k]) + l1[k] * __ldg(r0 + i1[k])) +
-               ly.l1 * (l0[k] * __ldg(r1 + i0[k]) + l1[k] * __ldg(r1 + i1[k]));
+      for (int k = 0; k < VEC; ++k) {
+        const int d = i0[k] - base, e = i1[k] - base;
+        const float t0 = d ? a1 : a0, t1 = e == 0 ? a0 : (e == 1 ? a1 : a2);
+        const float u0 = d ? c1 : c0, u1 = e == 0 ? c0 : (e == 1 ? c1 : c2);
+        out[k] = ly.l0 * (l0[k] * t0 + l1[k] * t1) + ly.l1 * (l0[k] * u0 + l1[k] * u1);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        out[k] = ly.l0 * (l0[k] * __ldg(r0 + i0[k]) + l1[k] * __ldg(r0 + i1[k])) +
+                 ly.l1 * (l0[k] * __ldg(r1 + i0[k]) + l1[k] * __ldg(r1 + i1[k]));
+    }
     float* dst = y + (int64_t)row * W + (int64_t)xv * VEC;
     if (VEC == 4) {
       st_stream(reinterpret_cast<float4*>(dst), make_float4(out[0], out[1], out[2], out[3]));
@@ -92,6 +107,65 @@ upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int n
         if (a1 == j) acc += b1 * v;
       }
       T[(int64_t)(row0 + rl) * w + j] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// Fast variant of the width pass for moderate magnifications (<= UPB_MAXT source columns per output):
+// thread j keeps the weights w(X, j) of its ~2/scale + 5 candidate columns in registers (they are the
+// same for every row) and the staged rows are skewed (addr = X + X/32) so that lanes striding the row
+// by the magnification hit distinct banks.  Per output: <= UPB_MAXT x (LDS + FMA).
+constexpr int UPB_MAXT = 24;
+__device__ __forceinline__ int skew(int X) { return X + (X >> 5); }
+__global__ void __launch_bounds__(1024)
+upsample_bwd_w_fast_kernel(const float* __restrict__ dy, float* __restrict__ T, int n_rows, int w, int W,
+                           float sw, int vec_ok) {
+  extern __shared__ float rows_sh[];  // [UPB_ROWS][skew(W) + 1]
+  const int pitch = skew(W) + 1;
+  const int j = threadIdx.x;
+  float wgt[UPB_MAXT];
+  int lo = 0;
+  if (j < w) {
+    const float inv = 1.f / sw;
+    lo = max(0, (int)floorf((float)(j - 1) * inv) - 2);
+    const int hi = min(W - 1, (int)ceilf((float)(j + 1) * inv) + 2);
+#pragma unroll
+    for (int k = 0; k < UPB_MAXT; ++k) {
+      const int X = lo + k;
+      float f = 0.f;
+      if (X <= hi) {
+        const Lerp lx = lerp_at(X, sw, w);
+        f = (lx.i0 == j ? lx.l0 : 0.f) + (lx.i1 == j ? lx.l1 : 0.f);
+      }
+      wgt[k] = f;
+    }
+  }
+  for (int row0 = blockIdx.x * UPB_ROWS; row0 < n_rows; row0 += gridDim.x * UPB_ROWS) {
+    const int rows_here = min(UPB_ROWS, n_rows - row0);
+    const float* src = dy + (int64_t)row0 * W;
+    if (vec_ok) {
+      for (int i = threadIdx.x; i < rows_here * (W / 4); i += blockDim.x) {
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(src) + i);
+        const int rl = (i * 4) / W, X = i * 4 - rl * W;
+        float* d = rows_sh + rl * pitch;
+        d[skew(X)] = v.x; d[skew(X + 1)] = v.y; d[skew(X + 2)] = v.z; d[skew(X + 3)] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < rows_here * W; i += blockDim.x) {
+        const int rl = i / W, X = i - rl * W;
+        rows_sh[rl * pitch + skew(X)] = src[i];
+      }
+    }
+    __syncthreads();
+    if (j < w) {
+      for (int rl = 0; rl < rows_here; ++rl) {
+        const float* row = rows_sh + rl * pitch;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < UPB_MAXT; ++k) acc = fmaf(wgt[k], row[skew(min(lo + k, W - 1))], acc);
+        T[(int64_t)(row0 + rl) * w + j] = acc;
+      }
     }
     __syncthreads();
   }
@@ -224,7 +298,15 @@ extern "C" int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, i
     ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     prof::Scope ps("upsample_bwd_w", 0, 4.0 * N * C * ((double)H * W + (double)H * w), st);
-    upsample_bwd_w_kernel<<<grid_w, UP_THREADS, smem, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
+    const bool fast = sw > 0.f && w <= 1024 && (int)ceilf(2.f / sw) + 7 <= UPB_MAXT;
+    if (fast) {
+      const size_t smem_f = (size_t)UPB_ROWS * (W + (W >> 5) + 1) * 4;
+      if (smem_f > 48 * 1024)
+        ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+      upsample_bwd_w_fast_kernel<<<grid_w, (unsigned)round_up(w, 32), smem_f, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
+    } else {
+      upsample_bwd_w_kernel<<<grid_w, UP_THREADS, smem, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
+    }
     ASN_LAUNCH_CHECK();
   }
   int64_t items = (int64_t)N * C * h * w;
