@@ -127,27 +127,30 @@ aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYc
   const int n = blockIdx.x / groups_per_img;
   const int q0 = (blockIdx.x % groups_per_img) * 32;
   const int J = taps.n_taps * n_cls;
-  for (int idx = threadIdx.x; idx < NP * 32; idx += 256) {
-    const int j = idx >> 5, ql = idx & 31;
-    const int q = q0 + ql;
-    float v = 0.f;
-    if (j < J && q < P) {
-      const int t = j / n_cls, c = j - t * n_cls;
-      const int h = q / W - taps.dh[t], w = q % W - taps.dw[t];
-      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
-        v = __ldg(dy + ((int64_t)n * n_cls + c) * P + (int64_t)h * W + w);
+  const int ql = threadIdx.x & 31;       // lane = pixel -> coalesced reads of dy rows and writes of dYcolT rows
+  const int q = q0 + ql;
+  const int qh = q / W, qw = q - qh * W;
+  const float* dyn = dy + (int64_t)n * n_cls * P;
+  // zero the padding columns [J, NP) once
+  for (int idx = threadIdx.x; idx < (NP - J) * 32; idx += 256) tile[(idx & 31) * NP + J + (idx >> 5)] = __float2bfloat16(0.f);
+  for (int t = threadIdx.x >> 5; t < taps.n_taps; t += 8) {   // warp = tap
+    const int h = qh - taps.dh[t], w = qw - taps.dw[t];
+    const bool ok = q < P && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+    const float* src = dyn + (int64_t)h * W + w;
+    for (int c = 0; c < n_cls; ++c) {
+      const __nv_bfloat16 bv = __float2bfloat16(ok ? __ldg(src + (int64_t)c * P) : 0.f);
+      const int j = t * n_cls + c;
+      tile[ql * NP + j] = bv;
+      if (q < P) dYcolT[(int64_t)j * ldt + (int64_t)n * P + q] = bv;
     }
-    const __nv_bfloat16 bv = __float2bfloat16(v);
-    tile[ql * NP + j] = bv;
-    if (q < P) dYcolT[(int64_t)j * ldt + (int64_t)n * P + q] = bv;
   }
   __syncthreads();
   // rows q0..q0+31 of dYcol are contiguous: NP*2 bytes each, NP % 8 == 0 -> 16-byte vectors
   const int vec_per_row = NP / 8;
-  const uint4* src = reinterpret_cast<const uint4*>(tile);
+  const uint4* srcv = reinterpret_cast<const uint4*>(tile);
   uint4* dst = reinterpret_cast<uint4*>(dYcol + ((int64_t)n * P + q0) * NP);
   const int rows = min(32, P - q0);
-  for (int i = threadIdx.x; i < rows * vec_per_row; i += 256) dst[i] = src[i];
+  for (int i = threadIdx.x; i < rows * vec_per_row; i += 256) dst[i] = srcv[i];
 }
 
 // Wp[j][ci] (bf16, j = t*n_cls + c, rows >= J zero) and WpT[ci][j] from the fp32 OIHW branch weights

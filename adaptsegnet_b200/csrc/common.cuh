@@ -61,6 +61,15 @@ static inline int wave_grid(int64_t work_items, int threads, int ctas_per_sm) {
   return (int)(need < cap ? need : cap);
 }
 
+// one work item per thread: CTAs launch and retire continuously, which keeps a steady stream of loads in
+// flight (a capped grid-stride grid phase-locks: every CTA loads, then every CTA computes)
+static inline int full_grid(int64_t work_items, int threads) {
+  int64_t need = (work_items + threads - 1) / threads;
+  if (need < 1) need = 1;
+  const int64_t cap = 0x7fffffff;
+  return (int)(need < cap ? need : cap);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

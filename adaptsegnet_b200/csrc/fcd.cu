@@ -110,11 +110,11 @@ __host__ __device__ inline int tap_a(int k) { return k == 0 ? -1 : (k == 3 ? 1 :
 __host__ __device__ inline int tap_r(int k) { return (k == 0 || k == 2) ? 1 : 0; }
 
 // ---- input pack: fp32 NCHW (probabilities or logits) -> bf16 [N][H][W0p][32] ------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 fcd_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a0, int N, int C, int H, int W,
                       int W0p, int softmax) {
   const int64_t total = (int64_t)N * H * W0p;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int wp = (int)(i % W0p);
     const int h = (int)((i / W0p) % H);
     const int n = (int)(i / ((int64_t)W0p * H));
@@ -157,11 +157,11 @@ fcd_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a
 
 // dA0 bf16 [N][H][W0p][32] -> dx fp32 NCHW; with logits given, the channel-softmax backward is fused:
 // dz = p * (g - sum_c p*g), p = softmax(x).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 fcd_unpack_dx_kernel(const __nv_bfloat16* __restrict__ da0, const float* __restrict__ logits,
                      float* __restrict__ dx, int N, int C, int H, int W, int W0p) {
   const int64_t total = (int64_t)N * H * W;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
     const int h = (int)((i / W) % H);
     const int n = (int)(i / ((int64_t)W * H));
@@ -740,7 +740,7 @@ extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpa
   for (int l = 0; l <= 4; ++l) A[l] = reinterpret_cast<__nv_bfloat16*>(ab + p.act_off[l]);
   {
     prof::Scope ps("fcd_pack_input", 0, (double)N * H * W * (4.0 * n_cls + 64.0), st);
-    fcd_pack_input_kernel<<<wave_grid((int64_t)N * H * p.W0p, 256, 8), 256, 0, st>>>(x_nchw, A[0], N, n_cls, H, W,
+    fcd_pack_input_kernel<<<full_grid((int64_t)N * H * p.W0p, 128), 128, 0, st>>>(x_nchw, A[0], N, n_cls, H, W,
                                                                                      p.W0p, x_is_logits);
     ASN_LAUNCH_CHECK();
   }
@@ -783,7 +783,7 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
   const float* wc = reinterpret_cast<const float*>(wb + p.wc_off);
 
   // classifier
-  fcd_cls_dgrad_kernel<<<wave_grid((int64_t)N * p.H[4] * p.W[4] * (p.C[4] / 2), 256, 8), 256, 0, st>>>(
+  fcd_cls_dgrad_kernel<<<full_grid((int64_t)N * p.H[4] * p.W[4] * (p.C[4] / 2), 256), 256, 0, st>>>(
       dout, wc, A[4], dPre[4], N, p.H[4], p.W[4], p.C[4], p.H[5], p.W[5]);
   ASN_LAUNCH_CHECK();
   if (dparams_host) {
@@ -809,7 +809,7 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
   }
   if (dx_nchw) {
     prof::Scope ps("fcd_unpack_dx", 0, (double)N * H * W * (64.0 + 4.0 * n_cls * (x_logits ? 2 : 1)), st);
-    fcd_unpack_dx_kernel<<<wave_grid((int64_t)N * H * W, 256, 8), 256, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls, H, W,
+    fcd_unpack_dx_kernel<<<full_grid((int64_t)N * H * W, 128), 128, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls, H, W,
                                                                                 p.W0p);
     ASN_LAUNCH_CHECK();
   }

@@ -7,7 +7,7 @@
 
 namespace asn {
 
-constexpr int PW_THREADS = 256;
+constexpr int PW_THREADS = 128;
 
 struct CeStats {
   double loss_sum;
@@ -317,13 +317,13 @@ static int launch_ce(const float* z, const int64_t* y, int N, int C, int H, int 
   prof::Scope ps(BWD ? "softmax_ce_bwd" : "softmax_ce_fwd", 0,
                  (double)N * HW * (4.0 * C * (BWD ? 2 : 1) + 8.0), st);
   if (C == 19 && vec) {
-    int grid = wave_grid((int64_t)N * (HW / 4), PW_THREADS, 4);
+    int grid = full_grid((int64_t)N * (HW / 4), PW_THREADS);
     ce_kernel<19, 4, BWD><<<grid, PW_THREADS, 0, st>>>(z, yl, N, HW, ignore, mask_negative, cw, size_average, s, gscale, dz);
   } else if (C == 19) {
-    int grid = wave_grid((int64_t)N * HW, PW_THREADS, 8);
+    int grid = full_grid((int64_t)N * HW, PW_THREADS);
     ce_kernel<19, 1, BWD><<<grid, PW_THREADS, 0, st>>>(z, yl, N, HW, ignore, mask_negative, cw, size_average, s, gscale, dz);
   } else {
-    int grid = wave_grid((int64_t)N * HW, PW_THREADS, 8);
+    int grid = full_grid((int64_t)N * HW, PW_THREADS);
     ce_generic_kernel<BWD><<<grid, PW_THREADS, 0, st>>>(z, yl, N, C, HW, ignore, mask_negative, cw, size_average, s, gscale, dz);
   }
   ASN_LAUNCH_CHECK();
@@ -362,11 +362,11 @@ static int launch_softmax(const float* a, const float* b, float* out, int N, int
                                         reinterpret_cast<uintptr_t>(out)) & 15) == 0);
   prof::Scope ps(BWD ? "softmax_bwd" : "softmax_fwd", 0, 4.0 * N * C * HW * (BWD ? 3 : 2), st);
   if (C == 19 && vec) {
-    softmax_kernel<19, 4, BWD><<<wave_grid((int64_t)N * (HW / 4), PW_THREADS, 4), PW_THREADS, 0, st>>>(a, b, out, N, HW);
+    softmax_kernel<19, 4, BWD><<<full_grid((int64_t)N * (HW / 4), PW_THREADS), PW_THREADS, 0, st>>>(a, b, out, N, HW);
   } else if (C == 19) {
-    softmax_kernel<19, 1, BWD><<<wave_grid((int64_t)N * HW, PW_THREADS, 8), PW_THREADS, 0, st>>>(a, b, out, N, HW);
+    softmax_kernel<19, 1, BWD><<<full_grid((int64_t)N * HW, PW_THREADS), PW_THREADS, 0, st>>>(a, b, out, N, HW);
   } else {
-    softmax_generic_kernel<BWD><<<wave_grid((int64_t)N * HW, PW_THREADS, 8), PW_THREADS, 0, st>>>(a, b, out, N, C, HW);
+    softmax_generic_kernel<BWD><<<full_grid((int64_t)N * HW, PW_THREADS), PW_THREADS, 0, st>>>(a, b, out, N, C, HW);
   }
   ASN_LAUNCH_CHECK();
   return ASN_OK;

@@ -27,6 +27,12 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ x, float* __restri
   }
   const int base = i0[0], b1 = min(base + 1, w - 1), b2 = min(base + 2, w - 1);
   const bool narrow = (i0[VEC - 1] - base) <= 1 && (i1[VEC - 1] - base) <= 2;
+  float wx[VEC][3];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k)
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      wx[k][m] = (i0[k] - base == m ? l0[k] : 0.f) + (i1[k] - base == m ? l1[k] : 0.f);
   const int n_rows = NC * H;
   for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
     const int nc = row / H;
@@ -36,16 +42,13 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ x, float* __restri
     const float* r1 = x + ((int64_t)nc * h + ly.i1) * w;
     float out[VEC];
     if (VEC == 4 && narrow) {
-      // the 4 outputs touch at most source columns base, base+1, base+2: 6 gathers instead of 16
-      const float a0 = __ldg(r0 + base), a1 = __ldg(r0 + b1), a2 = __ldg(r0 + b2);
-      const float c0 = __ldg(r1 + base), c1 = __ldg(r1 + b1), c2 = __ldg(r1 + b2);
+      // the 4 outputs touch at most source columns base, base+1, base+2: 6 gathers, then
+      // out[k] = sum_m wx[k][m] * (ly.l0 * r0[m] + ly.l1 * r1[m]) with the x-weights folded once per thread
+      const float v0 = ly.l0 * __ldg(r0 + base) + ly.l1 * __ldg(r1 + base);
+      const float v1 = ly.l0 * __ldg(r0 + b1) + ly.l1 * __ldg(r1 + b1);
+      const float v2 = ly.l0 * __ldg(r0 + b2) + ly.l1 * __ldg(r1 + b2);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const int d = i0[k] - base, e = i1[k] - base;
-        const float t0 = d ? a1 : a0, t1 = e == 0 ? a0 : (e == 1 ? a1 : a2);
-        const float u0 = d ? c1 : c0, u1 = e == 0 ? c0 : (e == 1 ? c1 : c2);
-        out[k] = ly.l0 * (l0[k] * t0 + l1[k] * t1) + ly.l1 * (l0[k] * u0 + l1[k] * u1);
-      }
+      for (int k = 0; k < VEC; ++k) out[k] = wx[k][0] * v0 + wx[k][1] * v1 + wx[k][2] * v2;
     } else {
 #pragma unroll
       for (int k = 0; k < VEC; ++k)
@@ -66,7 +69,7 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ x, float* __restri
 // backward pass 1: collapse the width.  A CTA stages UPB_ROWS full-res rows (nc, Y) in shared memory
 // with coalesced 16-byte loads, then every thread sums, for one (row, j), the (<= ~2/scale) columns
 // whose x0 or x1 is j.  T[nc, Y, j] (N*C*H*w floats) is the workspace.
-constexpr int UPB_ROWS = 4;
+constexpr int UPB_ROWS = 8;
 __global__ void __launch_bounds__(UP_THREADS)
 upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int n_rows, int w, int W, float sw,
                       int vec_ok) {
@@ -145,11 +148,24 @@ upsample_bwd_w_fast_kernel(const float* __restrict__ dy, float* __restrict__ T, 
     const int rows_here = min(UPB_ROWS, n_rows - row0);
     const float* src = dy + (int64_t)row0 * W;
     if (vec_ok) {
-      for (int i = threadIdx.x; i < rows_here * (W / 4); i += blockDim.x) {
-        const float4 v = ld_stream(reinterpret_cast<const float4*>(src) + i);
-        const int rl = (i * 4) / W, X = i * 4 - rl * W;
-        float* d = rows_sh + rl * pitch;
-        d[skew(X)] = v.x; d[skew(X + 1)] = v.y; d[skew(X + 2)] = v.z; d[skew(X + 3)] = v.w;
+      // batches of 4 independent 16-byte loads per thread before the first shared-memory store
+      const int n4 = rows_here * (W / 4);
+      for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (i < n4) v[u] = ld_stream(reinterpret_cast<const float4*>(src) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (i < n4) {
+            const int rl = (i * 4) / W, X = i * 4 - rl * W;
+            float* d = rows_sh + rl * pitch;
+            d[skew(X)] = v[u].x; d[skew(X + 1)] = v[u].y; d[skew(X + 2)] = v[u].z; d[skew(X + 3)] = v[u].w;
+          }
+        }
       }
     } else {
       for (int i = threadIdx.x; i < rows_here * W; i += blockDim.x) {
@@ -201,8 +217,8 @@ upsample_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred, 
                        int w, int H, int W, float sh, float sw) {
   const int wv = (W + 3) / 4;
   const int64_t total = (int64_t)N * H * wv;
-  for (int64_t i = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * UP_THREADS) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
     int xv = (int)(i % wv);
     int64_t row = i / wv;
     int Y = (int)(row % H);
@@ -312,7 +328,7 @@ extern "C" int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, i
   int64_t items = (int64_t)N * C * h * w;
   {
     prof::Scope ps("upsample_bwd_h", 0, 4.0 * N * C * ((double)H * w + (double)h * w), st);
-    upsample_bwd_h_kernel<<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(T, dx, N * C, h, w, H, sh);
+    upsample_bwd_h_kernel<<<full_grid(items, UP_THREADS), UP_THREADS, 0, st>>>(T, dx, N * C, h, w, H, sh);
     ASN_LAUNCH_CHECK();
   }
   return ASN_OK;
@@ -326,7 +342,7 @@ extern "C" int asn_upsample_argmax_u8(const float* x, int N, int C, int h, int w
   float sh = lerp_scale(h, H), sw = lerp_scale(w, W);
   int64_t items = (int64_t)N * H * ((W + 3) / 4);
   prof::Scope ps("upsample_argmax", 0, 4.0 * N * C * h * w + (double)N * H * W, st);
-  upsample_argmax_kernel<<<wave_grid(items, UP_THREADS, 8), UP_THREADS, 0, st>>>(x, pred, N, C, h, w, H, W, sh, sw);
+  upsample_argmax_kernel<<<full_grid(items, 128), 128, 0, st>>>(x, pred, N, C, h, w, H, W, sh, sw);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }

@@ -323,6 +323,10 @@ class AsppWeightPack:
         self.key = None
         self.wp = self.wpt = self.bias_sum = None
 
+    def invalidate(self):
+        """force a re-pack on the next use (CUDA-graph capture: the pack kernels must be part of the graph)"""
+        self.key = None
+
     def get(self, weights, biases, n_active):
         key = tuple((w.data_ptr(), w._version) for w in list(weights) + list(biases)) + (n_active,)
         if key != self.key:
@@ -443,6 +447,9 @@ class FcdWeightPack:
     def __init__(self):
         self.key = None
         self.buf = None
+
+    def invalidate(self):
+        self.key = None
 
     def get(self, params, n_cls, ndf):
         key = tuple((p.data_ptr(), p._version) for p in params)

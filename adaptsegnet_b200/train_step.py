@@ -79,8 +79,14 @@ class FlatGrads:
 class AdaptSegTrainer:
     """Holds G (DeeplabMulti), D1/D2 (FCDiscriminator), their optimizers and runs iterations."""
 
-    def __init__(self, cfg: TrainConfig | None = None, device="cuda", model=None, model_D1=None, model_D2=None):
+    def __init__(self, cfg: TrainConfig | None = None, device="cuda", model=None, model_D1=None, model_D2=None,
+                 use_cuda_graph=False):
+        """``use_cuda_graph``: capture everything of an iteration up to the gradients (both G forwards/backwards,
+        all discriminator passes, ~2 300 kernel launches) into one CUDA graph and replay it; the gradient
+        all-reduce and the three optimizer steps stay eager.  Same kernels, same order, no per-launch CPU cost."""
         self.cfg = cfg = cfg or TrainConfig()
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph = None
         self.device = torch.device(device)
         self.multi = cfg.level == "multi-level"
         self.model = (model or DeeplabMulti(cfg.num_classes)).to(self.device).train()
@@ -120,16 +126,20 @@ class AdaptSegTrainer:
             for p in module.parameters():
                 p.requires_grad = flag
 
-    def step(self, src_images, src_labels, tgt_images, i_iter=0, group=None, do_optimizer_step=True):
-        """One iteration.  Returns the dict of (device) loss scalars the reference prints.
-        ``do_optimizer_step=False`` leaves the accumulated gradients in place (parity tests)."""
+    def _packs(self):
+        packs = [self.model.layer5._pack, self.model.layer6._pack, self.model_D2._pack]
+        if self.multi:
+            packs.append(self.model_D1._pack)
+        return packs
+
+    def _grads_step(self, src_images, src_labels, tgt_images):
+        """Everything of train...:578-679: forwards, losses, backwards; gradients end up in the flat buffers."""
         cfg = self.cfg
         it = cfg.iter_size
         self.flat_G.zero()
         self.flat_D2.zero()
         if self.multi:
             self.flat_D1.zero()
-        self._adjust_lr(i_iter)
         out = {}
         # ---------------- train G: discriminators frozen (train...:583-587) ----------------
         self._set_requires_grad(self.model_D1, False)
@@ -167,7 +177,41 @@ class AdaptSegTrainer:
             l_tgt = self.bce_loss(self._d_out(D, p_tgt.detach()), TARGET_LABEL) / it / 2
             l_tgt.backward()
             out[name] = l_src.detach() + l_tgt.detach()
+        return out
 
+    def _capture(self, src_images, src_labels, tgt_images):
+        """warm up on a side stream (cuDNN autotuning, lazy kernel attributes), then capture one _grads_step"""
+        self._static_in = (src_images.clone(), src_labels.clone(), tgt_images.clone())
+        bn_state = {k: v.clone() for k, v in self.model.state_dict().items()
+                    if k.endswith(("running_mean", "running_var", "num_batches_tracked"))}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._grads_step(*self._static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.model.load_state_dict(bn_state, strict=False)  # the warm-up must not count as training steps
+        for pk in self._packs():
+            pk.invalidate()                                  # weight packing becomes part of the graph
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._grads_step(*self._static_in)
+        self.model.load_state_dict(bn_state, strict=False)  # capture does not execute, but keep it explicit
+
+    def step(self, src_images, src_labels, tgt_images, i_iter=0, group=None, do_optimizer_step=True):
+        """One iteration.  Returns the dict of (device) loss scalars the reference prints.
+        ``do_optimizer_step=False`` leaves the accumulated gradients in place (parity tests)."""
+        self._adjust_lr(i_iter)
+        if self.use_cuda_graph:
+            if self._graph is None:
+                self._capture(src_images, src_labels, tgt_images)
+            for dst, src in zip(self._static_in, (src_images, src_labels, tgt_images)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            out = self._static_out
+        else:
+            out = self._grads_step(src_images, src_labels, tgt_images)
         # ---------------- data-parallel averaging, then the three optimizer steps ----------------
         self.flat_G.all_reduce_mean(group)
         self.flat_D2.all_reduce_mean(group)

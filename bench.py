@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--level", default="multi-level", choices=["multi-level", "single-level"])
     ap.add_argument("--gan", default="Vanilla", choices=["Vanilla", "LS"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="replay the iteration (up to the gradients) as a CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
+    ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -163,6 +166,8 @@ def workload_config(args, world):
             "per_gpu_batch": "1 source + 1 target image", "global_pairs_per_step": world,
             "parallelism": f"dp{world} (NCCL all-reduce of 3 flat gradient buffers per step)",
             "hot_path": "libasn_b200 sm_100a kernels (tcgen05 heads + discriminators, fused losses)",
+            "execution": ("forward/backward of the iteration replayed as one CUDA graph; all-reduce + optimizers eager"
+                          if getattr(args, "cuda_graph", 0) and args.impl == "b200" else "eager"),
             "trunk": "ResNet-101 as PyTorch modules on cuDNN (TF32), timed, not rewritten",
             "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed"}
 
@@ -185,10 +190,11 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.benchmark = True  # train_gta2cityscapes_multi.py:228
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)  # train_gta2cityscapes_multi.py:228
 
     torch.manual_seed(SEED)  # identical replicas
-    trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan), device=dev)
+    trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan), device=dev,
+                              use_cuda_graph=bool(args.cuda_graph))
     src_h, lab_h, tgt_h = TR.synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
     src_h, lab_h, tgt_h = src_h.pin_memory(), lab_h.pin_memory(), tgt_h.pin_memory()
     src, lab, tgt = src_h.to(dev), lab_h.to(dev), tgt_h.to(dev)
@@ -217,40 +223,58 @@ def run_b200(args):
         trainer.step(src, lab, tgt, i_iter=it[0])
         it[0] += 1
 
-    losses_host = torch.empty(6, dtype=torch.float32).pin_memory()
+    n_losses = 6 if args.level == "multi-level" else 3
+    losses_host = torch.empty(n_losses, dtype=torch.float32).pin_memory()
 
     def step_e2e(_):
-        s = src_h.to(dev, non_blocking=True)
-        l = lab_h.to(dev, non_blocking=True)
-        t = tgt_h.to(dev, non_blocking=True)
+        # host -> device copies of this step's inputs from pinned memory (straight into the graph's static
+        # input buffers when replaying a CUDA graph), the step, and the losses back on the host
+        if trainer.use_cuda_graph and trainer._graph is not None:
+            s, l, t = trainer._static_in
+            s.copy_(src_h, non_blocking=True)
+            l.copy_(lab_h, non_blocking=True)
+            t.copy_(tgt_h, non_blocking=True)
+        else:
+            s = src_h.to(dev, non_blocking=True)
+            l = lab_h.to(dev, non_blocking=True)
+            t = tgt_h.to(dev, non_blocking=True)
         out = trainer.step(s, l, t, i_iter=it[0])
         vals = torch.stack([v.float() for v in out.values()])
-        losses_host[:vals.numel()].copy_(vals, non_blocking=True)
+        losses_host.copy_(vals, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the losses every iteration
         it[0] += 1
 
     for _ in range(args.warmup):
         step_resident(0)
-    # ---- device-resident timing, with per-kernel events and clock sampling ----
+    # ---- device-resident timing with clock sampling ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    ms_total = timed(args.steps, step_resident)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end timing from pinned host buffers ----
+    ms_e2e = None
+    if not args.no_e2e:
+        step_e2e(0)
+        ms_e2e = timed(args.steps, step_e2e)
+    # ---- per-kernel CUDA-event timing, live inside K more steps.  Events cannot be recorded inside a captured
+    #      graph, so this pass runs the same iteration eagerly (same kernels, same inputs, same order). ----
+    graph_mode = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False
+    step_resident(0)
     prof.enable(True)
     launches0 = ops.launch_count
-    ms_total = timed(args.steps, step_resident)
+    ms_eager = timed(args.steps, step_resident)
     launches = ops.launch_count - launches0
     kernels = prof.report()
     prof.enable(False)
-    clocks = sampler.stop() if rank == 0 else None
-    # ---- end-to-end timing from pinned host buffers ----
-    step_e2e(0)
-    ms_e2e = timed(args.steps, step_e2e)
+    trainer.use_cuda_graph = graph_mode
 
     if rank == 0:
         peaks = load_peaks()
         ms_per_step = ms_total / args.steps
         value = world * 1000.0 / ms_per_step
-        e2e_value = world * 1000.0 / (ms_e2e / args.steps)
+        e2e_value = world * 1000.0 / (ms_e2e / args.steps) if ms_e2e else None
         # dominant kernel of the hot path (largest total device time among this library's kernels)
         name, rec = max(kernels.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = rec["ms"] / rec["launches"]
@@ -276,8 +300,9 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": int(src_h.numel() * 4 + lab_h.numel() * 8 + tgt_h.numel() * 4),
-                        "d2h_bytes_per_step": 4 * (6 if args.level == "multi-level" else 3)},
+                        "d2h_bytes_per_step": 4 * n_losses},
                 "gpu_launches": int(launches), "roofline": roof,
+                "cuda_graph": bool(graph_mode), "eager_ms_per_step_with_kernel_events": ms_eager / args.steps,
                 "hot_path_ms_per_step": hot_ms, "hot_path_kernels": breakdown}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan)

@@ -1,0 +1,62 @@
+"""Single-kernel microbenchmarks at BASELINE sizes (back-to-back launches, L2 flushed between cases).
+Writes a JSON dict {case: {us, gbs|tflops, frac}} -- used for profiles/ and DESIGN.md tables."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from adaptsegnet_b200 import ops, prof
+
+dev = "cuda"
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+    if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+torch.manual_seed(0)
+res = {}
+
+
+def run(name, fn, reps=10):
+    fn()
+    torch.cuda.synchronize()
+    prof.enable(True)
+    for _ in range(reps):
+        flush.zero_()          # evict: every case starts from HBM
+        fn()
+    torch.cuda.synchronize()
+    rep = prof.report()
+    prof.enable(False)
+    out = {}
+    for k, v in rep.items():
+        us = v["ms"] / v["launches"] * 1e3
+        e = {"us": round(us, 2), "launches": v["launches"] // reps}
+        if v["flops"] > 0:
+            e["tflops"] = round(v["flops"] / v["launches"] / (us * 1e-6) / 1e12, 1)
+            e["frac_of_bf16_burst"] = round(e["tflops"] / peaks["bf16_tflops"], 3)
+        else:
+            e["gbs"] = round(v["bytes"] / v["launches"] / (us * 1e-6) / 1e9, 1)
+            e["frac_of_hbm_copy"] = round(e["gbs"] / peaks["hbm_gbs"], 3)
+        out[k] = e
+    res[name] = out
+
+
+# config 5: 500 frames of 1024x2048 labels/predictions (here 50 per launch, int64 labels as the reference holds them)
+n_px = 50 * 1024 * 2048
+lab64 = torch.randint(0, 19, (n_px,), device=dev)
+lab64[torch.rand(n_px, device=dev) < 0.1] = 255
+pred = torch.randint(0, 19, (n_px,), device=dev, dtype=torch.uint8)
+lab8 = lab64.to(torch.uint8)
+run("fast_hist_i64_50frames", lambda: ops.fast_hist(lab64, pred, 19))
+run("fast_hist_u8_50frames", lambda: ops.fast_hist(lab8, pred, 19))
+lowres = torch.randn(1, 19, 512 // 8 * 1, 1024 // 8, device=dev)  # eval: logits at 1/8 of 512x1024
+run("upsample_argmax_eval_1024x2048", lambda: ops.upsample_argmax(lowres, (1024, 2048)))
+z = torch.randn(1, 19, 720, 1280, device=dev)
+y = torch.randint(0, 19, (1, 720, 1280), device=dev)
+zz = z.clone().requires_grad_(True)
+def ce():
+    l = ops.softmax_cross_entropy(zz, y)
+    l.backward()
+run("softmax_ce_720x1280", ce)
+lr = torch.randn(1, 19, 90, 160, device=dev, requires_grad=True)
+def up():
+    u = ops.upsample_bilinear(lr, (720, 1280))
+    u.backward(z)
+run("upsample_90x160_to_720x1280", up)
+print(json.dumps(res, indent=1))
