@@ -69,7 +69,7 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ x, float* __restri
 // backward pass 1: collapse the width.  A CTA stages UPB_ROWS full-res rows (nc, Y) in shared memory
 // with coalesced 16-byte loads, then every thread sums, for one (row, j), the (<= ~2/scale) columns
 // whose x0 or x1 is j.  T[nc, Y, j] (N*C*H*w floats) is the workspace.
-constexpr int UPB_ROWS = 8;
+constexpr int UPB_ROWS = 4;
 __global__ void __launch_bounds__(UP_THREADS)
 upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int n_rows, int w, int W, float sw,
                       int vec_ok) {
