@@ -70,6 +70,44 @@ nchw_to_ckp_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
   }
 }
 
+// channels_last input: x [N*P][C] fp32 -> bf16, same layout (the trunk already produced NHWC)
+__global__ void __launch_bounds__(256)
+nhwc_f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = ld_stream(reinterpret_cast<const float4*>(x) + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
+// channels_last input: x [NP][C] fp32 -> out [C][ld] bf16 (64 x 64 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+nhwc_to_ckp_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int64_t NP_, int64_t ld) {
+  __shared__ float tile[64][65];
+  const int64_t p0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int pl = i / 64, cl = i % 64;
+    const int64_t p = p0 + pl;
+    const int c = c0 + cl;
+    tile[pl][cl] = (p < NP_ && c < C) ? __ldg(x + p * C + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    const int cl = i / 32, pp = (i % 32) * 2;
+    const int c = c0 + cl;
+    const int64_t p = p0 + pp;
+    if (c >= C) continue;
+    if (p + 1 < NP_ && (((uintptr_t)(out + (int64_t)c * ld + p)) & 3) == 0) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(tile[pp][cl], tile[pp + 1][cl]);
+      *reinterpret_cast<__nv_bfloat162*>(out + (int64_t)c * ld + p) = v;
+    } else {
+      if (p < NP_) out[(int64_t)c * ld + p] = __float2bfloat16(tile[pp][cl]);
+      if (p + 1 < NP_) out[(int64_t)c * ld + p + 1] = __float2bfloat16(tile[pp + 1][cl]);
+    }
+  }
+}
+
 struct AsppTaps {
   int n_taps;       // 9 * n_active
   int dh[36], dw[36];
@@ -322,9 +360,9 @@ static int aspp_check(int N, int Cin, int H, int W, int n_cls, int n_active, con
   return ASN_OK;
 }
 
-extern "C" int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const float* bias_sum, float* y_nchw, int N,
-                            int Cin, int H, int W, int n_cls, const int* dil_host, int n_active, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+extern "C" int asn_aspp_fwd(const float* x_nchw, int x_channels_last, const void* wp_bf16, const float* bias_sum,
+                            float* y_nchw, int N, int Cin, int H, int W, int n_cls, const int* dil_host, int n_active,
+                            void* workspace, size_t workspace_bytes, void* stream) {
   ASN_CHECK_ARG(x_nchw && wp_bf16 && bias_sum && y_nchw && workspace, "asn_aspp_fwd: null pointer");
   int rc = aspp_check(N, Cin, H, W, n_cls, n_active, dil_host);
   if (rc) return rc;
@@ -338,7 +376,13 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const floa
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(base + ws.x_nhwc);
   float* Z = reinterpret_cast<float*>(base + ws.z);
   const int P = H * W;
-  {
+  if (x_channels_last) {
+    ASN_CHECK_ARG((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0, "asn_aspp_fwd: channels_last x must be 16-byte aligned");
+    prof::Scope ps("aspp_x_cast_bf16", 0, 6.0 * N * P * Cin, st);
+    const int64_t n4 = (int64_t)N * P * Cin / 4;
+    nhwc_f32_to_bf16_kernel<<<full_grid(n4, 256), 256, 0, st>>>(x_nchw, xn, n4);
+    ASN_LAUNCH_CHECK();
+  } else {
     prof::Scope ps("aspp_x_to_nhwc_bf16", 0, 6.0 * N * P * Cin, st);
     nchw_to_nhwc_bf16_kernel<<<dim3(cdiv(P, 64), cdiv(Cin, 64), N), 256, 0, st>>>(x_nchw, xn, Cin, P);
     ASN_LAUNCH_CHECK();
@@ -356,8 +400,8 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const floa
   return ASN_OK;
 }
 
-extern "C" int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const float* dy_nchw, float* dx_nchw,
-                            float* const* dw_oihw, float* db, int N, int Cin, int H, int W, int n_cls,
+extern "C" int asn_aspp_bwd(const float* x_nchw, int x_channels_last, const void* wpt_bf16, const float* dy_nchw,
+                            float* dx_nchw, float* const* dw_oihw, float* db, int N, int Cin, int H, int W, int n_cls,
                             const int* dil_host, int n_active, void* workspace, size_t workspace_bytes,
                             void* stream) {
   ASN_CHECK_ARG(dy_nchw && workspace, "asn_aspp_bwd: null pointer");
@@ -386,7 +430,12 @@ extern "C" int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const flo
     aspp_dycols_kernel<<<N * cdiv(P, 32), 256, smem, st>>>(dy_nchw, dycol, dycolt, N, H, W, n_cls, ws.NP, ws.ldp, taps);
     ASN_LAUNCH_CHECK();
   }
-  if (dx_nchw) {
+  if (dx_nchw && x_channels_last) {
+    // dX[N*P][Cin] = dYcol[N*P][NP] . WpT[Cin][NP]^T : the gradient lands in channels_last, all images at once
+    rc = umma::gemm_tn(dycol, wpt_bf16, dx_nchw, N * P, Cin, ws.NP, ws.NP, ws.NP, Cin, 1, 0, 256, st,
+                       "aspp_dgrad_gemm", 2.0 * N * P * (9.0 * n_active * n_cls) * Cin);
+    if (rc) return rc;
+  } else if (dx_nchw) {
     for (int n = 0; n < N; ++n) {
       rc = umma::gemm_tn(wpt_bf16, dycol + (int64_t)n * P * ws.NP, dx_nchw + (int64_t)n * Cin * P, Cin, P, ws.NP,
                          ws.NP, ws.NP, P, 1, 0, 256, st, "aspp_dgrad_gemm",
@@ -397,7 +446,12 @@ extern "C" int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const flo
   if (dw_oihw) {
     __nv_bfloat16* xk = reinterpret_cast<__nv_bfloat16*>(base + ws.x_ckp);
     float* part = reinterpret_cast<float*>(base + ws.dwpart);
-    {
+    if (x_channels_last) {
+      prof::Scope ps("aspp_x_to_ckp_bf16", 0, 6.0 * N * P * Cin, st);
+      nhwc_to_ckp_bf16_kernel<<<dim3(cdiv((int64_t)N * P, 64), cdiv(Cin, 64)), 256, 0, st>>>(x_nchw, xk, Cin,
+                                                                                              (int64_t)N * P, ws.ldp);
+      ASN_LAUNCH_CHECK();
+    } else {
       prof::Scope ps("aspp_x_to_bf16", 0, 6.0 * N * P * Cin, st);
       // vector path needs 16-byte aligned rows on both sides: P % 4 == 0 (then ld % 8 == 0 keeps the stores aligned)
       const bool vec = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);

@@ -42,6 +42,13 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+def _is_channels_last(t: torch.Tensor) -> bool:
+    """a CUDA fp32 (N,C,H,W) tensor stored NHWC (and not also NCHW-contiguous, i.e. C > 1 and H*W > 1)"""
+    return (isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 4 and t.dtype == torch.float32
+            and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+            and t.shape[1] % 4 == 0)
+
+
 def precision_mode() -> str:
     """'bf16' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core FFMA, 1e-4 mode)."""
     m = os.environ.get("ASN_PRECISION", "bf16").lower()
@@ -354,7 +361,8 @@ class _AsppHeadTC(torch.autograd.Function):
     def forward(ctx, x, pack, dils, n_active, *params):
         nb = len(params) // 2
         weights, biases = params[:nb], params[nb:]
-        x = _req(x, torch.float32, "x")
+        cl = _is_channels_last(x)
+        x = x if cl else _req(x, torch.float32, "x")
         wp, wpt, bias_sum = pack.get(weights, biases, n_active)
         N, cin, H, W = x.shape
         n_cls = weights[0].shape[0]
@@ -362,17 +370,17 @@ class _AsppHeadTC(torch.autograd.Function):
         nbytes = lib.asn_aspp_workspace_bytes(N, cin, H, W, n_cls, n_active)
         ws = _ws(nbytes, x.device)
         y = torch.empty((N, n_cls, H, W), dtype=torch.float32, device=x.device)
-        check(lib.asn_aspp_fwd(x.data_ptr(), wp.data_ptr(), bias_sum.data_ptr(), y.data_ptr(), N, cin, H, W, n_cls,
+        check(lib.asn_aspp_fwd(x.data_ptr(), int(cl), wp.data_ptr(), bias_sum.data_ptr(), y.data_ptr(), N, cin, H, W, n_cls,
                                _lib.int_array(dils), n_active, ws.data_ptr(), nbytes, _stream()), "asn_aspp_fwd")
         _count(3)
         ctx.save_for_backward(x, wpt)
-        ctx.cfg = (tuple(dils), n_active, nb, n_cls, tuple(w.shape for w in weights))
+        ctx.cfg = (tuple(dils), n_active, nb, n_cls, tuple(w.shape for w in weights), cl)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, wpt = ctx.saved_tensors
-        dils, n_active, nb, n_cls, wshapes = ctx.cfg
+        dils, n_active, nb, n_cls, wshapes, cl = ctx.cfg
         dy = _req(dy, torch.float32, "dy")
         N, cin, H, W = x.shape
         lib = _lib.load()
@@ -381,10 +389,10 @@ class _AsppHeadTC(torch.autograd.Function):
         need_b = any(ctx.needs_input_grad[4 + nb:])
         nbytes = lib.asn_aspp_workspace_bytes(N, cin, H, W, n_cls, n_active)
         ws = _ws(nbytes, x.device)
-        dx = torch.empty_like(x) if need_x else None
+        dx = torch.empty_like(x) if need_x else None  # keeps x's memory format (NCHW or channels_last)
         dws = [torch.empty(wshapes[i], dtype=torch.float32, device=x.device) for i in range(n_active)] if need_w else None
         db = torch.empty((n_cls,), dtype=torch.float32, device=x.device) if need_b else None
-        check(lib.asn_aspp_bwd(x.data_ptr(), wpt.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_x else None,
+        check(lib.asn_aspp_bwd(x.data_ptr(), int(cl), wpt.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_x else None,
                                _lib.ptr_array([t.data_ptr() for t in dws]) if need_w else None,
                                db.data_ptr() if need_b else None, N, cin, H, W, n_cls, _lib.int_array(dils),
                                n_active, ws.data_ptr(), nbytes, _stream()), "asn_aspp_bwd")

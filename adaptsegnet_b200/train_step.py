@@ -80,16 +80,22 @@ class AdaptSegTrainer:
     """Holds G (DeeplabMulti), D1/D2 (FCDiscriminator), their optimizers and runs iterations."""
 
     def __init__(self, cfg: TrainConfig | None = None, device="cuda", model=None, model_D1=None, model_D2=None,
-                 use_cuda_graph=False):
+                 use_cuda_graph=False, channels_last=False):
         """``use_cuda_graph``: capture everything of an iteration up to the gradients (both G forwards/backwards,
         all discriminator passes, ~2 300 kernel launches) into one CUDA graph and replay it; the gradient
         all-reduce and the three optimizer steps stay eager.  Same kernels, same order, no per-launch CPU cost."""
         self.cfg = cfg = cfg or TrainConfig()
         self.use_cuda_graph = bool(use_cuda_graph)
+        self.channels_last = bool(channels_last)
         self._graph = None
         self.device = torch.device(device)
         self.multi = cfg.level == "multi-level"
         self.model = (model or DeeplabMulti(cfg.num_classes)).to(self.device).train()
+        if self.channels_last:
+            # execution detail of the unchanged trunk: cuDNN's sm_100 kernels are NHWC, so an NCHW trunk spends a
+            # quarter of its time in layout conversions; the head kernels take the channels_last features as they are
+            for name in ("conv1", "bn1", "layer1", "layer2", "layer3", "layer4"):
+                getattr(self.model, name).to(memory_format=torch.channels_last)
         self.model_D2 = (model_D2 or FCDiscriminator(cfg.num_classes)).to(self.device).train()
         self.model_D1 = (model_D1 or FCDiscriminator(cfg.num_classes)).to(self.device).train() if self.multi else None
         # optimizers exactly as train...:532-540 (the duplicated trunk parameters included, Q11)
@@ -144,6 +150,9 @@ class AdaptSegTrainer:
         # ---------------- train G: discriminators frozen (train...:583-587) ----------------
         self._set_requires_grad(self.model_D1, False)
         self._set_requires_grad(self.model_D2, False)
+        if self.channels_last:
+            src_images = src_images.contiguous(memory_format=torch.channels_last)
+            tgt_images = tgt_images.contiguous(memory_format=torch.channels_last)
         pred1, pred2 = self.model(src_images)
         loss_seg2 = self.seg_loss(pred2, src_labels)
         if self.multi:

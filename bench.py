@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the iteration (up to the gradients) as a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
+    ap.add_argument("--channels-last", type=int, default=1, help="run the (unchanged) trunk in channels_last")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
@@ -168,7 +169,9 @@ def workload_config(args, world):
             "hot_path": "libasn_b200 sm_100a kernels (tcgen05 heads + discriminators, fused losses)",
             "execution": ("forward/backward of the iteration replayed as one CUDA graph; all-reduce + optimizers eager"
                           if getattr(args, "cuda_graph", 0) and args.impl == "b200" else "eager"),
-            "trunk": "ResNet-101 as PyTorch modules on cuDNN (TF32), timed, not rewritten",
+            "trunk": ("ResNet-101 as PyTorch modules on cuDNN (TF32"
+                      + (", channels_last" if getattr(args, "channels_last", 0) and args.impl == "b200" else "")
+                      + "), timed, not rewritten"),
             "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -194,7 +197,7 @@ def run_b200(args):
 
     torch.manual_seed(SEED)  # identical replicas
     trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan), device=dev,
-                              use_cuda_graph=bool(args.cuda_graph))
+                              use_cuda_graph=bool(args.cuda_graph), channels_last=bool(args.channels_last))
     src_h, lab_h, tgt_h = TR.synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
     src_h, lab_h, tgt_h = src_h.pin_memory(), lab_h.pin_memory(), tgt_h.pin_memory()
     src, lab, tgt = src_h.to(dev), lab_h.to(dev), tgt_h.to(dev)

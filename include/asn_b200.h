@@ -167,12 +167,14 @@ ASN_API int asn_aspp_pack_weights(const float* const* w_oihw /* host array of n_
                           int n_active, int n_cls, int Cin, void* wp_bf16, void* wpt_bf16,
                           void* stream);
 ASN_API size_t asn_aspp_workspace_bytes(int N, int Cin, int H, int W, int n_cls, int n_active);
-ASN_API int asn_aspp_fwd(const float* x_nchw, const void* wp_bf16, const float* bias_sum, float* y_nchw,
+/* x_channels_last != 0: x (and dx) are (N,Cin,H,W) tensors stored channels_last (NHWC in memory), as a
+ * channels_last trunk hands them over; y / dy stay NCHW. */
+ASN_API int asn_aspp_fwd(const float* x_nchw, int x_channels_last, const void* wp_bf16, const float* bias_sum, float* y_nchw,
                  int N, int Cin, int H, int W, int n_cls, const int* dil_host, int n_active,
                  void* workspace, size_t workspace_bytes, void* stream);
 /* any of dx / dw / db may be NULL (skipped).  dw: host array of n_active device ptrs (OIHW fp32,
  * overwritten); db: device [n_cls] = sum over pixels of dy (identical for every active branch). */
-ASN_API int asn_aspp_bwd(const float* x_nchw, const void* wpt_bf16, const float* dy_nchw, float* dx_nchw,
+ASN_API int asn_aspp_bwd(const float* x_nchw, int x_channels_last, const void* wpt_bf16, const float* dy_nchw, float* dx_nchw,
                  float* const* dw_oihw, float* db, int N, int Cin, int H, int W, int n_cls,
                  const int* dil_host, int n_active, void* workspace, size_t workspace_bytes,
                  void* stream);

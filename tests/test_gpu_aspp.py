@@ -83,3 +83,31 @@ def test_aspp_full_size_vs_fp32_path():
     for i in range(4):
         assert rel_err(got[2][i], ref[2][i]) < 1e-2
         assert rel_err(got[3][i], ref[3][i]) < 1e-2
+
+
+def test_aspp_channels_last_input_matches_nchw():
+    """features handed over by a channels_last trunk (NHWC in memory) take the transposition-free path and
+    must give the same logits / gradients as the NCHW path; dx comes back in channels_last"""
+    from adaptsegnet_b200 import ops
+    rng = np.random.default_rng(21)
+    N, cin, h, w = 2, 128, 19, 27
+    x = feature_like(rng, (N, cin, h, w))
+    ws = [(rng.standard_normal((19, cin, 3, 3)) * 0.01).astype(np.float32) for _ in range(4)]
+    bs = [(rng.standard_normal(19) * 0.1).astype(np.float32) for _ in range(4)]
+    dy = rng.standard_normal((N, 19, h, w)).astype(np.float32)
+    ref = run_head("bf16", x, ws, bs, dy, 4)
+    xt = cuda(x).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    assert ops._is_channels_last(xt)
+    wts = [cuda(v).requires_grad_(True) for v in ws]
+    bts = [cuda(v).requires_grad_(True) for v in bs]
+    y = ops.aspp_head(xt, wts, bts, O.ASPP_DILATIONS, 4)
+    y.backward(cuda(dy))
+    torch.cuda.synchronize()
+    assert y.is_contiguous() and xt.grad.is_contiguous(memory_format=torch.channels_last)
+    assert rel_err(host(y), ref[0]) < 1e-5          # same bf16 operands, same GEMM
+    assert rel_err(host(xt.grad), ref[1]) < 1e-3    # dgrad runs as the transposed GEMM
+    for i in range(4):
+        assert rel_err(host(wts[i].grad), ref[2][i]) < 1e-5
+    yr = O.aspp_head_fwd(x, ws, bs)
+    dxr, _, _ = O.aspp_head_bwd(x, ws, dy)
+    assert rel_err(host(y), yr) < 1e-2 and rel_err(host(xt.grad), dxr) < 1e-2
