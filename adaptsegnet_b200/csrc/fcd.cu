@@ -433,6 +433,14 @@ static double layer_flops(const FcdPlan& p, int l) {
   return 2.0 * p.N * p.H[l] * p.W[l] * p.C[l] * 16.0 * cin;
 }
 
+// algorithmic HBM bytes of conv l: which = 0 -> input A_{l-1} + output-sized tensor of level l (bf16, as stored),
+// which = 1 -> A_{l-1} alone
+static double layer_bytes(const FcdPlan& p, int l, int which) {
+  const double in_b = l == 1 ? 2.0 * p.N * p.H[0] * p.W0p * 32 : 2.0 * p.N * p.H[l - 1] * p.W[l - 1] * p.C[l - 1];
+  const double out_b = 2.0 * p.N * p.H[l] * p.W[l] * p.C[l];
+  return which == 1 ? in_b : in_b + out_b;
+}
+
 // ---- tcgen05 launches ---------------------------------------------------------------------------
 // largest BLOCK_N dividing n that still yields enough tiles to occupy most SMs of the persistent grid
 static int block_n_for(int n, long long m_tiles = 1 << 30) {
@@ -527,7 +535,8 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
   P.mask_slope = 1.f;
   dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(Cout, bn), 1);
   static const char* names[5] = {"", "fcd_conv1_fwd", "fcd_conv2_fwd", "fcd_conv3_fwd", "fcd_conv4_fwd"};
-  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l));
+  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l),
+                layer_bytes(p, l, 0) + 2.0 * Cout * K);
 }
 
 // dIn (= dPre_{l-1} after the LeakyReLU mask, or dA0 for l == 1) from dPre_l
@@ -582,7 +591,9 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   P.mask_slope = FCD_SLOPE;
   dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(rows, bn), 4);
   static const char* names[5] = {"", "fcd_conv1_dgrad", "fcd_conv2_dgrad", "fcd_conv3_dgrad", "fcd_conv4_dgrad"};
-  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l));
+  // reads dPre_l and the mask source A_{l-1}, writes dIn (same size as A_{l-1})
+  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l),
+                layer_bytes(p, l, 0) + (l > 1 ? layer_bytes(p, l, 1) : 0.0) + 2.0 * 4 * rows * K);
 }
 
 static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* act_in, float* part,
@@ -640,7 +651,9 @@ static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   P.slope = 1.f;
   dim3 grid(cdiv(Cout, 128) * cdiv(nn, bn), P.taps, S);
   static const char* names[5] = {"", "fcd_conv1_wgrad", "fcd_conv2_wgrad", "fcd_conv3_wgrad", "fcd_conv4_wgrad"};
-  if ((rc = launch(MODE_WGRAD, bn, maps, P, grid, st, names[l], layer_flops(p, l)))) return rc;
+  if ((rc = launch(MODE_WGRAD, bn, maps, P, grid, st, names[l], layer_flops(p, l),
+                   layer_bytes(p, l, 0) + 4.0 * S * P.taps * Cout * nn)))
+    return rc;
   const int cin_real = l == 1 ? p.n_cls : p.C[l - 1];
   fcd_wgrad_reduce_kernel<<<wave_grid((int64_t)Cout * cin_real * 16, 256, 8), 256, 0, st>>>(part, dw, S, l, Cout,
                                                                                              cin_real, nn);

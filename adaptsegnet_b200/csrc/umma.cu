@@ -92,7 +92,7 @@ struct Stages {
 
 template <int MODE, int BLOCK_N>
 static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st, const char* name,
-                    double flops) {
+                    double flops, double bytes) {
   constexpr int STAGES = Stages<BLOCK_N>::value;
   using L = SmemLayout<BLOCK_N, STAGES>;
   auto kern = umma_kernel<MODE, BLOCK_N, STAGES>;
@@ -108,7 +108,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
   const long long tiles = (long long)grid.x * grid.y * grid.z;
   const long long slots = (long long)sm_count() * Stages<BLOCK_N>::ctas_per_sm;
   const int ctas = (int)(tiles < slots ? tiles : slots);
-  prof::Scope ps(name, flops, 0, st);
+  prof::Scope ps(name, flops, bytes, st);
   kern<<<ctas, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], Pp);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -124,9 +124,9 @@ bool block_n_supported(int mode, int block_n) {
 }
 
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
-           const char* prof_name, double prof_flops) {
+           const char* prof_name, double prof_flops, double prof_bytes) {
 #define ASN_CASE(MODE, BN) \
-  if (mode == MODE && block_n == BN) return launch_t<MODE, BN>(maps, P, grid, st, prof_name, prof_flops);
+  if (mode == MODE && block_n == BN) return launch_t<MODE, BN>(maps, P, grid, st, prof_name, prof_flops, prof_bytes);
   ASN_CASE(MODE_GEMM, 128)
   ASN_CASE(MODE_GEMM, 176)
   ASN_CASE(MODE_GEMM, 256)
@@ -171,7 +171,8 @@ int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda
   P.z_stride_out = split_stride;
   P.slope = 1.f;
   dim3 grid(cdiv(M, BLOCK_M), cdiv(N, block_n), split_k);
-  return launch(MODE_GEMM, block_n, maps, P, grid, st, prof_name, prof_flops >= 0 ? prof_flops : 2.0 * M * N * K);
+  return launch(MODE_GEMM, block_n, maps, P, grid, st, prof_name, prof_flops >= 0 ? prof_flops : 2.0 * M * N * K,
+                2.0 * M * K + 2.0 * N * K + 4.0 * M * N * split_k);
 }
 
 int effective_split(int K, int split_k) {

@@ -15,7 +15,7 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
 
 // maps = {a0, a1, a2, a3, b}.  grid as documented on umma_kernel.
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
-           const char* prof_name = "umma", double prof_flops = 0);
+           const char* prof_name = "umma", double prof_flops = 0, double prof_bytes = 0);
 
 // BLOCK_N choices compiled for each mode
 bool block_n_supported(int mode, int block_n);

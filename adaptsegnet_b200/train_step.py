@@ -62,7 +62,12 @@ class FlatGrads:
         self.flat = torch.zeros(total, dtype=torch.float32, device=uniq[0].device)
         off = 0
         for p in uniq:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            seg = self.flat[off:off + p.numel()]
+            if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+                n, c, h, w = p.shape   # same strides as the channels_last parameter (autograd's layout contract)
+                p.grad = seg.view(n, h, w, c).permute(0, 3, 1, 2)
+            else:
+                p.grad = seg.view_as(p)
             off += p.numel()
 
     def zero(self):
