@@ -110,97 +110,158 @@ __host__ __device__ inline int tap_a(int k) { return k == 0 ? -1 : (k == 3 ? 1 :
 __host__ __device__ inline int tap_r(int k) { return (k == 0 || k == 2) ? 1 : 0; }
 
 // ---- input pack: fp32 NCHW (probabilities or logits) -> bf16 [N][H][W0p][32] ------------------
+// One thread = PV consecutive pixels of a row (PV = 4 with 16-byte loads per channel plane when W % 4 == 0):
+// the C values per pixel stay in registers, the optional channel softmax (K4) is fused, and each pixel's
+// 32 bf16 (64 bytes) are written with 16-byte stores.  Pixel w lands at padded column w + 1; the zero columns
+// (0 and >= W + 1) are written by the thread that owns the neighbouring pixels.
+__device__ __forceinline__ void store_px32(__nv_bfloat16* dst, const float* v) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 hh = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    d[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+template <int PV>
 __global__ void __launch_bounds__(128)
 fcd_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a0, int N, int C, int H, int W,
                       int W0p, int softmax) {
-  const int64_t total = (int64_t)N * H * W0p;
+  const int wv = (W + PV - 1) / PV;
+  const int64_t total = (int64_t)N * H * wv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int wp = (int)(i % W0p);
-    const int h = (int)((i / W0p) % H);
-    const int n = (int)(i / ((int64_t)W0p * H));
-    const int w = wp - 1;
-    float v[32];
+    const int xv = (int)(i % wv);
+    const int64_t row = i / wv;               // n * H + h
+    const int h = (int)(row % H);
+    const int n = (int)(row / H);
+    const int w0 = xv * PV;
+    float v[PV][32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = 0.f;
-    if (w >= 0 && w < W) {
-      const float* src = x + ((int64_t)n * C * H + h) * W + w;
+    for (int k = 0; k < PV; ++k)
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < C) v[c] = __ldg(src + (int64_t)c * H * W);
-      if (softmax) {
+      for (int c = 0; c < 32; ++c) v[k][c] = 0.f;
+    const float* src = x + ((int64_t)n * C * H + h) * W + w0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c < C) {
+        if (PV == 4) {
+          const float4 t = ld_stream(reinterpret_cast<const float4*>(src + (int64_t)c * H * W));
+          v[0][c] = t.x; v[1][c] = t.y; v[2][c] = t.z; v[3][c] = t.w;
+        } else {
+          v[0][c] = __ldg(src + (int64_t)c * H * W);
+        }
+      }
+    }
+    if (softmax) {
+#pragma unroll
+      for (int k = 0; k < PV; ++k) {
         float m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (c < C) m = fmaxf(m, v[c]);
+          if (c < C) m = fmaxf(m, v[k][c]);
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (c < C) { v[c] = expf(v[c] - m); s += v[c]; }
+          if (c < C) { v[k][c] = expf(v[k][c] - m); s += v[k][c]; }
         const float inv = 1.f / s;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] *= inv;
+        for (int c = 0; c < 32; ++c) v[k][c] *= inv;
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(a0 + i * 32);
+    __nv_bfloat16* dst_row = a0 + row * (int64_t)W0p * 32;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t pk[4];
+    for (int k = 0; k < PV; ++k)
+      if (w0 + k < W) store_px32(dst_row + (int64_t)(w0 + k + 1) * 32, v[k]);
+    // zero padding columns of this row
+    float z[32];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 hh = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
-        pk[j] = *reinterpret_cast<uint32_t*>(&hh);
-      }
-      dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
+    for (int c = 0; c < 32; ++c) z[c] = 0.f;
+    if (xv == 0) store_px32(dst_row, z);
+    if (xv == wv - 1)
+      for (int wp = W + 1; wp < W0p; ++wp) store_px32(dst_row + (int64_t)wp * 32, z);
   }
 }
 
 // dA0 bf16 [N][H][W0p][32] -> dx fp32 NCHW; with logits given, the channel-softmax backward is fused:
-// dz = p * (g - sum_c p*g), p = softmax(x).
+// dz = p * (g - sum_c p*g), p = softmax(x).  PV pixels per thread (PV = 2: 8-byte accesses per channel plane;
+// 4 pixels would need 256 live floats and spill).
+template <int PV>
 __global__ void __launch_bounds__(128)
 fcd_unpack_dx_kernel(const __nv_bfloat16* __restrict__ da0, const float* __restrict__ logits,
                      float* __restrict__ dx, int N, int C, int H, int W, int W0p) {
-  const int64_t total = (int64_t)N * H * W;
+  const int wv = (W + PV - 1) / PV;
+  const int64_t total = (int64_t)N * H * wv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    const int h = (int)((i / W) % H);
-    const int n = (int)(i / ((int64_t)W * H));
-    const uint4* src = reinterpret_cast<const uint4*>(da0 + (((int64_t)n * H + h) * W0p + w + 1) * 32);
-    float g[32];
+    const int xv = (int)(i % wv);
+    const int64_t row = i / wv;
+    const int h = (int)(row % H);
+    const int n = (int)(row / H);
+    const int w0 = xv * PV;
+    float g[PV][32];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 u = __ldg(src + q);
-      uint32_t pk[4] = {u.x, u.y, u.z, u.w};
+    for (int k = 0; k < PV; ++k) {
+      const uint4* src = reinterpret_cast<const uint4*>(da0 + (row * (int64_t)W0p + min(w0 + k, W - 1) + 1) * 32);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 hh = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-        g[q * 8 + 2 * j] = __low2float(hh);
-        g[q * 8 + 2 * j + 1] = __high2float(hh);
+      for (int q = 0; q < 4; ++q) {
+        const uint4 u = __ldg(src + q);
+        const uint32_t pk[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+          g[k][q * 8 + 2 * j] = __low2float(hh);
+          g[k][q * 8 + 2 * j + 1] = __high2float(hh);
+        }
       }
     }
-    const int64_t base = ((int64_t)n * C * H + h) * W + w;
+    const int64_t base = ((int64_t)n * C * H + h) * W + w0;
     if (logits) {
-      float z[32];
-      float m = -INFINITY;
+      float z[PV][32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < C) { z[c] = __ldg(logits + base + (int64_t)c * H * W); m = fmaxf(m, z[c]); }
-      float s = 0.f;
+      for (int c = 0; c < 32; ++c) {
+        if (c < C) {
+          if (PV == 2) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(logits + base + (int64_t)c * H * W));
+            z[0][c] = t.x; z[1][c] = t.y;
+          } else {
+            z[0][c] = __ldg(logits + base + (int64_t)c * H * W);
+          }
+        }
+      }
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < C) { z[c] = expf(z[c] - m); s += z[c]; }
-      const float inv = 1.f / s;
-      float dot = 0.f;
+      for (int k = 0; k < PV; ++k) {
+        float m = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < C) { z[c] *= inv; dot += z[c] * g[c]; }
+        for (int c = 0; c < 32; ++c)
+          if (c < C) m = fmaxf(m, z[k][c]);
+        float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < C) g[c] = z[c] * (g[c] - dot);
+        for (int c = 0; c < 32; ++c)
+          if (c < C) { z[k][c] = expf(z[k][c] - m); s += z[k][c]; }
+        const float inv = 1.f / s;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < C) { z[k][c] *= inv; dot += z[k][c] * g[k][c]; }
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < C) g[k][c] = z[k][c] * (g[k][c] - dot);
+      }
     }
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < C) dx[base + (int64_t)c * H * W] = g[c];
+    for (int c = 0; c < 32; ++c) {
+      if (c < C) {
+        if (PV == 2) {
+          *reinterpret_cast<float2*>(dx + base + (int64_t)c * H * W) = make_float2(g[0][c], g[1][c]);
+        } else {
+          dx[base + (int64_t)c * H * W] = g[0][c];
+        }
+      }
+    }
   }
 }
 
@@ -753,8 +814,12 @@ extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpa
   for (int l = 0; l <= 4; ++l) A[l] = reinterpret_cast<__nv_bfloat16*>(ab + p.act_off[l]);
   {
     prof::Scope ps("fcd_pack_input", 0, (double)N * H * W * (4.0 * n_cls + 64.0), st);
-    fcd_pack_input_kernel<<<full_grid((int64_t)N * H * p.W0p, 128), 128, 0, st>>>(x_nchw, A[0], N, n_cls, H, W,
-                                                                                     p.W0p, x_is_logits);
+    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0)
+      fcd_pack_input_kernel<4><<<full_grid((int64_t)N * H * (W / 4), 128), 128, 0, st>>>(x_nchw, A[0], N, n_cls, H, W,
+                                                                                         p.W0p, x_is_logits);
+    else
+      fcd_pack_input_kernel<1><<<full_grid((int64_t)N * H * W, 128), 128, 0, st>>>(x_nchw, A[0], N, n_cls, H, W,
+                                                                                   p.W0p, x_is_logits);
     ASN_LAUNCH_CHECK();
   }
   for (int l = 1; l <= 4; ++l) {
@@ -822,8 +887,12 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
   }
   if (dx_nchw) {
     prof::Scope ps("fcd_unpack_dx", 0, (double)N * H * W * (64.0 + 4.0 * n_cls * (x_logits ? 2 : 1)), st);
-    fcd_unpack_dx_kernel<<<full_grid((int64_t)N * H * W, 128), 128, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls, H, W,
-                                                                                p.W0p);
+    if (W % 2 == 0 && ((reinterpret_cast<uintptr_t>(dx_nchw) | reinterpret_cast<uintptr_t>(x_logits)) & 7) == 0)
+      fcd_unpack_dx_kernel<2><<<full_grid((int64_t)N * H * (W / 2), 128), 128, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls,
+                                                                                        H, W, p.W0p);
+    else
+      fcd_unpack_dx_kernel<1><<<full_grid((int64_t)N * H * W, 128), 128, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls, H, W,
+                                                                                  p.W0p);
     ASN_LAUNCH_CHECK();
   }
   return ASN_OK;
