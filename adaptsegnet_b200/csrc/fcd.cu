@@ -814,7 +814,8 @@ extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpa
   for (int l = 0; l <= 4; ++l) A[l] = reinterpret_cast<__nv_bfloat16*>(ab + p.act_off[l]);
   {
     prof::Scope ps("fcd_pack_input", 0, (double)N * H * W * (4.0 * n_cls + 64.0), st);
-    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0)
+    // (4 pixels per thread measured slower on B200: 178 registers halve the occupancy)
+    if (false && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0)
       fcd_pack_input_kernel<4><<<full_grid((int64_t)N * H * (W / 4), 128), 128, 0, st>>>(x_nchw, A[0], N, n_cls, H, W,
                                                                                          p.W0p, x_is_logits);
     else
@@ -887,7 +888,8 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
   }
   if (dx_nchw) {
     prof::Scope ps("fcd_unpack_dx", 0, (double)N * H * W * (64.0 + 4.0 * n_cls * (x_logits ? 2 : 1)), st);
-    if (W % 2 == 0 && ((reinterpret_cast<uintptr_t>(dx_nchw) | reinterpret_cast<uintptr_t>(x_logits)) & 7) == 0)
+    // (2 pixels per thread measured slower on B200: 211 registers)
+    if (false && W % 2 == 0 && ((reinterpret_cast<uintptr_t>(dx_nchw) | reinterpret_cast<uintptr_t>(x_logits)) & 7) == 0)
       fcd_unpack_dx_kernel<2><<<full_grid((int64_t)N * H * (W / 2), 128), 128, 0, st>>>(dA0, x_logits, dx_nchw, N, n_cls,
                                                                                         H, W, p.W0p);
     else
