@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the iteration (up to the gradients) as a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
     ap.add_argument("--channels-last", type=int, default=1, help="run the (unchanged) trunk in channels_last")
+    ap.add_argument("--no-kernel-events", action="store_true", help="skip the per-kernel event pass (ncu runs)")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
@@ -263,6 +264,15 @@ def run_b200(args):
     # ---- per-kernel CUDA-event timing, live inside K more steps.  Events cannot be recorded inside a captured
     #      graph, so this pass runs the same iteration eagerly (same kernels, same inputs, same order). ----
     graph_mode = trainer.use_cuda_graph
+    if args.no_kernel_events:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": world * 1000.0 / (ms_total / args.steps), "unit": UNIT,
+                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                              "ms_per_step": ms_total / args.steps, "note": "profiling run: no kernel events"}),
+                  flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     trainer.use_cuda_graph = False
     step_resident(0)
     prof.enable(True)

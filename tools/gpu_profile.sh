@@ -1,12 +1,14 @@
 #!/bin/bash
-# ncu evidence for bench.py (run under gpurun, 1 GPU).  $1 = tag for output names.
+# ncu evidence (run under gpurun, 1 GPU).  $1 = tag for the output names.
+#  1. launch list of bench.py (every kernel of 3 eager iterations with its device time)
+#  2. --set full capture of the library's kernels in the short hot-path script
 TAG=${1:-r01}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-kernel-events --cuda-graph 0 --cudnn-benchmark 0"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "launch list exit $?"
-$CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:umma_kernel -s 40 -c 6 -o gpurun_out/prof_umma_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+python tools/hot_path_once.py > gpurun_out/plain2_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"umma_kernel|softmax_ce|fast_hist|upsample_fwd|pack_input" -s 20 -c 24 -o gpurun_out/prof_hot_$TAG python tools/hot_path_once.py > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "full capture exit $?"
-ls -la gpurun_out | tail -n 12
+ls -la gpurun_out | grep $TAG
