@@ -257,6 +257,7 @@ nchw_channel_sum_kernel(const float* __restrict__ src, float* __restrict__ out, 
 }
 
 int channel_sum_nchw(const float* src, float* out, int N, int O, int P, cudaStream_t st) {
+  prof::Scope ps("channel_sum", 0, 4.0 * N * O * P, st);
   nchw_channel_sum_kernel<<<O, 256, 0, st>>>(src, out, N, O, P);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -341,7 +342,8 @@ extern "C" int asn_aspp_pack_weights(const float* const* w_oihw, int n_active, i
     wp.w[b] = w_oihw[b];
   }
   const int NP = asn_aspp_np(n_cls, n_active);
-  aspp_pack_kernel<<<wave_grid((int64_t)NP * Cin, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  prof::Scope ps("aspp_pack_weights", 0, (36.0 * n_active / 4 + 4.0) * NP * Cin, static_cast<cudaStream_t>(stream));
+  aspp_pack_kernel<<<full_grid((int64_t)NP * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       wp, static_cast<__nv_bfloat16*>(wp_bf16), static_cast<__nv_bfloat16*>(wpt_bf16), n_active, n_cls, Cin, NP);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -477,8 +479,8 @@ extern "C" int asn_aspp_bwd(const float* x_nchw, int x_channels_last, const void
     ASN_LAUNCH_CHECK();
   }
   if (db) {
-    nchw_channel_sum_kernel<<<n_cls, 256, 0, st>>>(dy_nchw, db, N, n_cls, P);
-    ASN_LAUNCH_CHECK();
+    rc = channel_sum_nchw(dy_nchw, db, N, n_cls, P, st);
+    if (rc) return rc;
   }
   return ASN_OK;
 }

@@ -398,69 +398,62 @@ fcd_cls_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w
   }
 }
 
-// dwc[0][c][kh][kw] = sum_{n,oh,ow} dout * A4[n][2oh-1+kh][2ow-1+kw][c]
+// dwc[0][c][kh][kw] = sum_{n,oh,ow} dout * A4[n][2oh-1+kh][2ow-1+kw][c].
+// grid (16 taps, C/64, CLS_SLICES): thread = (channel, 1 of 4 pixel phases); coalesced 128-byte reads of A4
+// along the channels, shared-memory reduce over the phases, one fp32 atomic per (channel, tap, slice).
+constexpr int CLS_SLICES = 8;
 __global__ void __launch_bounds__(256)
 fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a4, float* __restrict__ dw,
                      int N, int H4, int W4, int C, int H5, int W5) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= 16 * C) return;
-  const int c = i % C, t = i / C;
-  const int kh = t / 4, kw = t % 4;
+  __shared__ float red[4][64];
+  const int t = blockIdx.x, kh = t / 4, kw = t % 4;
+  const int cl = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  const int n_out = N * H5 * W5;
   float acc = 0.f;
-  for (int n = 0; n < N; ++n)
-    for (int oh = 0; oh < H5; ++oh) {
-      const int ih = 2 * oh - 1 + kh;
-      if ((unsigned)ih >= (unsigned)H4) continue;
-      for (int ow = 0; ow < W5; ++ow) {
-        const int iw = 2 * ow - 1 + kw;
-        if ((unsigned)iw >= (unsigned)W4) continue;
-        acc = fmaf(__ldg(dout + ((int64_t)n * H5 + oh) * W5 + ow),
-                   __bfloat162float(a4[(((int64_t)n * H4 + ih) * W4 + iw) * C + c]), acc);
-      }
+  if (c < C) {
+    for (int o = blockIdx.z * 4 + ph; o < n_out; o += 4 * CLS_SLICES) {
+      const int ow = o % W5, oh = (o / W5) % H5, n = o / (W5 * H5);
+      const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
+      if ((unsigned)ih < (unsigned)H4 && (unsigned)iw < (unsigned)W4)
+        acc = fmaf(__ldg(dout + o), __bfloat162float(a4[(((int64_t)n * H4 + ih) * W4 + iw) * C + c]), acc);
     }
-  dw[(int64_t)c * 16 + t] = acc;
+  }
+  red[ph][cl] = acc;
+  __syncthreads();
+  if (ph == 0 && c < C) atomicAdd(dw + (int64_t)c * 16 + t, red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]);
 }
 
 // ---- reductions over pixels -------------------------------------------------------------------
-// partial[r][c] = sum over the r-th slice of rows of src[row][c] (bf16 [P][C]); then db[c] = sum_r
+// db[c] = sum over rows of src[row][c] (bf16 [P][C]).  Each CTA owns a slice of rows; thread = (channel pair,
+// row phase); phases are reduced in shared memory, then one fp32 atomic per (CTA, channel) into the zeroed db.
 __global__ void __launch_bounds__(256)
-fcd_colsum_partial_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int64_t P, int C,
-                          int rows_per_cta) {
+fcd_colsum_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ out, int64_t P, int C,
+                  int rows_per_cta) {
+  extern __shared__ float red[];  // [nsub][C]
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(P, r0 + rows_per_cta);
   const int pairs = C / 2;
   const int tpr = pairs < 256 ? pairs : 256;
   const int nsub = 256 / tpr;
   const int sub = threadIdx.x / tpr;
-  if (sub >= nsub) return;
-  for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int64_t r = r0 + sub; r < r1; r += nsub) {
-      __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * C + cp * 2);
-      a0 += __low2float(v);
-      a1 += __high2float(v);
+  if (sub < nsub) {
+    for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int64_t r = r0 + sub; r < r1; r += nsub) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * C + cp * 2);
+        a0 += __low2float(v);
+        a1 += __high2float(v);
+      }
+      red[sub * C + cp * 2] = a0;
+      red[sub * C + cp * 2 + 1] = a1;
     }
-    float* dst = partial + ((int64_t)blockIdx.x * nsub + sub) * C + cp * 2;
-    dst[0] = a0;
-    dst[1] = a1;
   }
-}
-__global__ void __launch_bounds__(256)
-fcd_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int R, int C) {
-  // 32 channels per CTA (lane = channel -> coalesced 128-byte reads), 8 warps split the R partial rows
-  __shared__ float red[8][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  float acc = 0.f;
-  if (c < C)
-    for (int r = warp; r < R; r += 8) acc += partial[(int64_t)r * C + c];
-  red[warp][lane] = acc;
   __syncthreads();
-  if (warp == 0 && c < C) {
+  for (int c = threadIdx.x; c < C; c += 256) {
     float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][lane];
-    out[c] = t;
+    for (int k = 0; k < nsub; ++k) t += red[k * C + c];
+    atomicAdd(out + c, t);
   }
 }
 
@@ -716,25 +709,25 @@ static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
                    layer_bytes(p, l, 0) + 4.0 * S * P.taps * Cout * nn)))
     return rc;
   const int cin_real = l == 1 ? p.n_cls : p.C[l - 1];
-  fcd_wgrad_reduce_kernel<<<wave_grid((int64_t)Cout * cin_real * 16, 256, 8), 256, 0, st>>>(part, dw, S, l, Cout,
+  prof::Scope ps_red("fcd_wgrad_reduce", 0, 4.0 * (S + 1.0) * P.taps * Cout * nn, st);
+  fcd_wgrad_reduce_kernel<<<full_grid((int64_t)Cout * cin_real * 16, 256), 256, 0, st>>>(part, dw, S, l, Cout,
                                                                                              cin_real, nn);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
 
 static int col_sum(const __nv_bfloat16* src, float* partial, float* out, int64_t P, int C, cudaStream_t st) {
-  const int tpr = C / 2 < 256 ? C / 2 : 256;   // threads per row
-  const int sub = 256 / tpr;                    // row subsets per CTA
+  (void)partial;
+  const int tpr = C / 2 < 256 ? C / 2 : 256;
+  const int sub = 256 / tpr;
   int64_t ctas = 2 * (int64_t)sm_count();
   if (ctas > (P + 63) / 64) ctas = (P + 63) / 64;
-  const int64_t cap = (int64_t)256 * 2048 / ((int64_t)sub * C);  // partial buffer: 512K floats
-  if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   const int rows_per_cta = (int)((P + ctas - 1) / ctas);
   ctas = (P + rows_per_cta - 1) / rows_per_cta;
-  fcd_colsum_partial_kernel<<<(unsigned)ctas, 256, 0, st>>>(src, partial, P, C, rows_per_cta);
-  ASN_LAUNCH_CHECK();
-  fcd_colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(partial, out, (int)ctas * sub, C);
+  prof::Scope ps("fcd_bias_grad", 0, 2.0 * P * C, st);
+  ASN_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
+  fcd_colsum_kernel<<<(unsigned)ctas, 256, (size_t)sub * C * sizeof(float), st>>>(src, out, P, C, rows_per_cta);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -787,7 +780,8 @@ extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, 
     const int cin_real = l == 1 ? n_cls : p.C[l - 1];
     const int rows = l == 1 ? 32 : p.C[l - 1];
     const int64_t total = (int64_t)p.C[l] * (l == 1 ? 512 : 16 * cin_real) + (int64_t)16 * rows * p.C[l] + p.C[l];
-    fcd_pack_conv_kernel<<<wave_grid(total, 256, 8), 256, 0, st>>>(
+    prof::Scope ps("fcd_pack_weights", 0, 4.0 * p.C[l] * cin_real * 16 + 2.0 * total, st);
+    fcd_pack_conv_kernel<<<full_grid(total, 256), 256, 0, st>>>(
         w, b, reinterpret_cast<__nv_bfloat16*>(base + p.wf_off[l]), reinterpret_cast<__nv_bfloat16*>(base + p.wd_off[l]),
         reinterpret_cast<float*>(base + p.bias_off[l]), l, p.C[l], cin_real, rows);
     ASN_LAUNCH_CHECK();
@@ -862,14 +856,19 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
   const float* wc = reinterpret_cast<const float*>(wb + p.wc_off);
 
   // classifier
+  prof::Scope ps_cls("fcd_classifier_dgrad", 0, 4.0 * N * p.H[4] * p.W[4] * p.C[4], st);
   fcd_cls_dgrad_kernel<<<full_grid((int64_t)N * p.H[4] * p.W[4] * (p.C[4] / 2), 256), 256, 0, st>>>(
       dout, wc, A[4], dPre[4], N, p.H[4], p.W[4], p.C[4], p.H[5], p.W[5]);
   ASN_LAUNCH_CHECK();
   if (dparams_host) {
     ASN_CHECK_ARG(dparams_host[8] && dparams_host[9], "asn_fcd_bwd: null classifier gradient");
-    fcd_cls_wgrad_kernel<<<cdiv(16 * p.C[4], 256), 256, 0, st>>>(dout, A[4], dparams_host[8], N, p.H[4], p.W[4], p.C[4],
-                                                                  p.H[5], p.W[5]);
-    ASN_LAUNCH_CHECK();
+    {
+      prof::Scope ps("fcd_classifier_wgrad", 2.0 * N * p.H[5] * p.W[5] * 16 * p.C[4], 0, st);
+      ASN_CUDA(cudaMemsetAsync(dparams_host[8], 0, (size_t)16 * p.C[4] * sizeof(float), st));
+      fcd_cls_wgrad_kernel<<<dim3(16, cdiv(p.C[4], 64), CLS_SLICES), 256, 0, st>>>(dout, A[4], dparams_host[8], N, p.H[4],
+                                                                                   p.W[4], p.C[4], p.H[5], p.W[5]);
+      ASN_LAUNCH_CHECK();
+    }
     if ((rc = channel_sum_nchw(dout, dparams_host[9], N, 1, p.H[5] * p.W[5], st))) return rc;
   }
   for (int l = 4; l >= 1; --l) {
