@@ -29,7 +29,7 @@ struct FcdPlan {
   // wpack
   size_t wf_off[5], wd_off[5], bias_off[5], wc_off, bc_off, wpack_total;  // index 1..4
   // workspace
-  size_t dpre_off[5], da0_off, part_off, dbpart_off, ws_total;
+  size_t dpre_off[5], da0_off, part_off[5], dbpart_off, ws_total;
   int split[5];          // wgrad split-K per layer
   size_t part_bytes;
 };
@@ -91,16 +91,18 @@ static int make_plan(FcdPlan& p, int N, int n_cls, int ndf, int H, int W) {
     const int nn = wgrad_n(p, l);
     const int bn = nn >= 256 ? 256 : nn;
     const int ctas = cdiv(p.C[l], 128) * cdiv(nn, bn) * wgrad_taps(l);
-    int S = (2 * sm_count() + ctas - 1) / ctas;
+    // one wave of the persistent grid (two CTAs per SM when BLOCK_N <= 128)
+    const int slots = sm_count() * (bn <= 128 ? 2 : 1);
+    int S = (slots + ctas - 1) / ctas;
     if (S > k_steps / 2) S = k_steps / 2;
     if (S < 1) S = 1;
     const int sps = cdiv(k_steps, S);
     p.split[l] = cdiv(k_steps, sps);
     const size_t bytes = (size_t)p.split[l] * wgrad_taps(l) * p.C[l] * nn * 4;
-    if (bytes > p.part_bytes) p.part_bytes = bytes;
+    p.part_off[l] = off; off += align256(bytes);   // every layer keeps its partials: one merged reduce at the end
+    p.part_bytes += bytes;
   }
-  p.part_off = off; off += align256(p.part_bytes);
-  p.dbpart_off = off; off += align256((size_t)256 * 2048 * 4);
+  p.dbpart_off = off; off += align256((size_t)4 * 256 * 2048 * 4);
   p.ws_total = off;
   return ASN_OK;
 }
@@ -424,51 +426,81 @@ fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __rest
   if (ph == 0 && c < C) atomicAdd(dw + (int64_t)c * 16 + t, red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]);
 }
 
-// ---- reductions over pixels -------------------------------------------------------------------
-// db[c] = sum over rows of src[row][c] (bf16 [P][C]).  Each CTA owns a slice of rows; thread = (channel pair,
-// row phase); phases are reduced in shared memory, then one fp32 atomic per (CTA, channel) into the zeroed db.
-__global__ void __launch_bounds__(256)
-fcd_colsum_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ out, int64_t P, int C,
-                  int rows_per_cta) {
-  extern __shared__ float red[];  // [nsub][C]
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t r1 = min(P, r0 + rows_per_cta);
+// ---- reductions at the end of the backward: one launch each for the four conv layers (blockIdx.y = layer) ----
+struct LayerReduce {
+  // bias gradient: db[c] = sum over rows of dpre[row][c]  (bf16 [P][C])
+  const __nv_bfloat16* dpre[4];
+  float* db[4];
+  float* db_partial[4];
+  long long P[4];
+  int C[4], rows_per_cta[4], ctas[4];
+  // weight gradient: dW[co][ci][kh][kw] = sum_z part[z][tap][co][col]
+  const float* part[4];
+  float* dw[4];
+  int S[4], Cout[4], Cin_real[4], Ncols[4];
+};
+
+// partial[cta * nsub + sub][c] = sum of this CTA's row slice (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) fcd_colsum_partial_kernel(LayerReduce R) {
+  const int l = blockIdx.y;
+  if ((int)blockIdx.x >= R.ctas[l]) return;
+  const __nv_bfloat16* src = R.dpre[l];
+  const int C = R.C[l];
+  const long long r0 = (long long)blockIdx.x * R.rows_per_cta[l];
+  const long long r1 = min(R.P[l], r0 + R.rows_per_cta[l]);
   const int pairs = C / 2;
   const int tpr = pairs < 256 ? pairs : 256;
   const int nsub = 256 / tpr;
   const int sub = threadIdx.x / tpr;
-  if (sub < nsub) {
-    for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {
-      float a0 = 0.f, a1 = 0.f;
-      for (int64_t r = r0 + sub; r < r1; r += nsub) {
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * C + cp * 2);
-        a0 += __low2float(v);
-        a1 += __high2float(v);
-      }
-      red[sub * C + cp * 2] = a0;
-      red[sub * C + cp * 2 + 1] = a1;
+  if (sub >= nsub) return;
+  for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {
+    float a0 = 0.f, a1 = 0.f;
+    for (long long r = r0 + sub; r < r1; r += nsub) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * C + cp * 2);
+      a0 += __low2float(v);
+      a1 += __high2float(v);
     }
+    float* dst = R.db_partial[l] + ((long long)blockIdx.x * nsub + sub) * C + cp * 2;
+    dst[0] = a0;
+    dst[1] = a1;
   }
+}
+// db[c] = sum_r partial[r][c]: 32 channels per CTA (lane = channel), 8 warps split the partial rows
+__global__ void __launch_bounds__(256) fcd_colsum_final_kernel(LayerReduce R) {
+  __shared__ float red[8][32];
+  const int l = blockIdx.y;
+  const int C = R.C[l];
+  if ((int)blockIdx.x * 32 >= C) return;
+  const int tpr = C / 2 < 256 ? C / 2 : 256;
+  const int rows = R.ctas[l] * (256 / tpr);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (c < C)
+    for (int r = warp; r < rows; r += 8) acc += R.db_partial[l][(long long)r * C + c];
+  red[warp][lane] = acc;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
+  if (warp == 0 && c < C) {
     float t = 0.f;
-    for (int k = 0; k < nsub; ++k) t += red[k * C + c];
-    atomicAdd(out + c, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    R.db[l][c] = t;
   }
 }
 
 // dW_l[co][ci][kh][kw] = sum_z part[z][tap][co][col]
-__global__ void __launch_bounds__(256)
-fcd_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int l, int Cout, int Cin_real,
-                        int Ncols) {
-  const int taps = l == 1 ? 8 : 16;
-  const int64_t total = (int64_t)Cout * Cin_real * 16;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+__global__ void __launch_bounds__(256) fcd_wgrad_reduce_kernel(LayerReduce R) {
+  const int l = blockIdx.y;           // 0..3 <-> conv1..conv4
+  const int Cout = R.Cout[l], Cin_real = R.Cin_real[l], Ncols = R.Ncols[l], S = R.S[l];
+  const int taps = l == 0 ? 8 : 16;
+  const long long total = (long long)Cout * Cin_real * 16;
+  const float* part = R.part[l];
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int kw = (int)(i % 4), kh = (int)((i / 4) % 4);
     const int ci = (int)((i / 16) % Cin_real);
-    const int co = (int)(i / ((int64_t)16 * Cin_real));
+    const int co = (int)(i / ((long long)16 * Cin_real));
     int tap, col;
-    if (l == 1) {
+    if (l == 0) {
       tap = kh * 2 + kw / 2;
       col = (kw % 2) * 32 + ci;
     } else {
@@ -476,8 +508,8 @@ fcd_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, 
       col = ci;
     }
     float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += __ldg(part + (((int64_t)s * taps + tap) * Cout + co) * Ncols + col);
-    dw[i] = acc;
+    for (int s = 0; s < S; ++s) acc += __ldg(part + (((long long)s * taps + tap) * Cout + co) * Ncols + col);
+    R.dw[l][i] = acc;
   }
 }
 
@@ -651,7 +683,7 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
 }
 
 static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* act_in, float* part,
-                      float* dw, cudaStream_t st) {
+                      int* S_out, cudaStream_t st) {
   using namespace umma;
   const int Hout = p.H[l], Wout = p.W[l], Cout = p.C[l];
   int th = 1, tw = 64;
@@ -708,27 +740,53 @@ static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   if ((rc = launch(MODE_WGRAD, bn, maps, P, grid, st, names[l], layer_flops(p, l),
                    layer_bytes(p, l, 0) + 4.0 * S * P.taps * Cout * nn)))
     return rc;
-  const int cin_real = l == 1 ? p.n_cls : p.C[l - 1];
-  prof::Scope ps_red("fcd_wgrad_reduce", 0, 4.0 * (S + 1.0) * P.taps * Cout * nn, st);
-  fcd_wgrad_reduce_kernel<<<full_grid((int64_t)Cout * cin_real * 16, 256), 256, 0, st>>>(part, dw, S, l, Cout,
-                                                                                             cin_real, nn);
-  ASN_LAUNCH_CHECK();
+  *S_out = S;
   return ASN_OK;
 }
 
-static int col_sum(const __nv_bfloat16* src, float* partial, float* out, int64_t P, int C, cudaStream_t st) {
-  (void)partial;
-  const int tpr = C / 2 < 256 ? C / 2 : 256;
-  const int sub = 256 / tpr;
-  int64_t ctas = 2 * (int64_t)sm_count();
-  if (ctas > (P + 63) / 64) ctas = (P + 63) / 64;
-  if (ctas < 1) ctas = 1;
-  const int rows_per_cta = (int)((P + ctas - 1) / ctas);
-  ctas = (P + rows_per_cta - 1) / rows_per_cta;
-  prof::Scope ps("fcd_bias_grad", 0, 2.0 * P * C, st);
-  ASN_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
-  fcd_colsum_kernel<<<(unsigned)ctas, 256, (size_t)sub * C * sizeof(float), st>>>(src, out, P, C, rows_per_cta);
-  ASN_LAUNCH_CHECK();
+// merged end-of-backward reductions: bias gradients (2 launches) and split-K weight gradients (1 launch)
+static int reduce_all(const FcdPlan& p, LayerReduce& R, cudaStream_t st) {
+  int max_ctas = 1, max_c = 1;
+  long long max_dw = 1;
+  double db_bytes = 0, dw_bytes = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int l = i + 1;
+    const int C = p.C[l];
+    const long long P = (long long)p.N * p.H[l] * p.W[l];
+    const int tpr = C / 2 < 256 ? C / 2 : 256;
+    const int sub = 256 / tpr;
+    long long ctas = 2LL * sm_count();
+    if (ctas > (P + 63) / 64) ctas = (P + 63) / 64;
+    const long long cap = (long long)256 * 2048 / ((long long)sub * C);
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    R.rows_per_cta[i] = (int)((P + ctas - 1) / ctas);
+    R.ctas[i] = (int)((P + R.rows_per_cta[i] - 1) / R.rows_per_cta[i]);
+    R.P[i] = P;
+    R.C[i] = C;
+    if (R.ctas[i] > max_ctas) max_ctas = R.ctas[i];
+    if (C > max_c) max_c = C;
+    const long long ndw = (long long)R.Cout[i] * R.Cin_real[i] * 16;
+    if (ndw > max_dw) max_dw = ndw;
+    db_bytes += 2.0 * P * C;
+    dw_bytes += 4.0 * (R.S[i] + 1.0) * (i == 0 ? 8 : 16) * R.Cout[i] * R.Ncols[i];
+  }
+  {
+    prof::Scope ps("fcd_bias_grad_partial", 0, db_bytes, st);
+    fcd_colsum_partial_kernel<<<dim3(max_ctas, 4), 256, 0, st>>>(R);
+    ASN_LAUNCH_CHECK();
+  }
+  {
+    prof::Scope ps("fcd_bias_grad_final", 0, 0, st);
+    fcd_colsum_final_kernel<<<dim3(cdiv(max_c, 32), 4), 256, 0, st>>>(R);
+    ASN_LAUNCH_CHECK();
+  }
+  {
+    prof::Scope ps("fcd_wgrad_reduce", 0, dw_bytes, st);
+    const long long blocks = (max_dw + 255) / 256;
+    fcd_wgrad_reduce_kernel<<<dim3((unsigned)(blocks < 4096 ? blocks : 4096), 4), 256, 0, st>>>(R);
+    ASN_LAUNCH_CHECK();
+  }
   return ASN_OK;
 }
 
@@ -851,8 +909,9 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
   __nv_bfloat16* dPre[5];
   for (int l = 1; l <= 4; ++l) dPre[l] = reinterpret_cast<__nv_bfloat16*>(ws + p.dpre_off[l]);
   __nv_bfloat16* dA0 = reinterpret_cast<__nv_bfloat16*>(ws + p.da0_off);
-  float* part = reinterpret_cast<float*>(ws + p.part_off);
   float* dbpart = reinterpret_cast<float*>(ws + p.dbpart_off);
+  LayerReduce R;
+  memset(&R, 0, sizeof(R));
   const float* wc = reinterpret_cast<const float*>(wb + p.wc_off);
 
   // classifier
@@ -876,8 +935,16 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
       float* dw = dparams_host[2 * (l - 1)];
       float* db = dparams_host[2 * (l - 1) + 1];
       ASN_CHECK_ARG(dw && db, "asn_fcd_bwd: null gradient pointer for layer %d", l);
-      if ((rc = conv_wgrad(p, l, dPre[l], A[l - 1], part, dw, st))) return rc;
-      if ((rc = col_sum(dPre[l], dbpart, db, (int64_t)N * p.H[l] * p.W[l], p.C[l], st))) return rc;
+      float* part = reinterpret_cast<float*>(ws + p.part_off[l]);
+      if ((rc = conv_wgrad(p, l, dPre[l], A[l - 1], part, &R.S[l - 1], st))) return rc;
+      R.part[l - 1] = part;
+      R.dw[l - 1] = dw;
+      R.Cout[l - 1] = p.C[l];
+      R.Cin_real[l - 1] = l == 1 ? n_cls : p.C[l - 1];
+      R.Ncols[l - 1] = wgrad_n(p, l);
+      R.dpre[l - 1] = dPre[l];
+      R.db[l - 1] = db;
+      R.db_partial[l - 1] = dbpart + (size_t)(l - 1) * 256 * 2048;
     }
     if (l > 1 || dx_nchw) {
       rc = conv_dgrad(p, l, dPre[l], reinterpret_cast<const __nv_bfloat16*>(wb + p.wd_off[l]), A[l - 1],
@@ -885,6 +952,7 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
       if (rc) return rc;
     }
   }
+  if (dparams_host && (rc = reduce_all(p, R, st))) return rc;
   if (dx_nchw) {
     prof::Scope ps("fcd_unpack_dx", 0, (double)N * H * W * (64.0 + 4.0 * n_cls * (x_logits ? 2 : 1)), st);
     // (2 pixels per thread measured slower on B200: 211 registers)
