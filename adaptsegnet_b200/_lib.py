@@ -19,6 +19,7 @@ SIGNATURES = {
     "asn_abi_version": (c_int, []),
     "asn_last_error": (C.c_char_p, []),
     "asn_sm_count": (c_int, [C.POINTER(c_int)]),
+    "asn_launch_count": (c_int64, []),
     "asn_prof_enable": (c_int, [c_int]),
     "asn_prof_report": (c_int64, [C.c_char_p, c_int64]),
     "asn_fast_hist": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

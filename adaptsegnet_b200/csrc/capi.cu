@@ -1,6 +1,7 @@
 // error / device plumbing of the C ABI.
 #include "common.cuh"
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -43,6 +44,8 @@ static std::vector<cudaEvent_t> g_pool;
 static std::mutex g_mu;
 constexpr size_t MAX_RECORDS = 200000;
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool enabled() { return g_on; }
 
 static cudaEvent_t get_event() {
@@ -81,6 +84,8 @@ static void clear() {
 
 }  // namespace prof
 }  // namespace asn
+
+extern "C" int64_t asn_launch_count(void) { return asn::prof::g_launches.load(); }
 
 extern "C" int asn_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(asn::prof::g_mu);

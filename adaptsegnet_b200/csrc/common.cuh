@@ -16,6 +16,7 @@ int sm_count();
 // Optional per-kernel timing with CUDA events on the launching stream (asn_prof_enable /
 // asn_prof_report): bench.py uses it to time the dominant kernel live inside the timed steps.
 namespace prof {
+void count_launch();
 bool enabled();
 void begin(const char* name, double flops, double bytes, cudaStream_t st);
 void end(cudaStream_t st);
@@ -23,6 +24,7 @@ struct Scope {
   cudaStream_t st;
   bool on;
   Scope(const char* name, double flops, double bytes, cudaStream_t s) : st(s), on(enabled()) {
+    count_launch();
     if (on) begin(name, flops, bytes, st);
   }
   ~Scope() {

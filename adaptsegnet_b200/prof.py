@@ -11,6 +11,11 @@ def enable(on: bool = True) -> None:
     _lib.check(_lib.load().asn_prof_enable(1 if on else 0), "asn_prof_enable")
 
 
+def launch_count() -> int:
+    """kernels launched by libasn_b200 so far (counted inside the library at every launch site)"""
+    return int(_lib.load().asn_launch_count())
+
+
 def report() -> dict:
     """{"kernel": {"launches", "ms", "flops", "bytes"}}; synchronises the recorded events."""
     lib = _lib.load()

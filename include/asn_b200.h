@@ -62,6 +62,8 @@ ASN_API int asn_sm_count(int* out_host);
  * this library).  asn_prof_enable(1) clears and starts recording, asn_prof_enable(0) stops;
  * asn_prof_report synchronises the recorded events and writes a JSON object
  * {"kernel": {"launches", "ms", "flops", "bytes"}} (algorithmic flops / bytes); returns the size needed. */
+/* number of kernels this library has launched in this process (every launch site counts itself) */
+ASN_API int64_t asn_launch_count(void);
 ASN_API int asn_prof_enable(int on);
 ASN_API int64_t asn_prof_report(char* buf_host, int64_t capacity);
 
