@@ -162,18 +162,23 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": f"{args.level} AdaptSegNet train step, DeeplabMulti(ResNet-101, 19 cls) + "
-                        f"{'2x' if args.level == 'multi-level' else '1x'} FCDiscriminator, {args.gan} GAN, "
-                        f"src 1x3x{SRC_HW[0]}x{SRC_HW[1]} + tgt 1x3x{TGT_HW[0]}x{TGT_HW[1]} per GPU, random init",
-            "per_gpu_batch": "1 source + 1 target image", "global_pairs_per_step": world,
-            "parallelism": f"dp{world} (NCCL all-reduce of 3 flat gradient buffers per step)",
-            "hot_path": "libasn_b200 sm_100a kernels (tcgen05 heads + discriminators, fused losses)",
-            "execution": ("forward/backward of the iteration replayed as one CUDA graph; all-reduce + optimizers eager"
-                          if getattr(args, "cuda_graph", 0) and args.impl == "b200" else "eager"),
-            "trunk": ("ResNet-101 as PyTorch modules on cuDNN (TF32"
-                      + (", channels_last" if getattr(args, "channels_last", 0) and args.impl == "b200" else "")
-                      + "), timed, not rewritten"),
-            "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed"}
+    cfg = {"workload": f"{args.level} AdaptSegNet train step, DeeplabMulti(ResNet-101, 19 cls) + "
+                       f"{'2x' if args.level == 'multi-level' else '1x'} FCDiscriminator, {args.gan} GAN, "
+                       f"src 1x3x{SRC_HW[0]}x{SRC_HW[1]} + tgt 1x3x{TGT_HW[0]}x{TGT_HW[1]} per GPU, random init",
+           "per_gpu_batch": "1 source + 1 target image", "global_pairs_per_step": world}
+    if args.impl == "reference":
+        cfg.update({"parallelism": "none (rank 0 only, host CPU)",
+                    "hot_path": "the reference's own torch CPU ops (restated loop, oracle/torch_ref.RefTrainer)",
+                    "execution": "eager, all host threads", "trunk": "ResNet-101 on torch CPU (oneDNN), fp32"})
+        return cfg
+    cfg.update({"parallelism": f"dp{world} (NCCL all-reduce of 3 flat gradient buffers per step)",
+                "hot_path": "libasn_b200 sm_100a kernels (tcgen05 heads + discriminators, fused losses)",
+                "execution": ("forward/backward of the iteration replayed as one CUDA graph; all-reduce + optimizers eager"
+                              if args.cuda_graph else "eager"),
+                "trunk": ("ResNet-101 as PyTorch modules on cuDNN (TF32" + (", channels_last" if args.channels_last else "")
+                          + "), timed, not rewritten"),
+                "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed"})
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------------
