@@ -28,7 +28,14 @@ class FCDiscriminator(nn.Module):
             out += [conv.weight, conv.bias]
         return out
 
-    def forward(self, x, from_logits=False):
+    def forward(self, x, from_logits=False, return_saved=False):
         """x: (N, num_classes, H, W) fp32 -> (N, 1, H/32, W/32) logits.  ``from_logits=True`` fuses the
-        channel softmax the training script applies before calling D (train...:617-618)."""
-        return ops.fcd_forward(x, self._params(), self._pack, x_is_logits=from_logits)
+        channel softmax the training script applies before calling D (train...:617-618).
+        ``return_saved=True`` also returns a handle for :meth:`replay`."""
+        return ops.fcd_forward(x, self._params(), self._pack, x_is_logits=from_logits, return_saved=return_saved)
+
+    def replay(self, saved):
+        """D(x) for the same x and the same (unchanged) weights as the forward that produced ``saved``:
+        re-attaches that output to the parameters so a second loss can back-propagate into them without a
+        second forward (train...:665-666 repeats :617-618 bit for bit)."""
+        return ops.fcd_replay(saved, self._params(), self._pack)

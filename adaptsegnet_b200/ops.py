@@ -520,6 +520,49 @@ class _FcdTC(torch.autograd.Function):
         return (dx, None, None, *(dps if need_p else [None] * len(pshapes)))
 
 
+class FcdSaved:
+    """What a tensor-core discriminator forward left behind (bf16 activations, packed weights, output):
+    enough to run another backward through the SAME forward without recomputing it (fcd_replay)."""
+
+    def __init__(self, x_logits, wpack, acts, cfg, out, key):
+        self.x_logits, self.wpack, self.acts, self.cfg, self.out, self.key = x_logits, wpack, acts, cfg, out, key
+
+
+class _FcdReplay(torch.autograd.Function):
+    """Output of an earlier forward, re-attached to the parameters: backward = asn_fcd_bwd (parameter gradients
+    only) on the saved activations.  The reference runs D(softmax(pred_target)) twice per iteration with identical
+    weights and input (train...:617-618 and :665-666); the second pass is this replay."""
+
+    @staticmethod
+    def forward(ctx, saved, *params):
+        ctx.saved = saved
+        ctx.pshapes = tuple(p.shape for p in params)
+        return saved.out.detach().clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        sv = ctx.saved
+        N, n_cls, ndf, H, W, x_is_logits, _ = sv.cfg
+        dout = _req(dout, torch.float32, "dout")
+        lib = _lib.load()
+        nbytes = lib.asn_fcd_workspace_bytes(N, n_cls, ndf, H, W)
+        ws = _ws(nbytes, dout.device)
+        dps = [torch.empty(s, dtype=torch.float32, device=dout.device) for s in ctx.pshapes]
+        check(lib.asn_fcd_bwd(dout.data_ptr(), None, sv.wpack.data_ptr(), sv.acts.data_ptr(), None,
+                              _lib.ptr_array([t.data_ptr() for t in dps]), N, n_cls, ndf, H, W, ws.data_ptr(), nbytes,
+                              _stream()), "asn_fcd_bwd")
+        _count(12)
+        return (None, *dps)
+
+
+def fcd_replay(saved: FcdSaved, params, pack: "FcdWeightPack"):
+    """D(x) for the x and weights of an earlier fcd_forward(..., return_saved=True), without recomputing it."""
+    params = tuple(params)
+    if pack.key != saved.key or pack.key != tuple((p.data_ptr(), p._version) for p in params):
+        raise _lib.AsnError("fcd_replay: the discriminator's weights changed since the saved forward")
+    return _FcdReplay.apply(saved, *params)
+
+
 class _FcdF32(torch.autograd.Function):
     """fp32 CUDA-core path (ASN_PRECISION=fp32)."""
 
@@ -576,13 +619,22 @@ def fcd_saved_activations(out: torch.Tensor):
     return res
 
 
-def fcd_forward(x, params, pack: FcdWeightPack | None = None, x_is_logits: bool = False):
+def fcd_forward(x, params, pack: FcdWeightPack | None = None, x_is_logits: bool = False, return_saved: bool = False):
     """FCDiscriminator.forward (model/discriminator.py:21-34).  With x_is_logits the channel softmax
-    F.softmax(x) of train_gta2cityscapes_multi.py:617-618 is fused into the input pack (bf16 path)."""
+    F.softmax(x) of train_gta2cityscapes_multi.py:617-618 is fused into the input pack (bf16 path).
+    return_saved: also return an FcdSaved handle for fcd_replay (tensor-core path; None in fp32 mode)."""
     params = tuple(params)
     if precision_mode() == "fp32":
         if x_is_logits:
             x = softmax_channels(x)
-        return _FcdF32.apply(x, *params)
+        out = _FcdF32.apply(x, *params)
+        return (out, None) if return_saved else out
     pack = pack if pack is not None else FcdWeightPack()
-    return _FcdTC.apply(x, pack, bool(x_is_logits), *params)
+    out = _FcdTC.apply(x, pack, bool(x_is_logits), *params)
+    if not return_saved:
+        return out
+    fn = out.grad_fn
+    if fn is None:  # nothing requires grad: no autograd node holds the activations
+        return out, None
+    xs, wpack, acts = fn.saved_tensors
+    return out, FcdSaved(xs if fn.cfg[5] else None, wpack, acts, fn.cfg, out, pack.key)

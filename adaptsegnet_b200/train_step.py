@@ -40,6 +40,7 @@ class TrainConfig:
     gan: str = "Vanilla"
     level: str = "multi-level"  # or "single-level"
     fuse_softmax: bool = True   # D(softmax(pred)) with the softmax fused into D's input pack
+    reuse_target_forward: bool = True  # D-step on the target reuses the G-step's D(softmax(pred_target)) activations
 
 
 def lr_poly(base_lr, it, max_iter, power):
@@ -170,10 +171,19 @@ class AdaptSegTrainer:
         out["loss_seg2"] = loss_seg2.detach() / it
 
         pred_target1, pred_target2 = self.model(tgt_images)
-        loss_adv2 = self.bce_loss(self._d_out(self.model_D2, pred_target2), SOURCE_LABEL)
+        reuse = cfg.reuse_target_forward and cfg.fuse_softmax and ops.precision_mode() == "bf16"
+        saved = {}
+
+        def d_target(D, pred, key):
+            if reuse:
+                out, saved[key] = D(pred, from_logits=True, return_saved=True)
+                return out
+            return self._d_out(D, pred)
+
+        loss_adv2 = self.bce_loss(d_target(self.model_D2, pred_target2, "D2"), SOURCE_LABEL)
         loss = cfg.lambda_adv_target2 * loss_adv2
         if self.multi:
-            loss_adv1 = self.bce_loss(self._d_out(self.model_D1, pred_target1), SOURCE_LABEL)
+            loss_adv1 = self.bce_loss(d_target(self.model_D1, pred_target1, "D1"), SOURCE_LABEL)
             loss = cfg.lambda_adv_target1 * loss_adv1 + loss
             out["loss_adv_target1"] = loss_adv1.detach() / it
         (loss / it).backward()
@@ -182,13 +192,16 @@ class AdaptSegTrainer:
         # ---------------- train D (train...:635-679) ----------------
         self._set_requires_grad(self.model_D1, True)
         self._set_requires_grad(self.model_D2, True)
-        levels = [(self.model_D2, pred2, pred_target2, "loss_D2")]
+        levels = [(self.model_D2, pred2, pred_target2, "loss_D2", "D2")]
         if self.multi:
-            levels.insert(0, (self.model_D1, pred1, pred_target1, "loss_D1"))
-        for D, p_src, p_tgt, name in levels:
+            levels.insert(0, (self.model_D1, pred1, pred_target1, "loss_D1", "D1"))
+        for D, p_src, p_tgt, name, key in levels:
             l_src = self.bce_loss(self._d_out(D, p_src.detach()), SOURCE_LABEL) / it / 2
             l_src.backward()
-            l_tgt = self.bce_loss(self._d_out(D, p_tgt.detach()), TARGET_LABEL) / it / 2
+            # train...:665-666 recomputes D(softmax(pred_target)) with unchanged weights and input; the replay
+            # re-attaches the G-step's output (and activations) to D's parameters instead
+            d_tgt = D.replay(saved[key]) if saved.get(key) is not None else self._d_out(D, p_tgt.detach())
+            l_tgt = self.bce_loss(d_tgt, TARGET_LABEL) / it / 2
             l_tgt.backward()
             out[name] = l_src.detach() + l_tgt.detach()
         return out
