@@ -253,6 +253,15 @@ def run_b200(args):
         torch.cuda.current_stream().synchronize()  # the caller reads the losses every iteration
         it[0] += 1
 
+    graph_note = None
+    if trainer.use_cuda_graph:
+        try:  # capture happens inside the first step; never let a capture problem take the benchmark down
+            step_resident(0)
+        except Exception as exc:  # noqa: BLE001
+            graph_note = f"CUDA-graph capture failed ({type(exc).__name__}: {str(exc)[:120]}); ran eager"
+            torch.cuda.synchronize()
+            trainer.use_cuda_graph = False
+            trainer._graph = None
     for _ in range(args.warmup):
         step_resident(0)
     # ---- device-resident timing with clock sampling ----
@@ -330,7 +339,8 @@ def run_b200(args):
                         "h2d_bytes_per_step": int(src_h.numel() * 4 + lab_h.numel() * 8 + tgt_h.numel() * 4),
                         "d2h_bytes_per_step": 4 * n_losses},
                 "gpu_launches": int(launches), "roofline": roof,
-                "cuda_graph": bool(graph_mode), "eager_ms_per_step_with_kernel_events": ms_eager / args.steps,
+                "cuda_graph": bool(graph_mode), "cuda_graph_note": graph_note,
+                "eager_ms_per_step_with_kernel_events": ms_eager / args.steps,
                 "hot_path_ms_per_step": hot_ms, "hot_path_kernels": breakdown}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan)
