@@ -601,7 +601,9 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
   }
   const int K = P.taps * P.c_chunks * 64;
   const int bn = block_n_for(Cout, (long long)p.N * cdiv(OH, th) * cdiv(OW, tw));
-  if ((rc = encode_2d(&maps[4], wf, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)bn))) return rc;
+  if ((rc = encode_2d(&maps[4], wf, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2,
+                      (uint32_t)(bn / cluster_size(MODE_CONV, bn)))))
+    return rc;
   P.M = 0;
   P.N = Cout;
   P.k_steps = P.taps * P.c_chunks;
@@ -640,7 +642,9 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   maps[1] = maps[2] = maps[3] = maps[0];
   const int K = 4 * Cout;
   const int bn = block_n_for(rows, 4LL * p.N * cdiv(eh, th) * cdiv(ew, tw));
-  if ((rc = encode_2d(&maps[4], wd, (uint64_t)K, (uint64_t)4 * rows, (uint64_t)K * 2, (uint32_t)bn))) return rc;
+  if ((rc = encode_2d(&maps[4], wd, (uint64_t)K, (uint64_t)4 * rows, (uint64_t)K * 2,
+                      (uint32_t)(bn / cluster_size(MODE_CONV, bn)))))
+    return rc;
   Params P;
   memset(&P, 0, sizeof(P));
   P.N = rows;

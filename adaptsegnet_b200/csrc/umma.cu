@@ -3,6 +3,8 @@
 // GEMM entry point asn_gemm_bf16_tn.
 #include "umma_host.cuh"
 
+#include <stdlib.h>
+
 namespace asn {
 namespace umma {
 
@@ -90,12 +92,19 @@ struct Stages {
   static constexpr int value = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
 
-template <int MODE, int BLOCK_N>
+// cluster size the launcher uses for (mode, block_n): 2 = pairs of x-neighbouring tiles share the B tile through
+// TMA multicast (each CTA fetches half of it) -- callers must encode the B tensor map with box rows block_n / 2.
+int cluster_size(int mode, int block_n) {
+  if (getenv("ASN_NO_MULTICAST")) return 1;
+  return (mode == MODE_GEMM || mode == MODE_CONV) && block_n >= 128 ? 2 : 1;
+}
+
+template <int MODE, int BLOCK_N, int CL>
 static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st, const char* name,
                     double flops, double bytes) {
   constexpr int STAGES = Stages<BLOCK_N>::value;
   using L = SmemLayout<BLOCK_N, STAGES>;
-  auto kern = umma_kernel<MODE, BLOCK_N, STAGES>;
+  auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL>;
   static bool configured = false;
   if (!configured) {
     ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -105,11 +114,27 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
   Pp.grid_x = (int)grid.x;
   Pp.grid_y = (int)grid.y;
   Pp.grid_z = (int)grid.z;
-  const long long tiles = (long long)grid.x * grid.y * grid.z;
-  const long long slots = (long long)sm_count() * Stages<BLOCK_N>::ctas_per_sm;
-  const int ctas = (int)(tiles < slots ? tiles : slots);
+  const long long tiles = (long long)((grid.x + CL - 1) / CL) * grid.y * grid.z;  // (pairs of) tiles
+  const long long slots = (long long)sm_count() * Stages<BLOCK_N>::ctas_per_sm / CL;
+  const int ctas = (int)(tiles < slots ? tiles : slots) * CL;
   prof::Scope ps(name, flops, bytes, st);
-  kern<<<ctas, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], Pp);
+  if (CL == 1) {
+    kern<<<ctas, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], Pp);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ASN_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], Pp));
+  }
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -125,18 +150,25 @@ bool block_n_supported(int mode, int block_n) {
 
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
            const char* prof_name, double prof_flops, double prof_bytes) {
-#define ASN_CASE(MODE, BN) \
-  if (mode == MODE && block_n == BN) return launch_t<MODE, BN>(maps, P, grid, st, prof_name, prof_flops, prof_bytes);
-  ASN_CASE(MODE_GEMM, 128)
-  ASN_CASE(MODE_GEMM, 176)
-  ASN_CASE(MODE_GEMM, 256)
-  ASN_CASE(MODE_CONV, 32)
-  ASN_CASE(MODE_CONV, 64)
-  ASN_CASE(MODE_CONV, 128)
-  ASN_CASE(MODE_CONV, 256)
-  ASN_CASE(MODE_WGRAD, 64)
-  ASN_CASE(MODE_WGRAD, 128)
-  ASN_CASE(MODE_WGRAD, 256)
+  const int cl = cluster_size(mode, block_n);
+#define ASN_CASE(MODE, BN, CLS) \
+  if (mode == MODE && block_n == BN && cl == CLS)  \
+    return launch_t<MODE, BN, CLS>(maps, P, grid, st, prof_name, prof_flops, prof_bytes);
+  ASN_CASE(MODE_GEMM, 128, 1)
+  ASN_CASE(MODE_GEMM, 176, 1)
+  ASN_CASE(MODE_GEMM, 256, 1)
+  ASN_CASE(MODE_GEMM, 128, 2)
+  ASN_CASE(MODE_GEMM, 176, 2)
+  ASN_CASE(MODE_GEMM, 256, 2)
+  ASN_CASE(MODE_CONV, 32, 1)
+  ASN_CASE(MODE_CONV, 64, 1)
+  ASN_CASE(MODE_CONV, 128, 1)
+  ASN_CASE(MODE_CONV, 256, 1)
+  ASN_CASE(MODE_CONV, 128, 2)
+  ASN_CASE(MODE_CONV, 256, 2)
+  ASN_CASE(MODE_WGRAD, 64, 1)
+  ASN_CASE(MODE_WGRAD, 128, 1)
+  ASN_CASE(MODE_WGRAD, 256, 1)
 #undef ASN_CASE
   set_error("umma::launch: no kernel for mode %d block_n %d", mode, block_n);
   return ASN_EUNSUPPORTED;
@@ -153,7 +185,8 @@ int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda
   CUtensorMap maps[5];
   int rc = encode_2d(&maps[0], A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BLOCK_M);
   if (rc) return rc;
-  rc = encode_2d(&maps[4], B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)block_n);
+  rc = encode_2d(&maps[4], B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2,
+                 (uint32_t)(block_n / cluster_size(MODE_GEMM, block_n)));
   if (rc) return rc;
   maps[1] = maps[2] = maps[3] = maps[0];
   Params P;

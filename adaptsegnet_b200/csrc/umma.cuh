@@ -80,6 +80,26 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t dst, 
       : "memory");
 }
 
+// same 2-D box, delivered to the same shared-memory offset of every CTA in `mask` (and completing on the
+// mbarrier at the same offset in each of them)
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_holder, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_holder), "r"(ncols)
                : "memory");
@@ -108,6 +128,13 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
 // all previously issued tcgen05 ops of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// same, arriving on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 // 32 lanes x 16 consecutive fp32 columns: thread t receives lane (base_lane + t), columns c..c+15
@@ -212,14 +239,20 @@ struct SmemLayout {
 
 struct TileCoord {
   int z, n0, m0, img, oh0, ow0, wg_tap, ks_begin, nsteps;
+  bool valid;
 };
 
-template <int MODE, int BLOCK_N>
-__device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
+// CL = 1: tile -> (bx, by, bz).  CL = 2 (cluster of two CTAs sharing B by multicast): `tile` indexes PAIRS of
+// x-neighbours, this CTA takes bx = 2 * pair + rank; a pair hanging over the end of an odd grid_x still runs its
+// main loop (the multicast must stay in lock-step) on out-of-range coordinates -- TMA zero-fills, `valid` masks.
+template <int MODE, int BLOCK_N, int CL>
+__device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int rank) {
   TileCoord t;
-  const int bx = tile % P.grid_x;
-  const int by = (tile / P.grid_x) % P.grid_y;
-  t.z = tile / (P.grid_x * P.grid_y);
+  const int gx = CL == 1 ? P.grid_x : (P.grid_x + 1) / 2;
+  const int bx = CL == 1 ? tile % gx : 2 * (tile % gx) + rank;
+  const int by = (tile / gx) % P.grid_y;
+  t.z = tile / (gx * P.grid_y);
+  t.valid = bx < P.grid_x;
   t.m0 = t.img = t.oh0 = t.ow0 = t.wg_tap = 0;
   t.ks_begin = 0;
   int ks_end = P.k_steps;
@@ -246,7 +279,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
   return t;
 }
 
-template <int MODE, int BLOCK_N, int STAGES>
+template <int MODE, int BLOCK_N, int STAGES, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, (BLOCK_N <= 128 ? 2 : 1))
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -266,7 +299,11 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = P.grid_x * P.grid_y * P.grid_z;
+  const int rank = CL == 1 ? 0 : (int)cluster_ctarank();
+  const int first_tile = CL == 1 ? (int)blockIdx.x : (int)blockIdx.x / CL;   // cluster id
+  const int tile_stride = CL == 1 ? (int)gridDim.x : (int)gridDim.x / CL;
+  const int total_tiles = (CL == 1 ? P.grid_x : (P.grid_x + 1) / 2) * P.grid_y * P.grid_z;
+  constexpr uint16_t CL_MASK = (1u << CL) - 1;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -279,7 +316,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);  // a stage is free when every CTA that receives the multicast has consumed it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
@@ -292,7 +329,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 1) __syncthreads(); else cluster_sync_all();  // peers' barriers must exist before the first multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder_ptr;
 
@@ -301,8 +338,8 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     if (lane == 0) {
       const CUtensorMap* amaps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
       uint32_t it = 0;  // k-steps issued so far: the ring keeps streaming across tiles
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile<MODE, BLOCK_N>(P, tile);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        const TileCoord t = decode_tile<MODE, BLOCK_N, CL>(P, tile, rank);
         for (int i = 0; i < t.nsteps; ++i, ++it) {
           const int ks = t.ks_begin + i;
           const int s = it % STAGES;
@@ -313,14 +350,22 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           if (MODE == MODE_GEMM) {
             mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
             tma_load_2d(&map_a0, sa, full_bar(s), ks * BLOCK_K, t.m0);
-            tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.n0);
+            if (CL == 1)
+              tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.n0);
+            else  // this CTA fetches its half of the B tile for the whole cluster
+              tma_load_2d_mcast(&map_b, sb + rank * (L::B_BYTES / CL), full_bar(s), ks * BLOCK_K,
+                                t.n0 + rank * (BLOCK_N / CL), CL_MASK);
           } else if (MODE == MODE_CONV) {
             const int tap = ks / P.c_chunks, cc = ks - tap * P.c_chunks;
             const int e = t.z * P.taps + tap;
             mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
             tma_load_4d(amaps[P.tap_map[e]], sa, full_bar(s), cc * BLOCK_K, t.ow0 + P.tap_dw[e],
                         t.oh0 + P.tap_dh[e], t.img);
-            tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.z * P.b_rows_per_z + t.n0);
+            if (CL == 1)
+              tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.z * P.b_rows_per_z + t.n0);
+            else
+              tma_load_2d_mcast(&map_b, sb + rank * (L::B_BYTES / CL), full_bar(s), ks * BLOCK_K,
+                                t.z * P.b_rows_per_z + t.n0 + rank * (BLOCK_N / CL), CL_MASK);
           } else {
             // k-step = one box of 64 pixels: A = dY channels [m0, m0+128), B = X@tap channels [n0, n0+BLOCK_N)
             const int bx = ks % P.tiles_w, by = (ks / P.tiles_w) % P.tiles_h, im = ks / (P.tiles_w * P.tiles_h);
@@ -344,8 +389,8 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       constexpr uint32_t idesc = MODE == MODE_WGRAD ? make_idesc(BLOCK_M, BLOCK_N, 1, 1)
                                                     : make_idesc(BLOCK_M, BLOCK_N, 0, 0);
       uint32_t it = 0, tile_iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
-        const TileCoord t = decode_tile<MODE, BLOCK_N>(P, tile);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
+        const TileCoord t = decode_tile<MODE, BLOCK_N, CL>(P, tile, rank);
         const uint32_t acc = tile_iter & 1;
         const uint32_t acc_ph = (tile_iter >> 1) & 1;
         mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
@@ -373,7 +418,8 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             }
             mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+          // frees the stage (here and, under multicast, in the peer) once these MMAs have read it
+          if (CL == 1) mma_commit(empty_bar(s)); else mma_commit_mcast(empty_bar(s), CL_MASK);
         }
         mma_commit(tmem_full_bar(acc));  // accumulator of this tile complete
       }
@@ -383,8 +429,8 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;        // accumulator row owned by this thread
     uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
-      const TileCoord t = decode_tile<MODE, BLOCK_N>(P, tile);
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
+      const TileCoord t = decode_tile<MODE, BLOCK_N, CL>(P, tile, rank);
       const uint32_t acc = tile_iter & 1;
       const uint32_t acc_ph = (tile_iter >> 1) & 1;
       mbar_wait(tmem_full_bar(acc), acc_ph);
@@ -393,12 +439,12 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       bool row_ok;
       long long row_off;
       if (MODE == MODE_GEMM) {
-        row_ok = (t.m0 + r) < P.M;
+        row_ok = t.valid && (t.m0 + r) < P.M;
         row_off = (long long)t.z * P.z_stride_out + (long long)(t.m0 + r) * P.ld_out;
       } else if (MODE == MODE_CONV) {
         const int dy = r / P.tw, dx = r - dy * P.tw;
         const int oh = t.oh0 + dy, ow = t.ow0 + dx;
-        row_ok = oh < P.oh_ext[t.z] && ow < P.ow_ext[t.z];
+        row_ok = t.valid && oh < P.oh_ext[t.z] && ow < P.ow_ext[t.z];
         const int fh = oh * P.sy + P.oy[t.z], fw = ow * P.sx + P.ox[t.z];
         row_off = (((long long)t.img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
       } else {
@@ -478,9 +524,9 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
   }
 
-  // ---- teardown ----
+  // ---- teardown (a CTA may not exit while its peer can still multicast into it or signal its barriers) ----
   tc_fence_before();
-  __syncthreads();
+  if (CL == 1) __syncthreads(); else cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);

@@ -19,6 +19,8 @@ int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, di
 
 // BLOCK_N choices compiled for each mode
 bool block_n_supported(int mode, int block_n);
+// 1 or 2: with 2, encode the B tensor map with box rows block_n / 2 (each CTA of a pair multicasts its half)
+int cluster_size(int mode, int block_n);
 
 }  // namespace umma
 }  // namespace asn
