@@ -94,8 +94,12 @@ struct Stages {
 
 // cluster size the launcher uses for (mode, block_n): 2 = pairs of x-neighbouring tiles share the B tile through
 // TMA multicast (each CTA fetches half of it) -- callers must encode the B tensor map with box rows block_n / 2.
+// OFF by default: measured on B200 (profiles/README.md) it changes nothing -- the kernels are bound by the bytes
+// delivered INTO the SMs' shared memory (~6.3 KB/clk chip-wide), and a multicast byte still lands in both SMs.
+// ASN_MULTICAST=1 turns it on (parity-tested: tests pass in both settings).
 int cluster_size(int mode, int block_n) {
-  if (getenv("ASN_NO_MULTICAST")) return 1;
+  static const bool on = getenv("ASN_MULTICAST") != nullptr && getenv("ASN_MULTICAST")[0] == '1';
+  if (!on) return 1;
   return (mode == MODE_GEMM || mode == MODE_CONV) && block_n >= 128 ? 2 : 1;
 }
 
