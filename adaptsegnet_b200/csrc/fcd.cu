@@ -569,6 +569,9 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
   const int OH = p.H[l], OW = p.W[l], Cout = p.C[l];
   int th = 1, tw = 128;
   pick_tile(OH, OW, 128, &th, &tw);
+  const int bn_guess = block_n_for(Cout, (long long)p.N * cdiv(OH, th) * cdiv(OW, tw));
+  const int rows = rows_per_cta(MODE_CONV, (long long)p.N * cdiv(OH, th) * cdiv(OW, tw), cdiv(Cout, bn_guess));
+  if (rows == 256) pick_tile(OH, OW, 256, &th, &tw);
   CUtensorMap maps[5];
   Params P;
   memset(&P, 0, sizeof(P));
@@ -600,9 +603,9 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
       }
   }
   const int K = P.taps * P.c_chunks * 64;
-  const int bn = block_n_for(Cout, (long long)p.N * cdiv(OH, th) * cdiv(OW, tw));
+  const int bn = bn_guess;
   if ((rc = encode_2d(&maps[4], wf, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2,
-                      (uint32_t)(bn / cluster_size(MODE_CONV, bn)))))
+                      (uint32_t)(bn / (rows == 128 ? cluster_size(MODE_CONV, bn) : 1)))))
     return rc;
   P.M = 0;
   P.N = Cout;
@@ -624,7 +627,7 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
   dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(Cout, bn), 1);
   static const char* names[5] = {"", "fcd_conv1_fwd", "fcd_conv2_fwd", "fcd_conv3_fwd", "fcd_conv4_fwd"};
   return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l),
-                layer_bytes(p, l, 0) + 2.0 * Cout * K);
+                layer_bytes(p, l, 0) + 2.0 * Cout * K, rows);
 }
 
 // dIn (= dPre_{l-1} after the LeakyReLU mask, or dA0 for l == 1) from dPre_l
@@ -636,14 +639,16 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   const int eh = (Hin + 1) / 2, ew = (Win + 1) / 2;  // largest parity class
   int th = 1, tw = 128;
   pick_tile(eh, ew, 128, &th, &tw);
+  const int bn = block_n_for(rows, 4LL * p.N * cdiv(eh, th) * cdiv(ew, tw));
+  const int tile_rows = rows_per_cta(MODE_CONV, (long long)p.N * cdiv(eh, th) * cdiv(ew, tw), 4LL * cdiv(rows, bn));
+  if (tile_rows == 256) pick_tile(eh, ew, 256, &th, &tw);
   CUtensorMap maps[5];
   int rc;
   if ((rc = encode_plain(&maps[0], dpre, p.N, Hout, Wout, Cout, th, tw))) return rc;
   maps[1] = maps[2] = maps[3] = maps[0];
   const int K = 4 * Cout;
-  const int bn = block_n_for(rows, 4LL * p.N * cdiv(eh, th) * cdiv(ew, tw));
   if ((rc = encode_2d(&maps[4], wd, (uint64_t)K, (uint64_t)4 * rows, (uint64_t)K * 2,
-                      (uint32_t)(bn / cluster_size(MODE_CONV, bn)))))
+                      (uint32_t)(bn / (tile_rows == 128 ? cluster_size(MODE_CONV, bn) : 1)))))
     return rc;
   Params P;
   memset(&P, 0, sizeof(P));
@@ -683,7 +688,7 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   static const char* names[5] = {"", "fcd_conv1_dgrad", "fcd_conv2_dgrad", "fcd_conv3_dgrad", "fcd_conv4_dgrad"};
   // reads dPre_l and the mask source A_{l-1}, writes dIn (same size as A_{l-1})
   return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l),
-                layer_bytes(p, l, 0) + (l > 1 ? layer_bytes(p, l, 1) : 0.0) + 2.0 * 4 * rows * K);
+                layer_bytes(p, l, 0) + (l > 1 ? layer_bytes(p, l, 1) : 0.0) + 2.0 * 4 * rows * K, tile_rows);
 }
 
 static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* act_in, float* part,

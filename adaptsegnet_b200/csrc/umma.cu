@@ -80,14 +80,13 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
   return encode(m, base, 4, dims, strides_bytes, box);
 }
 
-// Persistent CTAs per SM and ring depth.  BLOCK_N <= 128: two CTAs per SM (2 x 2*BLOCK_N <= 512 TMEM
-// columns, ~104 KB ring each) -- their k-steps are cheap (<= 256 MMA cycles), so one TMA-issuing
-// thread per SM cannot keep the tensor pipe fed; two producers can.  BLOCK_N > 128: one CTA per SM
-// with the whole ~192 KB ring (the double-buffered accumulator needs all 512 TMEM columns).
-template <int BLOCK_N>
+// Persistent CTAs per SM and ring depth.  MT = 1 and BLOCK_N <= 128: two CTAs per SM (2 x 2*BLOCK_N <= 512 TMEM
+// columns, ~104 KB ring each) -- their k-steps are cheap, two TMA-issuing threads per SM keep the pipe fed better than
+// one.  Otherwise one CTA per SM with the whole ~196 KB ring.
+template <int BLOCK_N, int MT>
 struct Stages {
-  static constexpr int ctas_per_sm = BLOCK_N <= 128 ? 2 : 1;
-  static constexpr int stage = 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
+  static constexpr int ctas_per_sm = (BLOCK_N <= 128 && MT == 1) ? 2 : 1;
+  static constexpr int stage = MT * 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
   static constexpr int fit = ((ctas_per_sm == 2 ? 104 : 196) * 1024) / stage;
   static constexpr int value = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
@@ -103,12 +102,12 @@ int cluster_size(int mode, int block_n) {
   return (mode == MODE_GEMM || mode == MODE_CONV) && block_n >= 128 ? 2 : 1;
 }
 
-template <int MODE, int BLOCK_N, int CL>
+template <int MODE, int BLOCK_N, int CL, int MT>
 static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st, const char* name,
                     double flops, double bytes) {
-  constexpr int STAGES = Stages<BLOCK_N>::value;
-  using L = SmemLayout<BLOCK_N, STAGES>;
-  auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL>;
+  constexpr int STAGES = Stages<BLOCK_N, MT>::value;
+  using L = SmemLayout<BLOCK_N, STAGES, MT>;
+  auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL, MT>;
   static bool configured = false;
   if (!configured) {
     ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -119,7 +118,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
   Pp.grid_y = (int)grid.y;
   Pp.grid_z = (int)grid.z;
   const long long tiles = (long long)((grid.x + CL - 1) / CL) * grid.y * grid.z;  // (pairs of) tiles
-  const long long slots = (long long)sm_count() * Stages<BLOCK_N>::ctas_per_sm / CL;
+  const long long slots = (long long)sm_count() * Stages<BLOCK_N, MT>::ctas_per_sm / CL;
   const int ctas = (int)(tiles < slots ? tiles : slots) * CL;
   prof::Scope ps(name, flops, bytes, st);
   if (CL == 1) {
@@ -152,29 +151,46 @@ bool block_n_supported(int mode, int block_n) {
   return false;
 }
 
+// 256-row CTA tiles (MT = 2) pay off when there is still more than a wave of them; `m_tiles_128` = number of
+// 128-row tiles along M, `other` = tiles along the remaining grid dimensions.
+int rows_per_cta(int mode, long long m_tiles_128, long long other) {
+  static const bool off = getenv("ASN_NO_MT2") != nullptr;
+  if (off || mode == MODE_WGRAD) return BLOCK_M;
+  const long long tiles2 = ((m_tiles_128 + 1) / 2) * other;
+  return tiles2 * 4 >= 5LL * sm_count() ? 2 * BLOCK_M : BLOCK_M;
+}
+
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
-           const char* prof_name, double prof_flops, double prof_bytes) {
-  const int cl = cluster_size(mode, block_n);
-#define ASN_CASE(MODE, BN, CLS) \
-  if (mode == MODE && block_n == BN && cl == CLS)  \
-    return launch_t<MODE, BN, CLS>(maps, P, grid, st, prof_name, prof_flops, prof_bytes);
-  ASN_CASE(MODE_GEMM, 128, 1)
-  ASN_CASE(MODE_GEMM, 176, 1)
-  ASN_CASE(MODE_GEMM, 256, 1)
-  ASN_CASE(MODE_GEMM, 128, 2)
-  ASN_CASE(MODE_GEMM, 176, 2)
-  ASN_CASE(MODE_GEMM, 256, 2)
-  ASN_CASE(MODE_CONV, 32, 1)
-  ASN_CASE(MODE_CONV, 64, 1)
-  ASN_CASE(MODE_CONV, 128, 1)
-  ASN_CASE(MODE_CONV, 256, 1)
-  ASN_CASE(MODE_CONV, 128, 2)
-  ASN_CASE(MODE_CONV, 256, 2)
-  ASN_CASE(MODE_WGRAD, 64, 1)
-  ASN_CASE(MODE_WGRAD, 128, 1)
-  ASN_CASE(MODE_WGRAD, 256, 1)
+           const char* prof_name, double prof_flops, double prof_bytes, int rows) {
+  const int cl = rows == BLOCK_M ? cluster_size(mode, block_n) : 1;
+  const int mt = rows / BLOCK_M;
+#define ASN_CASE(MODE, BN, CLS, MTS) \
+  if (mode == MODE && block_n == BN && cl == CLS && mt == MTS)  \
+    return launch_t<MODE, BN, CLS, MTS>(maps, P, grid, st, prof_name, prof_flops, prof_bytes);
+  ASN_CASE(MODE_GEMM, 128, 1, 1)
+  ASN_CASE(MODE_GEMM, 176, 1, 1)
+  ASN_CASE(MODE_GEMM, 256, 1, 1)
+  ASN_CASE(MODE_GEMM, 128, 2, 1)
+  ASN_CASE(MODE_GEMM, 176, 2, 1)
+  ASN_CASE(MODE_GEMM, 256, 2, 1)
+  ASN_CASE(MODE_GEMM, 128, 1, 2)
+  ASN_CASE(MODE_GEMM, 176, 1, 2)
+  ASN_CASE(MODE_GEMM, 256, 1, 2)
+  ASN_CASE(MODE_CONV, 32, 1, 1)
+  ASN_CASE(MODE_CONV, 64, 1, 1)
+  ASN_CASE(MODE_CONV, 128, 1, 1)
+  ASN_CASE(MODE_CONV, 256, 1, 1)
+  ASN_CASE(MODE_CONV, 128, 2, 1)
+  ASN_CASE(MODE_CONV, 256, 2, 1)
+  ASN_CASE(MODE_CONV, 32, 1, 2)
+  ASN_CASE(MODE_CONV, 64, 1, 2)
+  ASN_CASE(MODE_CONV, 128, 1, 2)
+  ASN_CASE(MODE_CONV, 256, 1, 2)
+  ASN_CASE(MODE_WGRAD, 64, 1, 1)
+  ASN_CASE(MODE_WGRAD, 128, 1, 1)
+  ASN_CASE(MODE_WGRAD, 256, 1, 1)
 #undef ASN_CASE
-  set_error("umma::launch: no kernel for mode %d block_n %d", mode, block_n);
+  set_error("umma::launch: no kernel for mode %d block_n %d rows %d", mode, block_n, rows);
   return ASN_EUNSUPPORTED;
 }
 
@@ -187,10 +203,13 @@ int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda
   ASN_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "gemm_tn: lda/ldb must be >= K and multiples of 8");
   ASN_CHECK_ARG(block_n_supported(MODE_GEMM, block_n), "gemm_tn: unsupported block_n %d", block_n);
   CUtensorMap maps[5];
-  int rc = encode_2d(&maps[0], A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BLOCK_M);
+  const int k_steps_all = cdiv(K, BLOCK_K);
+  int split_req = split_k < 1 ? 1 : (split_k > k_steps_all ? k_steps_all : split_k);
+  const int rows = rows_per_cta(MODE_GEMM, cdiv(M, BLOCK_M), (long long)cdiv(N, block_n) * split_req);
+  int rc = encode_2d(&maps[0], A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, (uint32_t)rows);
   if (rc) return rc;
   rc = encode_2d(&maps[4], B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2,
-                 (uint32_t)(block_n / cluster_size(MODE_GEMM, block_n)));
+                 (uint32_t)(block_n / (rows == BLOCK_M ? cluster_size(MODE_GEMM, block_n) : 1)));
   if (rc) return rc;
   maps[1] = maps[2] = maps[3] = maps[0];
   Params P;
@@ -207,9 +226,9 @@ int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda
   P.ld_out = ldc;
   P.z_stride_out = split_stride;
   P.slope = 1.f;
-  dim3 grid(cdiv(M, BLOCK_M), cdiv(N, block_n), split_k);
+  dim3 grid(cdiv(M, rows), cdiv(N, block_n), split_k);
   return launch(MODE_GEMM, block_n, maps, P, grid, st, prof_name, prof_flops >= 0 ? prof_flops : 2.0 * M * N * K,
-                2.0 * M * K + 2.0 * N * K + 4.0 * M * N * split_k);
+                2.0 * M * K + 2.0 * N * K + 4.0 * M * N * split_k, rows);
 }
 
 int effective_split(int K, int split_k) {

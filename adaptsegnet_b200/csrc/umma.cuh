@@ -216,11 +216,15 @@ struct Params {
   float mask_slope;
 };
 
-// two accumulator buffers of BLOCK_N fp32 columns each, power-of-two allocation
-template <int BLOCK_N>
+// A CTA tile is MT x 128 rows: MT accumulators of BLOCK_N fp32 columns that share every B stage (per byte of shared
+// memory filled, MT = 2 does twice the MMA work on B).  Two sets of accumulators (double buffering against the
+// epilogue) when 2 * MT * BLOCK_N <= 512 columns, otherwise one.  Power-of-two allocation.
+template <int BLOCK_N, int MT>
 struct TmemCols {
-  static constexpr int value = 2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
-                               : 2 * BLOCK_N <= 256 ? 256 : 512;
+  static constexpr int per_tile = MT * BLOCK_N;
+  static constexpr int nacc = 2 * per_tile <= 512 ? 2 : 1;
+  static constexpr int need = nacc * per_tile;
+  static constexpr int value = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
 };
 
 constexpr int BLOCK_M = 128;
@@ -228,9 +232,9 @@ constexpr int BLOCK_K = 64;  // bf16 elements per k-step = one 128-byte swizzle 
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT = 1>
 struct SmemLayout {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+  static constexpr int A_BYTES = MT * BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
@@ -245,7 +249,7 @@ struct TileCoord {
 // CL = 1: tile -> (bx, by, bz).  CL = 2 (cluster of two CTAs sharing B by multicast): `tile` indexes PAIRS of
 // x-neighbours, this CTA takes bx = 2 * pair + rank; a pair hanging over the end of an odd grid_x still runs its
 // main loop (the multicast must stay in lock-step) on out-of-range coordinates -- TMA zero-fills, `valid` masks.
-template <int MODE, int BLOCK_N, int CL>
+template <int MODE, int BLOCK_N, int CL, int MT>
 __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int rank) {
   TileCoord t;
   const int gx = CL == 1 ? P.grid_x : (P.grid_x + 1) / 2;
@@ -257,7 +261,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int 
   t.ks_begin = 0;
   int ks_end = P.k_steps;
   if (MODE == MODE_GEMM) {
-    t.m0 = bx * BLOCK_M;
+    t.m0 = bx * (BLOCK_M * MT);
     t.n0 = by * BLOCK_N;
     t.ks_begin = t.z * P.steps_per_split;
     ks_end = min(P.k_steps, t.ks_begin + P.steps_per_split);
@@ -279,13 +283,15 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int 
   return t;
 }
 
-template <int MODE, int BLOCK_N, int STAGES, int CL>
-__global__ void __launch_bounds__(NUM_THREADS, (BLOCK_N <= 128 ? 2 : 1))
+template <int MODE, int BLOCK_N, int STAGES, int CL, int MT>
+__global__ void __launch_bounds__(NUM_THREADS, ((BLOCK_N <= 128 && MT == 1) ? 2 : 1))
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
-  constexpr int TMEM_COLS = TmemCols<BLOCK_N>::value;
+  using L = SmemLayout<BLOCK_N, STAGES, MT>;
+  constexpr int TMEM_COLS = TmemCols<BLOCK_N, MT>::value;
+  constexpr int NACC = TmemCols<BLOCK_N, MT>::nacc;
+  static_assert(MT == 1 || MODE != MODE_WGRAD, "WGRAD tiles are 128 channels tall");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
@@ -339,7 +345,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       const CUtensorMap* amaps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
       uint32_t it = 0;  // k-steps issued so far: the ring keeps streaming across tiles
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-        const TileCoord t = decode_tile<MODE, BLOCK_N, CL>(P, tile, rank);
+        const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
         for (int i = 0; i < t.nsteps; ++i, ++it) {
           const int ks = t.ks_begin + i;
           const int s = it % STAGES;
@@ -390,12 +396,12 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                                     : make_idesc(BLOCK_M, BLOCK_N, 0, 0);
       uint32_t it = 0, tile_iter = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
-        const TileCoord t = decode_tile<MODE, BLOCK_N, CL>(P, tile, rank);
-        const uint32_t acc = tile_iter & 1;
-        const uint32_t acc_ph = (tile_iter >> 1) & 1;
-        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
+        const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
+        const uint32_t acc = NACC == 2 ? (tile_iter & 1) : 0;
+        const uint32_t acc_ph = NACC == 2 ? ((tile_iter >> 1) & 1) : (tile_iter & 1);
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator set
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N);
         for (int i = 0; i < t.nsteps; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -417,6 +423,10 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               db = make_smem_desc(sb + k * 32, 16, 1024);
             }
             mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (MT == 2) {  // rows 128..255 of the tile: next 16 KB of the A stage, same B
+              const uint64_t da1 = make_smem_desc(sa + BLOCK_M * BLOCK_K * 2 + k * 32, 16, 1024);
+              mma_f16_ss(tmem_d + BLOCK_N, da1, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
           }
           // frees the stage (here and, under multicast, in the peer) once these MMAs have read it
           if (CL == 1) mma_commit(empty_bar(s)); else mma_commit_mcast(empty_bar(s), CL_MASK);
@@ -427,15 +437,17 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   } else {
     // =============================== epilogue ===============================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;        // accumulator row owned by this thread
     uint32_t tile_iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
-      const TileCoord t = decode_tile<MODE, BLOCK_N, CL>(P, tile, rank);
-      const uint32_t acc = tile_iter & 1;
-      const uint32_t acc_ph = (tile_iter >> 1) & 1;
+      const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
+      const uint32_t acc = NACC == 2 ? (tile_iter & 1) : 0;
+      const uint32_t acc_ph = NACC == 2 ? ((tile_iter >> 1) & 1) : (tile_iter & 1);
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+      const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N) + sub * BLOCK_N;
+      const int r = sub * BLOCK_M + q * 32 + lane;  // row of the CTA tile owned by this thread in this pass
       bool row_ok;
       long long row_off;
       if (MODE == MODE_GEMM) {
@@ -517,6 +529,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           }
         }
       }
+      }  // sub
       // this thread's TMEM reads of the tile are complete (tcgen05.wait::ld in tmem_ld16): release the buffer
       __syncwarp();
       tc_fence_before();

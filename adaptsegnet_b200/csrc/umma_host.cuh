@@ -14,8 +14,12 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
               uint32_t box1, uint32_t box2);
 
 // maps = {a0, a1, a2, a3, b}.  grid as documented on umma_kernel.
+// rows = rows of the CTA tile: 128, or 256 (two accumulators sharing every B stage; the A tensor map / pixel box must
+// then cover 256 rows).  grid.x counts tiles of that height.
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
-           const char* prof_name = "umma", double prof_flops = 0, double prof_bytes = 0);
+           const char* prof_name = "umma", double prof_flops = 0, double prof_bytes = 0, int rows = BLOCK_M);
+// 128 or 256: the tile height the launcher recommends for this many 128-row tiles x other grid dimensions
+int rows_per_cta(int mode, long long m_tiles_128, long long other);
 
 // BLOCK_N choices compiled for each mode
 bool block_n_supported(int mode, int block_n);
