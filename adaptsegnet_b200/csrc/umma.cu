@@ -87,7 +87,7 @@ template <int BLOCK_N, int MT>
 struct Stages {
   static constexpr int ctas_per_sm = (BLOCK_N <= 128 && MT == 1) ? 2 : 1;
   static constexpr int stage = MT * 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
-  static constexpr int fit = ((ctas_per_sm == 2 ? 104 : 196) * 1024) / stage;
+  static constexpr int fit = ((ctas_per_sm == 2 ? 100 : 196) * 1024) / stage;  // + 12 KB epilogue staging
   static constexpr int value = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
 

@@ -231,6 +231,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements per k-step = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
+constexpr int EPI_PITCH = 20;  // floats per staged row: 16 columns + 4 pad (16-byte aligned, conflict-free float4 rows)
 
 template <int BLOCK_N, int STAGES, int MT = 1>
 struct SmemLayout {
@@ -238,7 +239,9 @@ struct SmemLayout {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers (<= 21 x 8 B) + alignment slack
+  static constexpr int STG_OFFSET = BAR_OFFSET + 256;                     // barriers take <= 21 x 8 B
+  static constexpr int ROW_OFFSET = STG_OFFSET + 4 * 32 * EPI_PITCH * 4;  // 4 epilogue warps x [32][EPI_PITCH] fp32
+  static constexpr int TOTAL = ROW_OFFSET + 4 * 32 * 8 + 1024;            // + row tables + alignment slack
 };
 
 struct TileCoord {
@@ -436,7 +439,17 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
   } else {
     // =============================== epilogue ===============================
+    // TMEM -> registers (thread = accumulator row) -> a per-warp shared-memory transpose buffer -> global.
+    // Going through shared memory turns the natural "one thread owns one row" ownership into stores where the
+    // four lanes of a quad write 64 (fp32) / 32 (bf16) contiguous bytes of one row and a warp instruction covers
+    // eight complete row segments -- full 32-byte sectors instead of 32 scattered 16-byte pieces.  Bias, LeakyReLU
+    // and the LeakyReLU-mask multiply are applied on the way out (mask reads are coalesced the same way).
     const int q = warp & 3;             // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + L::STG_OFFSET) +
+                 q * (32 * EPI_PITCH);
+    long long* row_tab = reinterpret_cast<long long*>(smem_raw + (smem_base - smem_u32(smem_raw)) + L::ROW_OFFSET) +
+                         q * 32;  // element offset of each of this warp's 32 rows, -1 = masked row
+    const int rr = lane >> 2, cq = lane & 3;  // write-out role: row (of 8) and column quad
     uint32_t tile_iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
       const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
@@ -446,89 +459,98 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
-      const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N) + sub * BLOCK_N;
-      const int r = sub * BLOCK_M + q * 32 + lane;  // row of the CTA tile owned by this thread in this pass
-      bool row_ok;
-      long long row_off;
-      if (MODE == MODE_GEMM) {
-        row_ok = t.valid && (t.m0 + r) < P.M;
-        row_off = (long long)t.z * P.z_stride_out + (long long)(t.m0 + r) * P.ld_out;
-      } else if (MODE == MODE_CONV) {
-        const int dy = r / P.tw, dx = r - dy * P.tw;
-        const int oh = t.oh0 + dy, ow = t.ow0 + dx;
-        row_ok = t.valid && oh < P.oh_ext[t.z] && ow < P.ow_ext[t.z];
-        const int fh = oh * P.sy + P.oy[t.z], fw = ow * P.sx + P.ox[t.z];
-        row_off = (((long long)t.img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
-      } else {
-        row_ok = (t.m0 + r) < P.M;
-        row_off = (long long)t.z * P.z_stride_out + (long long)t.wg_tap * P.tap_stride_out +
-                  (long long)(t.m0 + r) * P.ld_out;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
-        float v[16];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
-        if (t.nsteps > 0) {
-          tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        }
-        const int n = t.n0 + c;
-        if (!row_ok || n >= P.N) continue;
-        if (P.epi == EPI_F32) {
-          float* dst = reinterpret_cast<float*>(P.out) + row_off + n;
-          if (n + 16 <= P.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N) + sub * BLOCK_N;
+        {  // row table: thread = row
+          const int r = sub * BLOCK_M + q * 32 + lane;
+          bool row_ok;
+          long long row_off;
+          if (MODE == MODE_GEMM) {
+            row_ok = t.valid && (t.m0 + r) < P.M;
+            row_off = (long long)t.z * P.z_stride_out + (long long)(t.m0 + r) * P.ld_out;
+          } else if (MODE == MODE_CONV) {
+            const int dy = r / P.tw, dx = r - dy * P.tw;
+            const int oh = t.oh0 + dy, ow = t.ow0 + dx;
+            row_ok = t.valid && oh < P.oh_ext[t.z] && ow < P.ow_ext[t.z];
+            const int fh = oh * P.sy + P.oy[t.z], fw = ow * P.sx + P.ox[t.z];
+            row_off = (((long long)t.img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
           } else {
-            for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = v[i];
+            row_ok = (t.m0 + r) < P.M;
+            row_off = (long long)t.z * P.z_stride_out + (long long)t.wg_tap * P.tap_stride_out +
+                      (long long)(t.m0 + r) * P.ld_out;
           }
-        } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + row_off + n;
-          const bool full = n + 16 <= P.N;
-          if (P.bias) {
+          __syncwarp();
+          row_tab[lane] = row_ok ? row_off : -1;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 16) {
+          float v[16];
+          __syncwarp();  // previous chunk's reads of stg are done; also reconverges for the .aligned tcgen05.ld
+          if (t.nsteps > 0) {
+            tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+          } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += (full || n + i < P.N) ? __ldg(P.bias + n + i) : 0.f;
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
           }
-          if (P.slope != 1.f) {
+          float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * P.slope;
+          for (int i = 0; i < 4; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+          const int n = t.n0 + c + cq * 4;  // first of this lane's four output columns
+          if (n >= P.N) continue;
+          const bool full = n + 4 <= P.N;
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (P.epi == EPI_BF16 && P.bias) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bv[i] = (full || n + i < P.N) ? __ldg(P.bias + n + i) : 0.f;
           }
-          if (P.mask_src) {
-            const __nv_bfloat16* ms = P.mask_src + row_off + n;
-            if (full && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
-              const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(ms));
-              const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(ms) + 1);
-              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                // bf16 > 0  <=>  sign bit clear and not zero
-                const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
-                v[2 * i] *= (lo != 0u && lo < 0x8000u) ? 1.f : P.mask_slope;
-                v[2 * i + 1] *= (hi != 0u && hi < 0x8000u) ? 1.f : P.mask_slope;
+          for (int j = 0; j < 4; ++j) {
+            const int rl = j * 8 + rr;
+            const long long off = row_tab[rl];
+            if (off < 0) continue;
+            const float4 x = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq * 4);
+            float o[4] = {x.x, x.y, x.z, x.w};
+            if (P.epi == EPI_F32) {
+              float* dst = reinterpret_cast<float*>(P.out) + off + n;
+              if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                *reinterpret_cast<float4*>(dst) = x;
+              } else {
+                for (int i = 0; i < 4 && n + i < P.N; ++i) dst[i] = o[i];
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (full || n + i < P.N) v[i] *= (__bfloat162float(ms[i]) > 0.f ? 1.f : P.mask_slope);
-            }
-          }
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            uint32_t pk[8];
+              for (int i = 0; i < 4; ++i) {
+                o[i] += bv[i];
+                if (P.slope != 1.f) o[i] = o[i] > 0.f ? o[i] : o[i] * P.slope;
+              }
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + off + n;
+              const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+              if (P.mask_src) {
+                const __nv_bfloat16* ms = P.mask_src + off + n;
+                if (vec) {
+                  const uint2 m = __ldg(reinterpret_cast<const uint2*>(ms));
+                  const uint32_t mw[2] = {m.x, m.y};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                  for (int i = 0; i < 2; ++i) {  // bf16 > 0  <=>  sign bit clear and not zero
+                    const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+                    o[2 * i] *= (lo != 0u && lo < 0x8000u) ? 1.f : P.mask_slope;
+                    o[2 * i + 1] *= (hi != 0u && hi < 0x8000u) ? 1.f : P.mask_slope;
+                  }
+                } else {
+                  for (int i = 0; i < 4 && n + i < P.N; ++i)
+                    o[i] *= (__bfloat162float(ms[i]) > 0.f ? 1.f : P.mask_slope);
+                }
+              }
+              if (vec) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+                *reinterpret_cast<uint2*>(dst) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+              } else {
+                for (int i = 0; i < 4 && n + i < P.N; ++i) dst[i] = __float2bfloat16(o[i]);
+              }
             }
-            reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            for (int i = 0; i < 16 && n + i < P.N; ++i) dst[i] = __float2bfloat16(v[i]);
           }
         }
-      }
       }  // sub
       // this thread's TMEM reads of the tile are complete (tcgen05.wait::ld in tmem_ld16): release the buffer
       __syncwarp();
