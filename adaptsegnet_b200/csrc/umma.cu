@@ -80,14 +80,13 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
   return encode(m, base, 4, dims, strides_bytes, box);
 }
 
-// Persistent CTAs per SM and ring depth.  MT = 1 and BLOCK_N <= 128: two CTAs per SM (2 x 2*BLOCK_N <= 512 TMEM
-// columns, ~104 KB ring each) -- their k-steps are cheap, two TMA-issuing threads per SM keep the pipe fed better than
-// one.  Otherwise one CTA per SM with the whole ~196 KB ring.
+// One persistent CTA per SM (320 threads: eight epilogue warps); the ring takes what the 227 KB of shared memory
+// leave after the ~40 KB of epilogue staging.
 template <int BLOCK_N, int MT>
 struct Stages {
-  static constexpr int ctas_per_sm = (BLOCK_N <= 128 && MT == 1) ? 2 : 1;
+  static constexpr int ctas_per_sm = 1;
   static constexpr int stage = MT * 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
-  static constexpr int fit = ((ctas_per_sm == 2 ? 100 : 196) * 1024) / stage;  // + 12 KB epilogue staging
+  static constexpr int fit = (184 * 1024) / stage;
   static constexpr int value = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
 
@@ -154,8 +153,9 @@ bool block_n_supported(int mode, int block_n) {
 // 256-row CTA tiles (MT = 2) pay off when there is still more than a wave of them; `m_tiles_128` = number of
 // 128-row tiles along M, `other` = tiles along the remaining grid dimensions.
 int rows_per_cta(int mode, long long m_tiles_128, long long other) {
-  static const bool off = getenv("ASN_NO_MT2") != nullptr;
-  if (off || mode == MODE_WGRAD) return BLOCK_M;
+  // measured on B200: no gain at the shapes of this path (the epilogue, not the operand feed, bounds them) -> opt-in
+  static const bool on = getenv("ASN_MT2") != nullptr && getenv("ASN_MT2")[0] == '1';
+  if (!on || mode == MODE_WGRAD) return BLOCK_M;
   const long long tiles2 = ((m_tiles_128 + 1) / 2) * other;
   return tiles2 * 4 >= 5LL * sm_count() ? 2 * BLOCK_M : BLOCK_M;
 }

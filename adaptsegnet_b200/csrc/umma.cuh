@@ -150,6 +150,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ------------------------------------------------------------------------------------------
 // descriptors (cute/arch/mma_sm100_desc.hpp bit layout)
 // ------------------------------------------------------------------------------------------
@@ -230,8 +247,10 @@ struct TmemCols {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements per k-step = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_PITCH = 20;  // floats per staged row: 16 columns + 4 pad (16-byte aligned, conflict-free float4 rows)
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, alternating column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // TMA producer warp + MMA warp + epilogue warps
+constexpr int EPI_CHUNK = 32;                      // accumulator columns staged per pass
+constexpr int EPI_PITCH = EPI_CHUNK + 4;           // floats per staged row (16-byte aligned, conflict-free float4 rows)
 
 template <int BLOCK_N, int STAGES, int MT = 1>
 struct SmemLayout {
@@ -240,8 +259,8 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int STG_OFFSET = BAR_OFFSET + 256;                     // barriers take <= 21 x 8 B
-  static constexpr int ROW_OFFSET = STG_OFFSET + 4 * 32 * EPI_PITCH * 4;  // 4 epilogue warps x [32][EPI_PITCH] fp32
-  static constexpr int TOTAL = ROW_OFFSET + 4 * 32 * 8 + 1024;            // + row tables + alignment slack
+  static constexpr int ROW_OFFSET = STG_OFFSET + EPI_WARPS * 32 * EPI_PITCH * 4;  // per-warp [32][EPI_PITCH] fp32
+  static constexpr int TOTAL = ROW_OFFSET + EPI_WARPS * 32 * 8 + 1024;            // + row tables + alignment slack
 };
 
 struct TileCoord {
@@ -287,7 +306,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int 
 }
 
 template <int MODE, int BLOCK_N, int STAGES, int CL, int MT>
-__global__ void __launch_bounds__(NUM_THREADS, ((BLOCK_N <= 128 && MT == 1) ? 2 : 1))
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
@@ -329,7 +348,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), NUM_THREADS - 64);  // every epilogue thread arrives
+      mbar_init(tmem_empty_bar(a), 32 * EPI_WARPS);  // every epilogue thread arrives
     }
     fence_barrier_init();
   }
@@ -440,16 +459,19 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   } else {
     // =============================== epilogue ===============================
     // TMEM -> registers (thread = accumulator row) -> a per-warp shared-memory transpose buffer -> global.
-    // Going through shared memory turns the natural "one thread owns one row" ownership into stores where the
-    // four lanes of a quad write 64 (fp32) / 32 (bf16) contiguous bytes of one row and a warp instruction covers
-    // eight complete row segments -- full 32-byte sectors instead of 32 scattered 16-byte pieces.  Bias, LeakyReLU
-    // and the LeakyReLU-mask multiply are applied on the way out (mask reads are coalesced the same way).
+    // Going through shared memory turns the natural "one thread owns one row" ownership into stores where the four
+    // lanes of a quad write 128 (fp32) / 64 (bf16) contiguous bytes of one row and a warp instruction covers eight
+    // complete row segments, instead of 32 scattered 16-byte pieces.  Bias, LeakyReLU and the LeakyReLU-mask multiply
+    // are applied on the way out (mask reads are coalesced the same way).  Eight warps: two per TMEM lane quarter,
+    // taking alternate 32-column chunks, so that short-K tiles (whose epilogue outlasts their MMAs) drain faster.
+    const int ew = warp - 2;            // 0..7
     const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = ew >> 2;           // which of the two warps of that quarter
     float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + L::STG_OFFSET) +
-                 q * (32 * EPI_PITCH);
+                 ew * (32 * EPI_PITCH);
     long long* row_tab = reinterpret_cast<long long*>(smem_raw + (smem_base - smem_u32(smem_raw)) + L::ROW_OFFSET) +
-                         q * 32;  // element offset of each of this warp's 32 rows, -1 = masked row
-    const int rr = lane >> 2, cq = lane & 3;  // write-out role: row (of 8) and column quad
+                         ew * 32;  // element offset of each of this warp's 32 rows, -1 = masked row
+    const int rr = lane >> 2, cq = lane & 3;  // write-out role: row (of 8) and group of 8 columns
     uint32_t tile_iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
       const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
@@ -482,77 +504,87 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           row_tab[lane] = row_ok ? row_off : -1;
         }
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 16) {
-          float v[16];
+        for (int c = half * EPI_CHUNK; c < BLOCK_N; c += 2 * EPI_CHUNK) {
+          float v[EPI_CHUNK];
           __syncwarp();  // previous chunk's reads of stg are done; also reconverges for the .aligned tcgen05.ld
           if (t.nsteps > 0) {
-            tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);  // may run past BLOCK_N: masked below
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            for (int i = 0; i < EPI_CHUNK; ++i) v[i] = 0.f;
           }
           float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < EPI_CHUNK / 4; ++i)
+            srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           __syncwarp();
-          const int n = t.n0 + c + cq * 4;  // first of this lane's four output columns
-          if (n >= P.N) continue;
-          const bool full = n + 4 <= P.N;
-          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          const int cl = c + cq * 8;        // first of this lane's eight columns inside the tile
+          const int n = t.n0 + cl;
+          if (cl >= BLOCK_N || n >= P.N) continue;
+          const int n_ok = min(min(BLOCK_N - cl, P.N - n), 8);  // valid columns of this lane
+          const bool full = n_ok == 8;
+          float bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = 0.f;
           if (P.epi == EPI_BF16 && P.bias) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) bv[i] = (full || n + i < P.N) ? __ldg(P.bias + n + i) : 0.f;
+            for (int i = 0; i < 8; ++i) bv[i] = i < n_ok ? __ldg(P.bias + n + i) : 0.f;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rl = j * 8 + rr;
             const long long off = row_tab[rl];
             if (off < 0) continue;
-            const float4 x = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq * 4);
-            float o[4] = {x.x, x.y, x.z, x.w};
+            const float4 x0 = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq * 8 + 4);
+            float o[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
             if (P.epi == EPI_F32) {
               float* dst = reinterpret_cast<float*>(P.out) + off + n;
               if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                *reinterpret_cast<float4*>(dst) = x;
+                reinterpret_cast<float4*>(dst)[0] = x0;
+                reinterpret_cast<float4*>(dst)[1] = x1;
               } else {
-                for (int i = 0; i < 4 && n + i < P.N; ++i) dst[i] = o[i];
+                for (int i = 0; i < n_ok; ++i) dst[i] = o[i];
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < 8; ++i) {
                 o[i] += bv[i];
                 if (P.slope != 1.f) o[i] = o[i] > 0.f ? o[i] : o[i] * P.slope;
               }
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + off + n;
-              const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+              const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
               if (P.mask_src) {
                 const __nv_bfloat16* ms = P.mask_src + off + n;
                 if (vec) {
-                  const uint2 m = __ldg(reinterpret_cast<const uint2*>(ms));
-                  const uint32_t mw[2] = {m.x, m.y};
+                  const uint4 m = __ldg(reinterpret_cast<const uint4*>(ms));
+                  const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-                  for (int i = 0; i < 2; ++i) {  // bf16 > 0  <=>  sign bit clear and not zero
+                  for (int i = 0; i < 4; ++i) {  // bf16 > 0  <=>  sign bit clear and not zero
                     const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
                     o[2 * i] *= (lo != 0u && lo < 0x8000u) ? 1.f : P.mask_slope;
                     o[2 * i + 1] *= (hi != 0u && hi < 0x8000u) ? 1.f : P.mask_slope;
                   }
                 } else {
-                  for (int i = 0; i < 4 && n + i < P.N; ++i)
-                    o[i] *= (__bfloat162float(ms[i]) > 0.f ? 1.f : P.mask_slope);
+                  for (int i = 0; i < n_ok; ++i) o[i] *= (__bfloat162float(ms[i]) > 0.f ? 1.f : P.mask_slope);
                 }
               }
               if (vec) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
-                *reinterpret_cast<uint2*>(dst) =
-                    make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                  pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               } else {
-                for (int i = 0; i < 4 && n + i < P.N; ++i) dst[i] = __float2bfloat16(o[i]);
+                for (int i = 0; i < n_ok; ++i) dst[i] = __float2bfloat16(o[i]);
               }
             }
           }
         }
       }  // sub
-      // this thread's TMEM reads of the tile are complete (tcgen05.wait::ld in tmem_ld16): release the buffer
+      // this thread's TMEM reads of the tile are complete (tcgen05.wait::ld in tmem_ld32): release the buffer
       __syncwarp();
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
