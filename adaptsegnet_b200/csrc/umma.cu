@@ -80,14 +80,16 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
   return encode(m, base, 4, dims, strides_bytes, box);
 }
 
-// One persistent CTA per SM (320 threads: eight epilogue warps); the ring takes what the 227 KB of shared memory
-// leave after the ~40 KB of epilogue staging.
-template <int BLOCK_N, int MT>
-struct Stages {
-  static constexpr int ctas_per_sm = 1;
+// Launch shape per (mode, BLOCK_N): EW = 8 -> one persistent CTA per SM, ring of <= 184 KB; EW = 4 -> two CTAs per SM,
+// ring of <= 100 KB each (umma.cuh, EpiCfg).  Measured on B200: the weight-gradient tiles (long K over pixels, N <= 128)
+// and the 32-column dgrad of conv1 run faster as two pipelines per SM, everything else with the eight-warp epilogue.
+template <int MODE, int BLOCK_N, int MT>
+struct Shape {
+  static constexpr int EW = (MT == 1 && ((MODE == MODE_WGRAD && BLOCK_N <= 128) || (MODE == MODE_CONV && BLOCK_N <= 32))) ? 4 : 8;
+  static constexpr int ctas_per_sm = EW == 4 ? 2 : 1;
   static constexpr int stage = MT * 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
-  static constexpr int fit = (184 * 1024) / stage;
-  static constexpr int value = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
+  static constexpr int fit = ((EW == 4 ? 100 : 184) * 1024) / stage;
+  static constexpr int stages = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
 
 // cluster size the launcher uses for (mode, block_n): 2 = pairs of x-neighbouring tiles share the B tile through
@@ -104,9 +106,10 @@ int cluster_size(int mode, int block_n) {
 template <int MODE, int BLOCK_N, int CL, int MT>
 static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st, const char* name,
                     double flops, double bytes) {
-  constexpr int STAGES = Stages<BLOCK_N, MT>::value;
-  using L = SmemLayout<BLOCK_N, STAGES, MT>;
-  auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL, MT>;
+  using Sh = Shape<MODE, BLOCK_N, MT>;
+  constexpr int STAGES = Sh::stages, EW = Sh::EW, NUM_THREADS = EpiCfg<EW>::threads;
+  using L = SmemLayout<BLOCK_N, STAGES, MT, EW>;
+  auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL, MT, EW>;
   static bool configured = false;
   if (!configured) {
     ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -117,7 +120,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
   Pp.grid_y = (int)grid.y;
   Pp.grid_z = (int)grid.z;
   const long long tiles = (long long)((grid.x + CL - 1) / CL) * grid.y * grid.z;  // (pairs of) tiles
-  const long long slots = (long long)sm_count() * Stages<BLOCK_N, MT>::ctas_per_sm / CL;
+  const long long slots = (long long)sm_count() * Sh::ctas_per_sm / CL;
   const int ctas = (int)(tiles < slots ? tiles : slots) * CL;
   prof::Scope ps(name, flops, bytes, st);
   if (CL == 1) {

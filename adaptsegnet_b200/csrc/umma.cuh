@@ -247,20 +247,27 @@ struct TmemCols {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements per k-step = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, alternating column chunks
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // TMA producer warp + MMA warp + epilogue warps
-constexpr int EPI_CHUNK = 32;                      // accumulator columns staged per pass
-constexpr int EPI_PITCH = EPI_CHUNK + 4;           // floats per staged row (16-byte aligned, conflict-free float4 rows)
+// Two launch shapes (template parameter EW = epilogue warps):
+//   EW = 8: one CTA per SM, 320 threads, two epilogue warps per TMEM lane quarter taking alternate 32-column chunks
+//           (128 / 64 contiguous bytes per row per store) -- tiles whose epilogue would outlast their MMAs
+//   EW = 4: two CTAs per SM, 192 threads each, 16-column chunks -- long-K, small-N tiles (weight gradients), where two
+//           independent TMA/MMA pipelines per SM hide the per-k-step latencies better than one
+template <int EW>
+struct EpiCfg {
+  static constexpr int chunk = EW == 8 ? 32 : 16;   // accumulator columns staged per pass
+  static constexpr int pitch = chunk + 4;           // floats per staged row (16-byte aligned, conflict-free float4 rows)
+  static constexpr int threads = 64 + 32 * EW;      // TMA producer warp + MMA warp + epilogue warps
+};
 
-template <int BLOCK_N, int STAGES, int MT = 1>
+template <int BLOCK_N, int STAGES, int MT = 1, int EW = 8>
 struct SmemLayout {
   static constexpr int A_BYTES = MT * BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int STG_OFFSET = BAR_OFFSET + 256;                     // barriers take <= 21 x 8 B
-  static constexpr int ROW_OFFSET = STG_OFFSET + EPI_WARPS * 32 * EPI_PITCH * 4;  // per-warp [32][EPI_PITCH] fp32
-  static constexpr int TOTAL = ROW_OFFSET + EPI_WARPS * 32 * 8 + 1024;            // + row tables + alignment slack
+  static constexpr int ROW_OFFSET = STG_OFFSET + EW * 32 * EpiCfg<EW>::pitch * 4;  // per-warp [32][pitch] fp32
+  static constexpr int TOTAL = ROW_OFFSET + EW * 32 * 8 + 1024;                    // + row tables + alignment slack
 };
 
 struct TileCoord {
@@ -305,12 +312,15 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int 
   return t;
 }
 
-template <int MODE, int BLOCK_N, int STAGES, int CL, int MT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int MODE, int BLOCK_N, int STAGES, int CL, int MT, int EW>
+__global__ void __launch_bounds__(EpiCfg<EW>::threads, (EW == 4 ? 2 : 1))
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
-  using L = SmemLayout<BLOCK_N, STAGES, MT>;
+  using L = SmemLayout<BLOCK_N, STAGES, MT, EW>;
+  constexpr int EPI_CHUNK = EpiCfg<EW>::chunk, EPI_PITCH = EpiCfg<EW>::pitch;
+  constexpr int CPL = EPI_CHUNK / 4;  // columns per lane on the way out (8 or 4)
+  static_assert(EW == 8 || 2 * TmemCols<BLOCK_N, MT>::value <= 512, "two CTAs per SM need <= 256 TMEM columns each");
   constexpr int TMEM_COLS = TmemCols<BLOCK_N, MT>::value;
   constexpr int NACC = TmemCols<BLOCK_N, MT>::nacc;
   static_assert(MT == 1 || MODE != MODE_WGRAD, "WGRAD tiles are 128 channels tall");
@@ -348,7 +358,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 32 * EPI_WARPS);  // every epilogue thread arrives
+      mbar_init(tmem_empty_bar(a), 32 * EW);  // every epilogue thread arrives
     }
     fence_barrier_init();
   }
@@ -464,14 +474,14 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     // complete row segments, instead of 32 scattered 16-byte pieces.  Bias, LeakyReLU and the LeakyReLU-mask multiply
     // are applied on the way out (mask reads are coalesced the same way).  Eight warps: two per TMEM lane quarter,
     // taking alternate 32-column chunks, so that short-K tiles (whose epilogue outlasts their MMAs) drain faster.
-    const int ew = warp - 2;            // 0..7
+    const int ew = warp - 2;            // 0..EW-1
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = ew >> 2;           // which of the two warps of that quarter
+    const int half = ew >> 2;           // which of the (EW / 4) warps of that quarter
     float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + L::STG_OFFSET) +
                  ew * (32 * EPI_PITCH);
     long long* row_tab = reinterpret_cast<long long*>(smem_raw + (smem_base - smem_u32(smem_raw)) + L::ROW_OFFSET) +
                          ew * 32;  // element offset of each of this warp's 32 rows, -1 = masked row
-    const int rr = lane >> 2, cq = lane & 3;  // write-out role: row (of 8) and group of 8 columns
+    const int rr = lane >> 2, cq = lane & 3;  // write-out role: row (of 8) and group of CPL columns
     uint32_t tile_iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
       const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
@@ -504,11 +514,12 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           row_tab[lane] = row_ok ? row_off : -1;
         }
 #pragma unroll 1
-        for (int c = half * EPI_CHUNK; c < BLOCK_N; c += 2 * EPI_CHUNK) {
+        for (int c = half * EPI_CHUNK; c < BLOCK_N; c += (EW / 4) * EPI_CHUNK) {
           float v[EPI_CHUNK];
           __syncwarp();  // previous chunk's reads of stg are done; also reconverges for the .aligned tcgen05.ld
           if (t.nsteps > 0) {
-            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);  // may run past BLOCK_N: masked below
+            const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+            if (EPI_CHUNK == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);  // may run past BLOCK_N: masked below
           } else {
 #pragma unroll
             for (int i = 0; i < EPI_CHUNK; ++i) v[i] = 0.f;
@@ -518,49 +529,59 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           for (int i = 0; i < EPI_CHUNK / 4; ++i)
             srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           __syncwarp();
-          const int cl = c + cq * 8;        // first of this lane's eight columns inside the tile
+          const int cl = c + cq * CPL;      // first of this lane's CPL columns inside the tile
           const int n = t.n0 + cl;
           if (cl >= BLOCK_N || n >= P.N) continue;
-          const int n_ok = min(min(BLOCK_N - cl, P.N - n), 8);  // valid columns of this lane
-          const bool full = n_ok == 8;
-          float bv[8];
+          const int n_ok = min(min(BLOCK_N - cl, P.N - n), CPL);  // valid columns of this lane
+          const bool full = n_ok == CPL;
+          float bv[CPL];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = 0.f;
+          for (int i = 0; i < CPL; ++i) bv[i] = 0.f;
           if (P.epi == EPI_BF16 && P.bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) bv[i] = i < n_ok ? __ldg(P.bias + n + i) : 0.f;
+            for (int i = 0; i < CPL; ++i) bv[i] = i < n_ok ? __ldg(P.bias + n + i) : 0.f;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rl = j * 8 + rr;
             const long long off = row_tab[rl];
             if (off < 0) continue;
-            const float4 x0 = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq * 8);
-            const float4 x1 = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq * 8 + 4);
-            float o[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            float o[CPL];
+#pragma unroll
+            for (int g = 0; g < CPL / 4; ++g) {
+              const float4 x = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq * CPL + 4 * g);
+              o[4 * g] = x.x; o[4 * g + 1] = x.y; o[4 * g + 2] = x.z; o[4 * g + 3] = x.w;
+            }
             if (P.epi == EPI_F32) {
               float* dst = reinterpret_cast<float*>(P.out) + off + n;
               if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                reinterpret_cast<float4*>(dst)[0] = x0;
-                reinterpret_cast<float4*>(dst)[1] = x1;
+#pragma unroll
+                for (int g = 0; g < CPL / 4; ++g)
+                  reinterpret_cast<float4*>(dst)[g] = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
               } else {
                 for (int i = 0; i < n_ok; ++i) dst[i] = o[i];
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < CPL; ++i) {
                 o[i] += bv[i];
                 if (P.slope != 1.f) o[i] = o[i] > 0.f ? o[i] : o[i] * P.slope;
               }
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + off + n;
-              const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+              const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & (2 * CPL - 1)) == 0);
+              uint32_t mw[CPL / 2];
               if (P.mask_src) {
                 const __nv_bfloat16* ms = P.mask_src + off + n;
                 if (vec) {
-                  const uint4 m = __ldg(reinterpret_cast<const uint4*>(ms));
-                  const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                  if (CPL == 8) {
+                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(ms));
+                    mw[0] = m.x; mw[1] = m.y; mw[CPL / 2 - 2] = m.z; mw[CPL / 2 - 1] = m.w;
+                  } else {
+                    const uint2 m = __ldg(reinterpret_cast<const uint2*>(ms));
+                    mw[0] = m.x; mw[1] = m.y;
+                  }
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {  // bf16 > 0  <=>  sign bit clear and not zero
+                  for (int i = 0; i < CPL / 2; ++i) {  // bf16 > 0  <=>  sign bit clear and not zero
                     const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
                     o[2 * i] *= (lo != 0u && lo < 0x8000u) ? 1.f : P.mask_slope;
                     o[2 * i + 1] *= (hi != 0u && hi < 0x8000u) ? 1.f : P.mask_slope;
@@ -570,13 +591,16 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 }
               }
               if (vec) {
-                uint32_t pk[4];
+                uint32_t pk[CPL / 2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < CPL / 2; ++i) {
                   __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
                   pk[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (CPL == 8)
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[CPL / 2 - 2], pk[CPL / 2 - 1]);
+                else
+                  *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
               } else {
                 for (int i = 0; i < n_ok; ++i) dst[i] = __float2bfloat16(o[i]);
               }
