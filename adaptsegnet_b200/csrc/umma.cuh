@@ -5,13 +5,15 @@
 //
 // per k-step; A/B stages are filled by TMA (SWIZZLE_128B boxes whose inner extent is 64 bf16 =
 // 128 bytes), consumed by tcgen05.mma issued from one thread, released by tcgen05.commit.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  The kernel is PERSISTENT: one CTA
-// (two for BLOCK_N <= 128) per SM walks the tile list (tile = blockIdx.x + i * gridDim.x); the
-// shared-memory ring (~100-190 KB, 3-5 stages) keeps streaming across tile boundaries and the accumulator is double
-// buffered in TMEM (2 x BLOCK_N columns), so the epilogue of tile i overlaps the MMAs of tile
-// i+1 and the fixed costs (TMEM allocation, barrier init, descriptor prefetch, pipeline fill)
-// are paid once per SM instead of once per tile.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = epilogue (tcgen05.ld ->
+// registers -> shared-memory transpose -> coalesced global stores).  The kernel is PERSISTENT: each CTA walks the
+// tile list (tile = blockIdx.x + i * gridDim.x); the shared-memory ring (3-8 stages) keeps streaming across tile
+// boundaries and the accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of tile
+// i+1 and the fixed costs (TMEM allocation, barrier init, descriptor prefetch, pipeline fill) are paid once per SM
+// instead of once per tile.  Two launch shapes (EpiCfg): one 320-thread CTA per SM with eight epilogue warps, or two
+// 192-thread CTAs per SM with four each; umma.cu picks per (mode, BLOCK_N) from measurements.
+// Optional, both measured and OFF by default (see profiles/README.md): clusters of two CTAs sharing B through TMA
+// multicast (CL = 2, ASN_MULTICAST=1) and 256-row CTA tiles with two accumulators per B stage (MT = 2, ASN_MT2=1).
 //
 // Three operand-fetch programs share the skeleton:
 //   GEMM  : A and B are plain row-major [rows][K] matrices (K-major operands).
