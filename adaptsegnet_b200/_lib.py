@@ -42,7 +42,7 @@ SIGNATURES = {
     "asn_aspp_np": (c_int, [c_int, c_int]),
     "asn_aspp_pack_weights": (c_int, [PP, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "asn_aspp_workspace_bytes": (c_size_t, [c_int] * 6),
-    "asn_aspp_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+    "asn_aspp_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                              C.POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
     "asn_aspp_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, PP, c_void_p, c_int, c_int, c_int, c_int, c_int,
                              C.POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
@@ -57,6 +57,8 @@ SIGNATURES = {
                             c_void_p, c_size_t, c_void_p]),
     "asn_gemm_bf16_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
+    "asn_gemm_bf16_nt_mn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
 }
 
 _lib = None

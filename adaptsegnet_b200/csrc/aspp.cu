@@ -152,20 +152,18 @@ aspp_gather_kernel(const float* __restrict__ Z, const float* __restrict__ bias_s
   }
 }
 
-// dYcol[n*P + q][t*n_cls + c] = dy[n][c][q - shift_t] (0 outside), plus the transposed copy
-// dYcolT[t*n_cls + c][n*P + q].  One CTA per 32 pixels; the [32][NP] tile is staged in shared
-// memory so both outputs are written with coalesced stores.
+// dYcol[n*P + q][t*n_cls + c] = dy[n][c][q - shift_t] (0 outside).  One CTA per 32 pixels; the [32][NP] tile is
+// staged in shared memory so the rows are written with coalesced 16-byte stores.
 __global__ void __launch_bounds__(256)
-aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYcol,
-                   __nv_bfloat16* __restrict__ dYcolT, int N, int H, int W, int n_cls, int NP, int64_t ldt,
-                   AsppTaps taps) {
+aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYcol, int N, int H, int W, int n_cls,
+                   int NP, AsppTaps taps) {
   extern __shared__ __nv_bfloat16 tile[];  // [32][NP]
   const int P = H * W;
   const int groups_per_img = (P + 31) / 32;
   const int n = blockIdx.x / groups_per_img;
   const int q0 = (blockIdx.x % groups_per_img) * 32;
   const int J = taps.n_taps * n_cls;
-  const int ql = threadIdx.x & 31;       // lane = pixel -> coalesced reads of dy rows and writes of dYcolT rows
+  const int ql = threadIdx.x & 31;       // lane = pixel -> coalesced reads of the dy rows
   const int q = q0 + ql;
   const int qh = q / W, qw = q - qh * W;
   const float* dyn = dy + (int64_t)n * n_cls * P;
@@ -179,7 +177,6 @@ aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYc
       const __nv_bfloat16 bv = __float2bfloat16(ok ? __ldg(src + (int64_t)c * P) : 0.f);
       const int j = t * n_cls + c;
       tile[ql * NP + j] = bv;
-      if (q < P) dYcolT[(int64_t)j * ldt + (int64_t)n * P + q] = bv;
     }
   }
   __syncthreads();
@@ -292,20 +289,19 @@ static int make_taps(AsppTaps& t, const int* dil, int n_active, int W) {
 }
 
 struct AsppWs {
-  size_t x_nhwc, z, dycol, dycolt, x_ckp, dwpart, total;
+  size_t x_nhwc, z, dycol, dwpart, total;
   int NP, S;
-  int64_t ldp;
 };
+
+constexpr int ASPP_WGRAD_BN = 192;  // MN-major B tiles are made of 64-column boxes: 4 x 192 >= 688
 
 static AsppWs aspp_ws(int N, int Cin, int H, int W, int n_cls, int n_active) {
   AsppWs w;
   const int64_t P = (int64_t)N * H * W;
   w.NP = (int)round_up((int64_t)9 * n_active * n_cls, 16);
-  w.ldp = round_up(P, 8);
-  // split-K of the wgrad GEMM: aim at two CTAs per SM
-  const int bn = pick_block_n(w.NP);
-  const int tiles = cdiv(Cin, 128) * cdiv(w.NP, bn);
-  int S = (2 * sm_count() + tiles - 1) / tiles;
+  // split-K of the wgrad GEMM: one wave of persistent CTAs
+  const int tiles = cdiv(Cin, 128) * cdiv(w.NP, ASPP_WGRAD_BN);
+  int S = (sm_count() + tiles - 1) / tiles;
   const int k_steps = cdiv(P, 64);
   if (S > k_steps / 4) S = k_steps / 4;
   if (S < 1) S = 1;
@@ -316,11 +312,9 @@ static AsppWs aspp_ws(int N, int Cin, int H, int W, int n_cls, int n_active) {
     off += (bytes + 255) / 256 * 256;
     return o;
   };
-  w.x_nhwc = take((size_t)P * Cin * 2);
+  w.x_nhwc = take((size_t)P * Cin * 2);   // forward only, when the caller does not keep the bf16 copy
   w.z = take((size_t)P * w.NP * 4);
   w.dycol = take((size_t)P * w.NP * 2);
-  w.dycolt = take((size_t)w.NP * w.ldp * 2);
-  w.x_ckp = take((size_t)Cin * w.ldp * 2);
   w.dwpart = take((size_t)w.S * Cin * w.NP * 4);
   w.total = off;
   return w;
@@ -362,9 +356,9 @@ static int aspp_check(int N, int Cin, int H, int W, int n_cls, int n_active, con
   return ASN_OK;
 }
 
-extern "C" int asn_aspp_fwd(const float* x_nchw, int x_channels_last, const void* wp_bf16, const float* bias_sum,
-                            float* y_nchw, int N, int Cin, int H, int W, int n_cls, const int* dil_host, int n_active,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int asn_aspp_fwd(const float* x_nchw, int x_channels_last, void* x_bf16_keep, const void* wp_bf16,
+                            const float* bias_sum, float* y_nchw, int N, int Cin, int H, int W, int n_cls,
+                            const int* dil_host, int n_active, void* workspace, size_t workspace_bytes, void* stream) {
   ASN_CHECK_ARG(x_nchw && wp_bf16 && bias_sum && y_nchw && workspace, "asn_aspp_fwd: null pointer");
   int rc = aspp_check(N, Cin, H, W, n_cls, n_active, dil_host);
   if (rc) return rc;
@@ -375,7 +369,8 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, int x_channels_last, const void
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* base = static_cast<uint8_t*>(workspace);
-  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(base + ws.x_nhwc);
+  __nv_bfloat16* xn = x_bf16_keep ? static_cast<__nv_bfloat16*>(x_bf16_keep)
+                                  : reinterpret_cast<__nv_bfloat16*>(base + ws.x_nhwc);
   float* Z = reinterpret_cast<float*>(base + ws.z);
   const int P = H * W;
   if (x_channels_last) {
@@ -402,13 +397,13 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, int x_channels_last, const void
   return ASN_OK;
 }
 
-extern "C" int asn_aspp_bwd(const float* x_nchw, int x_channels_last, const void* wpt_bf16, const float* dy_nchw,
+extern "C" int asn_aspp_bwd(const void* x_bf16, int dx_channels_last, const void* wpt_bf16, const float* dy_nchw,
                             float* dx_nchw, float* const* dw_oihw, float* db, int N, int Cin, int H, int W, int n_cls,
                             const int* dil_host, int n_active, void* workspace, size_t workspace_bytes,
                             void* stream) {
   ASN_CHECK_ARG(dy_nchw && workspace, "asn_aspp_bwd: null pointer");
   ASN_CHECK_ARG(!dx_nchw || wpt_bf16, "asn_aspp_bwd: dx needs the transposed weight pack");
-  ASN_CHECK_ARG(!dw_oihw || x_nchw, "asn_aspp_bwd: dw needs x");
+  ASN_CHECK_ARG(!dw_oihw || x_bf16, "asn_aspp_bwd: dw needs the bf16 activations kept by the forward");
   int rc = aspp_check(N, Cin, H, W, n_cls, n_active, dil_host);
   if (rc) return rc;
   const AsppWs ws = aspp_ws(N, Cin, H, W, n_cls, n_active);
@@ -419,62 +414,41 @@ extern "C" int asn_aspp_bwd(const float* x_nchw, int x_channels_last, const void
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* base = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* dycol = reinterpret_cast<__nv_bfloat16*>(base + ws.dycol);
-  __nv_bfloat16* dycolt = reinterpret_cast<__nv_bfloat16*>(base + ws.dycolt);
   const int P = H * W;
   AsppTaps taps;
   make_taps(taps, dil_host, n_active, W);
+  const double flops = 2.0 * N * P * (9.0 * n_active * n_cls) * Cin;
   if (dx_nchw || dw_oihw) {
-    // padding columns [N*P, ldp) of dYcolT / Xckp are never read: the tensor maps end at N*P
     const size_t smem = (size_t)32 * ws.NP * 2;
     if (smem > 48 * 1024)
       ASN_CUDA(cudaFuncSetAttribute(aspp_dycols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prof::Scope ps("aspp_dy_cols", 0, 4.0 * N * P * ws.NP + 4.0 * N * P * n_cls, st);
-    aspp_dycols_kernel<<<N * cdiv(P, 32), 256, smem, st>>>(dy_nchw, dycol, dycolt, N, H, W, n_cls, ws.NP, ws.ldp, taps);
+    prof::Scope ps("aspp_dy_cols", 0, 2.0 * N * P * ws.NP + 4.0 * N * P * n_cls, st);
+    aspp_dycols_kernel<<<N * cdiv(P, 32), 256, smem, st>>>(dy_nchw, dycol, N, H, W, n_cls, ws.NP, taps);
     ASN_LAUNCH_CHECK();
   }
-  if (dx_nchw && x_channels_last) {
+  if (dx_nchw && dx_channels_last) {
     // dX[N*P][Cin] = dYcol[N*P][NP] . WpT[Cin][NP]^T : the gradient lands in channels_last, all images at once
     rc = umma::gemm_tn(dycol, wpt_bf16, dx_nchw, N * P, Cin, ws.NP, ws.NP, ws.NP, Cin, 1, 0, 256, st,
-                       "aspp_dgrad_gemm", 2.0 * N * P * (9.0 * n_active * n_cls) * Cin);
+                       "aspp_dgrad_gemm", flops);
     if (rc) return rc;
   } else if (dx_nchw) {
+    // dX^T[Cin][P] = WpT[Cin][NP] . dYcol[P][NP]^T per image: lands directly in NCHW
     for (int n = 0; n < N; ++n) {
       rc = umma::gemm_tn(wpt_bf16, dycol + (int64_t)n * P * ws.NP, dx_nchw + (int64_t)n * Cin * P, Cin, P, ws.NP,
-                         ws.NP, ws.NP, P, 1, 0, 256, st, "aspp_dgrad_gemm",
-                         2.0 * P * (9.0 * n_active * n_cls) * Cin);
+                         ws.NP, ws.NP, P, 1, 0, 256, st, "aspp_dgrad_gemm", flops / N);
       if (rc) return rc;
     }
   }
   if (dw_oihw) {
-    __nv_bfloat16* xk = reinterpret_cast<__nv_bfloat16*>(base + ws.x_ckp);
+    // dWp[Cin][NP] = X[N*P][Cin]^T . dYcol[N*P][NP]: both operands as they are (MN-major), split-K over the pixels
     float* part = reinterpret_cast<float*>(base + ws.dwpart);
-    if (x_channels_last) {
-      prof::Scope ps("aspp_x_to_ckp_bf16", 0, 6.0 * N * P * Cin, st);
-      nhwc_to_ckp_bf16_kernel<<<dim3(cdiv((int64_t)N * P, 64), cdiv(Cin, 64)), 256, 0, st>>>(x_nchw, xk, Cin,
-                                                                                              (int64_t)N * P, ws.ldp);
-      ASN_LAUNCH_CHECK();
-    } else {
-      prof::Scope ps("aspp_x_to_bf16", 0, 6.0 * N * P * Cin, st);
-      // vector path needs 16-byte aligned rows on both sides: P % 4 == 0 (then ld % 8 == 0 keeps the stores aligned)
-      const bool vec = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
-      const int rows = N * Cin;
-      if (vec) {
-        dim3 grid(cdiv(P / 4, 256) < 8 ? cdiv(P / 4, 256) : 8, rows < 32768 ? rows : 32768);
-        nchw_to_ckp_bf16_kernel<4><<<grid, 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
-      } else {
-        dim3 grid(cdiv(P, 256) < 8 ? cdiv(P, 256) : 8, rows < 32768 ? rows : 32768);
-        nchw_to_ckp_bf16_kernel<1><<<grid, 256, 0, st>>>(x_nchw, xk, N, Cin, P, ws.ldp);
-      }
-      ASN_LAUNCH_CHECK();
-    }
-    rc = umma::gemm_tn(xk, dycolt, part, Cin, ws.NP, N * P, (int)ws.ldp, (int)ws.ldp, ws.NP, ws.S,
-                       (long long)Cin * ws.NP, pick_block_n(ws.NP), st, "aspp_wgrad_gemm",
-                       2.0 * N * P * (9.0 * n_active * n_cls) * Cin);
+    rc = umma::gemm_nt_mn(x_bf16, dycol, part, Cin, ws.NP, N * P, Cin, ws.NP, ws.NP, ws.S, (long long)Cin * ws.NP,
+                          ASPP_WGRAD_BN, st, "aspp_wgrad_gemm", flops);
     if (rc) return rc;
     GradPtrs gp{};
     for (int b = 0; b < n_active; ++b) gp.w[b] = dw_oihw[b];
     prof::Scope ps("aspp_unpack_dw", 0, 4.0 * Cin * ws.NP * (ws.S + 1), st);
-    aspp_unpack_dw_kernel<<<wave_grid((int64_t)n_active * n_cls * Cin * 9, 256, 8), 256, 0, st>>>(
+    aspp_unpack_dw_kernel<<<full_grid((int64_t)n_active * n_cls * Cin * 9, 256), 256, 0, st>>>(
         part, ws.S, gp, n_active, n_cls, Cin, ws.NP);
     ASN_LAUNCH_CHECK();
   }

@@ -86,6 +86,7 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
 template <int MODE, int BLOCK_N, int MT>
 struct Shape {
   static constexpr int EW = (MT == 1 && ((MODE == MODE_WGRAD && BLOCK_N <= 128) || (MODE == MODE_CONV && BLOCK_N <= 32))) ? 4 : 8;
+  static_assert(MODE != MODE_GEMM_MN || BLOCK_N % 64 == 0, "MN-major B tiles are made of 64-column boxes");
   static constexpr int ctas_per_sm = EW == 4 ? 2 : 1;
   static constexpr int stage = MT * 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
   static constexpr int fit = ((EW == 4 ? 100 : 184) * 1024) / stage;
@@ -149,6 +150,7 @@ bool block_n_supported(int mode, int block_n) {
     case MODE_GEMM: return block_n == 128 || block_n == 176 || block_n == 256;
     case MODE_CONV: return block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256;
     case MODE_WGRAD: return block_n == 64 || block_n == 128 || block_n == 256;
+    case MODE_GEMM_MN: return block_n == 128 || block_n == 192;
   }
   return false;
 }
@@ -192,6 +194,8 @@ int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, di
   ASN_CASE(MODE_WGRAD, 64, 1, 1)
   ASN_CASE(MODE_WGRAD, 128, 1, 1)
   ASN_CASE(MODE_WGRAD, 256, 1, 1)
+  ASN_CASE(MODE_GEMM_MN, 192, 1, 1)
+  ASN_CASE(MODE_GEMM_MN, 128, 1, 1)
 #undef ASN_CASE
   set_error("umma::launch: no kernel for mode %d block_n %d rows %d", mode, block_n, rows);
   return ASN_EUNSUPPORTED;
@@ -234,6 +238,40 @@ int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda
                 2.0 * M * K + 2.0 * N * K + 4.0 * M * N * split_k, rows);
 }
 
+// C[M,N] (fp32, ldc; split_k partials at split_stride) = A^T . B for A[K][M] (lda), B[K][N] (ldb), bf16, M / N contiguous
+int gemm_nt_mn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, long long ldc,
+               int split_k, long long split_stride, int block_n, cudaStream_t st, const char* prof_name,
+               double prof_flops) {
+  ASN_CHECK_ARG(A && B && C, "gemm_nt_mn: null pointer");
+  ASN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_nt_mn: bad shape %d %d %d", M, N, K);
+  ASN_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= M && ldb >= N, "gemm_nt_mn: lda/ldb must be >= M/N and multiples of 8");
+  ASN_CHECK_ARG(block_n_supported(MODE_GEMM_MN, block_n), "gemm_nt_mn: unsupported block_n %d", block_n);
+  CUtensorMap maps[5];
+  int rc = encode_2d(&maps[0], A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64);
+  if (rc) return rc;
+  rc = encode_2d(&maps[4], B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64);
+  if (rc) return rc;
+  maps[1] = maps[2] = maps[3] = maps[0];
+  Params P;
+  memset(&P, 0, sizeof(P));
+  P.M = M;
+  P.N = N;
+  P.k_steps = cdiv(K, BLOCK_K);
+  if (split_k < 1) split_k = 1;
+  if (split_k > P.k_steps) split_k = P.k_steps;
+  P.steps_per_split = cdiv(P.k_steps, split_k);
+  split_k = cdiv(P.k_steps, P.steps_per_split);
+  P.a_boxes = M <= 64 ? 1 : 2;
+  P.epi = EPI_F32;
+  P.out = C;
+  P.ld_out = ldc;
+  P.z_stride_out = split_stride;
+  P.slope = 1.f;
+  dim3 grid(cdiv(M, BLOCK_M), cdiv(N, block_n), split_k);
+  return launch(MODE_GEMM_MN, block_n, maps, P, grid, st, prof_name, prof_flops >= 0 ? prof_flops : 2.0 * M * N * K,
+                2.0 * M * K + 2.0 * N * K + 4.0 * M * N * split_k);
+}
+
 int effective_split(int K, int split_k) {
   int k_steps = cdiv(K, BLOCK_K);
   if (split_k < 1) split_k = 1;
@@ -244,6 +282,13 @@ int effective_split(int K, int split_k) {
 
 }  // namespace umma
 }  // namespace asn
+
+extern "C" int asn_gemm_bf16_nt_mn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb,
+                                   int ldc, int split_k, void* stream) {
+  using namespace asn;
+  return umma::gemm_nt_mn(A, B, C, M, N, K, lda, ldb, ldc, split_k, (long long)M * ldc, N > 128 ? 192 : 128,
+                          static_cast<cudaStream_t>(stream), "gemm_nt_mn", -1.0);
+}
 
 extern "C" int asn_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb,
                                 int ldc, int split_k, void* stream) {

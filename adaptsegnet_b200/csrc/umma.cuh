@@ -23,6 +23,8 @@
 //           TMA, which is the convolution's zero padding.  B = packed weights (K-major).
 //   WGRAD : the reduction runs over pixels, so both operands arrive "MN-major": each stage
 //           holds 64 pixels x {128 | BLOCK_N} channels as 64-channel TMA boxes.
+//   GEMM_MN: the same operand fetch over plain 2-D [K][M] / [K][N] matrices (head weight gradient:
+//           X^T . dYcol straight from the NHWC activations, no transposed copies).
 #pragma once
 #include <cuda.h>
 
@@ -194,7 +196,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // ------------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------------
-enum { MODE_GEMM = 0, MODE_CONV = 1, MODE_WGRAD = 2 };
+enum {
+  MODE_GEMM = 0,     // C = A[M][K] . B[N][K]^T, both K-contiguous
+  MODE_CONV = 1,
+  MODE_WGRAD = 2,
+  MODE_GEMM_MN = 3   // C = A^T . B for A[K][M], B[K][N] (M / N contiguous): 2-D flavour of the WGRAD operand fetch
+};
 enum {
   EPI_F32 = 0,   // fp32 store
   EPI_BF16 = 1   // (+bias) (LeakyReLU) (x LeakyReLU mask of `mask_src`) -> bf16 store
@@ -291,7 +298,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int 
   t.m0 = t.img = t.oh0 = t.ow0 = t.wg_tap = 0;
   t.ks_begin = 0;
   int ks_end = P.k_steps;
-  if (MODE == MODE_GEMM) {
+  if (MODE == MODE_GEMM || MODE == MODE_GEMM_MN) {
     t.m0 = bx * (BLOCK_M * MT);
     t.n0 = by * BLOCK_N;
     t.ks_begin = t.z * P.steps_per_split;
@@ -325,7 +332,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   static_assert(EW == 8 || 2 * TmemCols<BLOCK_N, MT>::value <= 512, "two CTAs per SM need <= 256 TMEM columns each");
   constexpr int TMEM_COLS = TmemCols<BLOCK_N, MT>::value;
   constexpr int NACC = TmemCols<BLOCK_N, MT>::nacc;
-  static_assert(MT == 1 || MODE != MODE_WGRAD, "WGRAD tiles are 128 channels tall");
+  static_assert(MT == 1 || (MODE != MODE_WGRAD && MODE != MODE_GEMM_MN), "MN-major tiles are 128 rows tall");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
@@ -406,6 +413,15 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             else
               tma_load_2d_mcast(&map_b, sb + rank * (L::B_BYTES / CL), full_bar(s), ks * BLOCK_K,
                                 t.z * P.b_rows_per_z + t.n0 + rank * (BLOCK_N / CL), CL_MASK);
+          } else if (MODE == MODE_GEMM_MN) {
+            // k-step = 64 rows of K: A = columns [m0, m0+128) of A[K][M], B = columns [n0, n0+BLOCK_N) of B[K][N]
+            const uint32_t box_bytes = 64 * 64 * 2;
+            mbar_arrive_expect_tx(full_bar(s), (P.a_boxes + BLOCK_N / 64) * box_bytes);
+            for (int a = 0; a < P.a_boxes; ++a)
+              tma_load_2d(&map_a0, sa + a * box_bytes, full_bar(s), t.m0 + a * 64, ks * BLOCK_K);
+#pragma unroll
+            for (int b = 0; b < BLOCK_N / 64; ++b)
+              tma_load_2d(&map_b, sb + b * box_bytes, full_bar(s), t.n0 + b * 64, ks * BLOCK_K);
           } else {
             // k-step = one box of 64 pixels: A = dY channels [m0, m0+128), B = X@tap channels [n0, n0+BLOCK_N)
             const int bx = ks % P.tiles_w, by = (ks / P.tiles_w) % P.tiles_h, im = ks / (P.tiles_w * P.tiles_h);
@@ -426,8 +442,8 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc = MODE == MODE_WGRAD ? make_idesc(BLOCK_M, BLOCK_N, 1, 1)
-                                                    : make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+      constexpr bool MN_MAJOR = MODE == MODE_WGRAD || MODE == MODE_GEMM_MN;
+      constexpr uint32_t idesc = MN_MAJOR ? make_idesc(BLOCK_M, BLOCK_N, 1, 1) : make_idesc(BLOCK_M, BLOCK_N, 0, 0);
       uint32_t it = 0, tile_iter = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
         const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
@@ -446,7 +462,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             uint64_t da, db;
-            if (MODE == MODE_WGRAD) {
+            if (MN_MAJOR) {
               // MN-major, SW128: 64-channel chunks LBO = 64 px * 128 B apart, 8-pixel groups SBO = 1 KB apart;
               // advancing K by 16 pixels = 2 KB
               da = make_smem_desc(sa + k * 2048, 8192, 1024);
@@ -498,7 +514,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           const int r = sub * BLOCK_M + q * 32 + lane;
           bool row_ok;
           long long row_off;
-          if (MODE == MODE_GEMM) {
+          if (MODE == MODE_GEMM || MODE == MODE_GEMM_MN) {
             row_ok = t.valid && (t.m0 + r) < P.M;
             row_off = (long long)t.z * P.z_stride_out + (long long)(t.m0 + r) * P.ld_out;
           } else if (MODE == MODE_CONV) {

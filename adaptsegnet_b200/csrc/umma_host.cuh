@@ -35,6 +35,10 @@ namespace umma {
 int gemm_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, long long ldc,
             int split_k, long long split_stride, int block_n, cudaStream_t st, const char* prof_name = "gemm_bf16_tn",
             double prof_flops = -1.0);
+// C[M,N] (fp32, ldc) = A^T . B for bf16 A[K][M], B[K][N] (M / N contiguous): MN-major operands, no transposed copies
+int gemm_nt_mn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, long long ldc,
+               int split_k, long long split_stride, int block_n, cudaStream_t st,
+               const char* prof_name = "gemm_bf16_nt_mn", double prof_flops = -1.0);
 // number of z-slices gemm_tn actually launches for a requested split
 int effective_split(int K, int split_k);
 }  // namespace umma

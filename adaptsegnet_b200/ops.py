@@ -319,6 +319,21 @@ def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, split_k: int = 1) -> torch.Te
     return c
 
 
+def gemm_bf16_nt_mn(a: torch.Tensor, b: torch.Tensor, split_k: int = 1) -> torch.Tensor:
+    """C[M,N] fp32 = A[K,M]^T @ B[K,N] for bf16 row-major A, B (reduction index = row; M, N % 8 == 0)."""
+    a = _req(a, torch.bfloat16, "A")
+    b = _req(b, torch.bfloat16, "B")
+    K, M = a.shape
+    K2, Nn = b.shape
+    assert K == K2
+    lib = _lib.load()
+    c = torch.zeros((max(split_k, 1), M, Nn), dtype=torch.float32, device=a.device)
+    check(lib.asn_gemm_bf16_nt_mn(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K, M, Nn, Nn, split_k, _stream()),
+          "asn_gemm_bf16_nt_mn")
+    _count()
+    return c
+
+
 # --------------------------------------------------------------------------------------
 # K1 ASPP classifier head
 # --------------------------------------------------------------------------------------
@@ -370,33 +385,41 @@ class _AsppHeadTC(torch.autograd.Function):
         nbytes = lib.asn_aspp_workspace_bytes(N, cin, H, W, n_cls, n_active)
         ws = _ws(nbytes, x.device)
         y = torch.empty((N, n_cls, H, W), dtype=torch.float32, device=x.device)
-        check(lib.asn_aspp_fwd(x.data_ptr(), int(cl), wp.data_ptr(), bias_sum.data_ptr(), y.data_ptr(), N, cin, H, W, n_cls,
+        need_w = any(ctx.needs_input_grad[4:4 + nb])
+        # the NHWC bf16 copy the forward makes anyway is all the backward needs of x (weight gradient)
+        x_bf16 = torch.empty((N * H * W, cin), dtype=torch.bfloat16, device=x.device) if need_w else None
+        check(lib.asn_aspp_fwd(x.data_ptr(), int(cl), x_bf16.data_ptr() if need_w else None, wp.data_ptr(),
+                               bias_sum.data_ptr(), y.data_ptr(), N, cin, H, W, n_cls,
                                _lib.int_array(dils), n_active, ws.data_ptr(), nbytes, _stream()), "asn_aspp_fwd")
         _count(3)
-        ctx.save_for_backward(x, wpt)
-        ctx.cfg = (tuple(dils), n_active, nb, n_cls, tuple(w.shape for w in weights), cl)
+        ctx.save_for_backward(x_bf16 if need_w else torch.empty(0, device=x.device), wpt)
+        ctx.cfg = (tuple(dils), n_active, nb, n_cls, tuple(w.shape for w in weights), cl, (N, cin, H, W))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, wpt = ctx.saved_tensors
-        dils, n_active, nb, n_cls, wshapes, cl = ctx.cfg
+        x_bf16, wpt = ctx.saved_tensors
+        dils, n_active, nb, n_cls, wshapes, cl, (N, cin, H, W) = ctx.cfg
         dy = _req(dy, torch.float32, "dy")
-        N, cin, H, W = x.shape
+        dev = dy.device
         lib = _lib.load()
         need_x = ctx.needs_input_grad[0]
         need_w = any(ctx.needs_input_grad[4:4 + nb])
         need_b = any(ctx.needs_input_grad[4 + nb:])
         nbytes = lib.asn_aspp_workspace_bytes(N, cin, H, W, n_cls, n_active)
-        ws = _ws(nbytes, x.device)
-        dx = torch.empty_like(x) if need_x else None  # keeps x's memory format (NCHW or channels_last)
-        dws = [torch.empty(wshapes[i], dtype=torch.float32, device=x.device) for i in range(n_active)] if need_w else None
-        db = torch.empty((n_cls,), dtype=torch.float32, device=x.device) if need_b else None
-        check(lib.asn_aspp_bwd(x.data_ptr(), int(cl), wpt.data_ptr(), dy.data_ptr(), dx.data_ptr() if need_x else None,
+        ws = _ws(nbytes, dev)
+        dx = None
+        if need_x:  # same memory format as the x that came in (NCHW or channels_last)
+            dx = torch.empty((N, cin, H, W), dtype=torch.float32, device=dev,
+                             memory_format=torch.channels_last if cl else torch.contiguous_format)
+        dws = [torch.empty(wshapes[i], dtype=torch.float32, device=dev) for i in range(n_active)] if need_w else None
+        db = torch.empty((n_cls,), dtype=torch.float32, device=dev) if need_b else None
+        check(lib.asn_aspp_bwd(x_bf16.data_ptr() if need_w else None, int(cl), wpt.data_ptr(), dy.data_ptr(),
+                               dx.data_ptr() if need_x else None,
                                _lib.ptr_array([t.data_ptr() for t in dws]) if need_w else None,
                                db.data_ptr() if need_b else None, N, cin, H, W, n_cls, _lib.int_array(dils),
                                n_active, ws.data_ptr(), nbytes, _stream()), "asn_aspp_bwd")
-        _count(1 + (N if need_x else 0) + (3 if need_w else 0) + (1 if need_b else 0))
+        _count(1 + ((1 if cl else N) if need_x else 0) + (2 if need_w else 0) + (1 if need_b else 0))
         gw = [(dws[i] if (need_w and i < n_active) else None) for i in range(nb)]
         # inactive branches (early-return variants) receive no gradient
         gb = [(db if (need_b and i < n_active) else None) for i in range(nb)]

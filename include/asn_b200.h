@@ -160,7 +160,7 @@ ASN_API int asn_lrelu_bwd_f32(const float* dy, const float* post, float* dx, int
  *     fwd  : Z[px, NP]   = Xnhwc[px, Cin] . Wp[NP, Cin]^T      (dense GEMM, no im2col of X)
  *            y[c, p]     = bias_sum[c] + sum_t Z[p + shift_t, t*n_cls + c]   (gather-sum)
  *     dgrad: dX[Cin, px] = WpT[Cin, NP] . dYcol[px, NP]^T ,  dYcol[q, t*n_cls+c] = dy[c, q - shift_t]
- *     wgrad: dWp[Cin,NP] = Xnchw[Cin, px] . dYcolT[NP, px]^T   (split-K over pixels)
+ *     wgrad: dWp[Cin,NP] = Xnhwc[px, Cin]^T . dYcol[px, NP]     (MN-major operands, split-K over pixels)
  *   asn_aspp_pack_weights builds Wp (bf16 [NP][Cin]) and WpT (bf16 [Cin][NP]) from the four
  *   fp32 OIHW weights; call it after every optimizer step.
  * ---------------------------------------------------------------------------------- */
@@ -170,13 +170,15 @@ ASN_API int asn_aspp_pack_weights(const float* const* w_oihw /* host array of n_
                           void* stream);
 ASN_API size_t asn_aspp_workspace_bytes(int N, int Cin, int H, int W, int n_cls, int n_active);
 /* x_channels_last != 0: x (and dx) are (N,Cin,H,W) tensors stored channels_last (NHWC in memory), as a
- * channels_last trunk hands them over; y / dy stay NCHW. */
-ASN_API int asn_aspp_fwd(const float* x_nchw, int x_channels_last, const void* wp_bf16, const float* bias_sum, float* y_nchw,
+ * channels_last trunk hands them over; y / dy stay NCHW.
+ * x_bf16_keep (nullable): caller-owned N*H*W*Cin bf16 buffer that receives the NHWC bf16 copy of x the forward
+ * makes anyway; asn_aspp_bwd takes it as `x_bf16` for the weight gradient (no second pass over the fp32 x). */
+ASN_API int asn_aspp_fwd(const float* x_nchw, int x_channels_last, void* x_bf16_keep, const void* wp_bf16, const float* bias_sum, float* y_nchw,
                  int N, int Cin, int H, int W, int n_cls, const int* dil_host, int n_active,
                  void* workspace, size_t workspace_bytes, void* stream);
 /* any of dx / dw / db may be NULL (skipped).  dw: host array of n_active device ptrs (OIHW fp32,
  * overwritten); db: device [n_cls] = sum over pixels of dy (identical for every active branch). */
-ASN_API int asn_aspp_bwd(const float* x_nchw, int x_channels_last, const void* wpt_bf16, const float* dy_nchw, float* dx_nchw,
+ASN_API int asn_aspp_bwd(const void* x_bf16, int dx_channels_last, const void* wpt_bf16, const float* dy_nchw, float* dx_nchw,
                  float* const* dw_oihw, float* db, int N, int Cin, int H, int W, int n_cls,
                  const int* dil_host, int n_active, void* workspace, size_t workspace_bytes,
                  void* stream);
@@ -219,6 +221,11 @@ ASN_API int asn_fcd_bwd(const float* dout, const float* x_logits, const void* wp
  * ---------------------------------------------------------------------------------- */
 ASN_API int asn_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb,
                      int ldc, int split_k, void* stream);
+/* same result from "MN-major" operands: C[M,N] = A[K,M]^T . B[K,N], A and B bf16 row major with the
+ * reduction dimension as the ROW index (M / N contiguous) - the weight-gradient form X^T . dY read
+ * straight from NHWC tensors.  lda/ldb multiples of 8. */
+ASN_API int asn_gemm_bf16_nt_mn(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb,
+                        int ldc, int split_k, void* stream);
 
 #ifdef __cplusplus
 }
