@@ -262,7 +262,10 @@ int channel_sum_nchw(const float* src, float* out, int N, int O, int P, cudaStre
 
 // ---- host orchestration --------------------------------------------------------------------
 
-static int pick_block_n(int n) {
+// BLOCK_N of the forward GEMM: least padding of N (176 for the 688 packed taps), except that with CTA pairs the
+// 256-wide MMA is ~20 % cheaper per MAC than the 176-wide one (tools/gemm_probe.py) and wins, in spite of padding
+// 688 -> 768, once there are at least two full rounds of 256 x 256 pair tiles.
+static int pick_block_n(int n, int64_t rows) {
   const int cand[3] = {128, 176, 256};
   int best = 256;
   int64_t best_pad = -1;
@@ -272,6 +275,10 @@ static int pick_block_n(int n) {
       best = cand[i];
       best_pad = pad;
     }
+  }
+  if (umma::cluster_size(umma::MODE_GEMM, 256) == 2) {
+    const int64_t pair_tiles = cdiv(cdiv(rows, (int64_t)128), (int64_t)2) * cdiv(n, 256);
+    if (pair_tiles >= sm_count()) best = 256;
   }
   return best;
 }
@@ -385,7 +392,7 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, int x_channels_last, void* x_bf
     ASN_LAUNCH_CHECK();
   }
   // algorithmic flops: 2 * px * (9*n_active*n_cls) * Cin  (N padding not counted)
-  rc = umma::gemm_tn(xn, wp_bf16, Z, N * P, ws.NP, Cin, Cin, Cin, ws.NP, 1, 0, pick_block_n(ws.NP), st,
+  rc = umma::gemm_tn(xn, wp_bf16, Z, N * P, ws.NP, Cin, Cin, Cin, ws.NP, 1, 0, pick_block_n(ws.NP, (int64_t)N * P), st,
                      "aspp_fwd_gemm", 2.0 * N * P * (9.0 * n_active * n_cls) * Cin);
   if (rc) return rc;
   AsppTaps taps;

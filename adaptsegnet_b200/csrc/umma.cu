@@ -83,37 +83,54 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
 // Launch shape per (mode, BLOCK_N): EW = 8 -> one persistent CTA per SM, ring of <= 184 KB; EW = 4 -> two CTAs per SM,
 // ring of <= 100 KB each (umma.cuh, EpiCfg).  Measured on B200: the weight-gradient tiles (long K over pixels, N <= 128)
 // and the 32-column dgrad of conv1 run faster as two pipelines per SM, everything else with the eight-warp epilogue.
-template <int MODE, int BLOCK_N, int MT>
+template <int MODE, int BLOCK_N, int MT, int CL = 1>
 struct Shape {
-  static constexpr int EW = (MT == 1 && ((MODE == MODE_WGRAD && BLOCK_N <= 128) || (MODE == MODE_CONV && BLOCK_N <= 32))) ? 4 : 8;
+  static constexpr int EW =
+      (MT == 1 && CL == 1 && ((MODE == MODE_WGRAD && BLOCK_N <= 128) || (MODE == MODE_CONV && BLOCK_N <= 32))) ? 4 : 8;
   static_assert(MODE != MODE_GEMM_MN || BLOCK_N % 64 == 0, "MN-major B tiles are made of 64-column boxes");
   static constexpr int ctas_per_sm = EW == 4 ? 2 : 1;
-  static constexpr int stage = MT * 16384 + ((BLOCK_N * 128 + 1023) / 1024) * 1024;
+  static constexpr int stage = MT * 16384 + (((BLOCK_N / CL) * 128 + 1023) / 1024) * 1024;
   static constexpr int fit = ((EW == 4 ? 100 : 184) * 1024) / stage;
   static constexpr int stages = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
 
-// cluster size the launcher uses for (mode, block_n): 2 = pairs of x-neighbouring tiles share the B tile through
-// TMA multicast (each CTA fetches half of it) -- callers must encode the B tensor map with box rows block_n / 2.
-// OFF by default: measured on B200 (profiles/README.md) it changes nothing -- the kernels are bound by the bytes
-// delivered INTO the SMs' shared memory (~6.3 KB/clk chip-wide), and a multicast byte still lands in both SMs.
-// ASN_MULTICAST=1 turns it on (parity-tested: tests pass in both settings).
+// cluster size the launcher uses for (mode, block_n): 2 = CTA pairs (tcgen05 cta_group::2) over x-neighbouring
+// tiles -- callers must encode the B tensor map with box rows block_n / 2 (each CTA of the pair fetches half of the B
+// tile).  ASN_PAIR=0 falls back to single-CTA tiles everywhere (A/B measurements; parity tests pass in both settings).
 int cluster_size(int mode, int block_n) {
-  static const bool on = getenv("ASN_MULTICAST") != nullptr && getenv("ASN_MULTICAST")[0] == '1';
-  if (!on) return 1;
+  static const bool off = getenv("ASN_PAIR") != nullptr && getenv("ASN_PAIR")[0] == '0';
+  if (off) return 1;
   return (mode == MODE_GEMM || mode == MODE_CONV) && block_n >= 128 ? 2 : 1;
 }
 
 template <int MODE, int BLOCK_N, int CL, int MT>
 static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st, const char* name,
                     double flops, double bytes) {
-  using Sh = Shape<MODE, BLOCK_N, MT>;
+  using Sh = Shape<MODE, BLOCK_N, MT, CL>;
   constexpr int STAGES = Sh::stages, EW = Sh::EW, NUM_THREADS = EpiCfg<EW>::threads;
-  using L = SmemLayout<BLOCK_N, STAGES, MT, EW>;
+  using L = SmemLayout<BLOCK_N, STAGES, MT, EW, CL>;
   auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL, MT, EW>;
   static bool configured = false;
+  static int max_clusters = 0;  // CL = 2: CTA pairs the device can keep resident at once (one per TPC)
   if (!configured) {
     ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    if (CL > 1) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(sm_count() / CL * CL);
+      q.blockDim = dim3(NUM_THREADS);
+      q.dynamicSmemBytes = L::TOTAL;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        max_clusters = sm_count() / CL;
+      }
+    }
     configured = true;
   }
   Params Pp = P;
@@ -121,7 +138,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
   Pp.grid_y = (int)grid.y;
   Pp.grid_z = (int)grid.z;
   const long long tiles = (long long)((grid.x + CL - 1) / CL) * grid.y * grid.z;  // (pairs of) tiles
-  const long long slots = (long long)sm_count() * Sh::ctas_per_sm / CL;
+  const long long slots = CL == 1 ? (long long)sm_count() * Sh::ctas_per_sm : (long long)max_clusters;
   const int ctas = (int)(tiles < slots ? tiles : slots) * CL;
   prof::Scope ps(name, flops, bytes, st);
   if (CL == 1) {
@@ -294,6 +311,7 @@ extern "C" int asn_gemm_bf16_tn(const void* A, const void* B, float* C, int M, i
                                 int ldc, int split_k, void* stream) {
   using namespace asn;
   int bn = N > 128 ? 256 : 128;
+  if (const char* e = getenv("ASN_GEMM_BN")) bn = atoi(e);  // probing only (tools/gemm_probe.py)
   return umma::gemm_tn(A, B, C, M, N, K, lda, ldb, ldc, split_k, (long long)M * ldc, bn,
                        static_cast<cudaStream_t>(stream));
 }

@@ -12,8 +12,11 @@
 // i+1 and the fixed costs (TMEM allocation, barrier init, descriptor prefetch, pipeline fill) are paid once per SM
 // instead of once per tile.  Two launch shapes (EpiCfg): one 320-thread CTA per SM with eight epilogue warps, or two
 // 192-thread CTAs per SM with four each; umma.cu picks per (mode, BLOCK_N) from measurements.
-// Optional, both measured and OFF by default (see profiles/README.md): clusters of two CTAs sharing B through TMA
-// multicast (CL = 2, ASN_MULTICAST=1) and 256-row CTA tiles with two accumulators per B stage (MT = 2, ASN_MT2=1).
+// CL = 2 runs the tile on a CTA PAIR (tcgen05 cta_group::2): the two CTAs of a cluster sit on the two SMs of a TPC, each
+// loads its own 128 rows of A and HALF of the B tile, and one thread of the leader CTA issues 256 x BLOCK_N MMAs that
+// read both shared memories and write both TMEMs -- per output element only (256 + BLOCK_N) / (2 * (128 + BLOCK_N)) of
+// the operand bytes enter the SMs, which is what bounds these kernels (profiles/README.md).
+// Optional and OFF by default: 256-row CTA tiles with two accumulators per B stage (MT = 2, ASN_MT2=1).
 //
 // Three operand-fetch programs share the skeleton:
 //   GEMM  : A and B are plain row-major [rows][K] matrices (K-major operands).
@@ -84,15 +87,31 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t dst, 
       : "memory");
 }
 
-// same 2-D box, delivered to the same shared-memory offset of every CTA in `mask` (and completing on the
-// mbarrier at the same offset in each of them)
-__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1,
-                                                  uint16_t mask) {
+// cta_group::2 flavours: the box lands in THIS CTA's shared memory, the bytes are counted on an mbarrier that may live
+// in the peer CTA (`bar` is a shared::cluster address, see mapa_rank)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -104,15 +123,29 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// CG = 2: executed by the same warp of BOTH CTAs of the pair; allocates the same columns in both TMEMs
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_holder, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_holder), "r"(ncols)
-               : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_holder), "r"(ncols)
+                 : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_holder), "r"(ncols)
+                 : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,14 +162,26 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// pair MMA: D (rows 0..127 in this CTA's TMEM, 128..255 in the peer's) (+)= A (128 rows from each CTA's shared
+// memory) . B (BLOCK_N / 2 rows from each); descriptors are shared-memory OFFSETS valid in both CTAs
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // all previously issued tcgen05 ops of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-
-// same, arriving on the mbarrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void mma_commit_mcast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+// pair flavour: arrives on the mbarrier at this offset in every CTA of `mask` once the pair MMAs have completed
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(mask)
                : "memory");
 }
@@ -268,10 +313,10 @@ struct EpiCfg {
   static constexpr int threads = 64 + 32 * EW;      // TMA producer warp + MMA warp + epilogue warps
 };
 
-template <int BLOCK_N, int STAGES, int MT = 1, int EW = 8>
+template <int BLOCK_N, int STAGES, int MT = 1, int EW = 8, int CL = 1>
 struct SmemLayout {
   static constexpr int A_BYTES = MT * BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / CL) * BLOCK_K * 2;  // a pair keeps half of the B tile in each CTA
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int STG_OFFSET = BAR_OFFSET + 256;                     // barriers take <= 21 x 8 B
@@ -284,9 +329,9 @@ struct TileCoord {
   bool valid;
 };
 
-// CL = 1: tile -> (bx, by, bz).  CL = 2 (cluster of two CTAs sharing B by multicast): `tile` indexes PAIRS of
-// x-neighbours, this CTA takes bx = 2 * pair + rank; a pair hanging over the end of an odd grid_x still runs its
-// main loop (the multicast must stay in lock-step) on out-of-range coordinates -- TMA zero-fills, `valid` masks.
+// CL = 1: tile -> (bx, by, bz).  CL = 2 (CTA pair): `tile` indexes PAIRS of x-neighbours, this CTA takes
+// bx = 2 * pair + rank; the second CTA of a pair hanging over the end of an odd grid_x still feeds the pair MMA,
+// from out-of-range coordinates -- TMA zero-fills, `valid` masks its stores.
 template <int MODE, int BLOCK_N, int CL, int MT>
 __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int rank) {
   TileCoord t;
@@ -326,13 +371,15 @@ __global__ void __launch_bounds__(EpiCfg<EW>::threads, (EW == 4 ? 2 : 1))
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
-  using L = SmemLayout<BLOCK_N, STAGES, MT, EW>;
+  using L = SmemLayout<BLOCK_N, STAGES, MT, EW, CL>;
   constexpr int EPI_CHUNK = EpiCfg<EW>::chunk, EPI_PITCH = EpiCfg<EW>::pitch;
   constexpr int CPL = EPI_CHUNK / 4;  // columns per lane on the way out (8 or 4)
   static_assert(EW == 8 || 2 * TmemCols<BLOCK_N, MT>::value <= 512, "two CTAs per SM need <= 256 TMEM columns each");
   constexpr int TMEM_COLS = TmemCols<BLOCK_N, MT>::value;
   constexpr int NACC = TmemCols<BLOCK_N, MT>::nacc;
   static_assert(MT == 1 || (MODE != MODE_WGRAD && MODE != MODE_GEMM_MN), "MN-major tiles are 128 rows tall");
+  static_assert(CL == 1 || (MT == 1 && EW == 8 && BLOCK_N % 16 == 0 && (MODE == MODE_GEMM || MODE == MODE_CONV)),
+                "pair mode: K-major modes, one CTA per SM, 256 x BLOCK_N MMAs (BLOCK_N a multiple of 16)");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
@@ -351,6 +398,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int tile_stride = CL == 1 ? (int)gridDim.x : (int)gridDim.x / CL;
   const int total_tiles = (CL == 1 ? P.grid_x : (P.grid_x + 1) / 2) * P.grid_y * P.grid_z;
   constexpr uint16_t CL_MASK = (1u << CL) - 1;
+  const bool leader = rank == 0;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -362,21 +410,21 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       prefetch_tmap(&map_a3);
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);  // a stage is free when every CTA that receives the multicast has consumed it
+      mbar_init(full_bar(s), 1);   // pair: only the leader's is used; it counts the bytes of both CTAs
+      mbar_init(empty_bar(s), 1);  // pair: the leader's commit arrives on both CTAs' copies
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 32 * EW);  // every epilogue thread arrives
+      mbar_init(tmem_empty_bar(a), CL * EW);  // one arrival per epilogue warp (of both CTAs, on the leader's copy)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc<CL>(tmem_holder, TMEM_COLS);
+    tmem_relinquish<CL>();
   }
   tc_fence_before();
-  if (CL == 1) __syncthreads(); else cluster_sync_all();  // peers' barriers must exist before the first multicast
+  if (CL == 1) __syncthreads(); else cluster_sync_all();  // the peer's barriers must exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder_ptr;
 
@@ -394,25 +442,34 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
-          if (MODE == MODE_GEMM) {
+          if (CL == 2) {
+            // pair: both CTAs load their own A rows and their half of the B rows into their own shared memory; all
+            // bytes are counted on the LEADER's barrier, which the leader arms for the two CTAs together (a peer box
+            // landing before the leader has armed the phase only drives the byte count negative for a moment)
+            const uint32_t lbar = mapa_rank(full_bar(s), 0);
+            if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * (L::A_BYTES + L::B_BYTES));
+            const int nb = t.n0 + rank * (BLOCK_N / 2);
+            if (MODE == MODE_GEMM) {
+              tma_load_2d_pair(&map_a0, sa, lbar, ks * BLOCK_K, t.m0);
+              tma_load_2d_pair(&map_b, sb, lbar, ks * BLOCK_K, nb);
+            } else {
+              const int tap = ks / P.c_chunks, cc = ks - tap * P.c_chunks;
+              const int e = t.z * P.taps + tap;
+              tma_load_4d_pair(amaps[P.tap_map[e]], sa, lbar, cc * BLOCK_K, t.ow0 + P.tap_dw[e], t.oh0 + P.tap_dh[e],
+                               t.img);
+              tma_load_2d_pair(&map_b, sb, lbar, ks * BLOCK_K, t.z * P.b_rows_per_z + nb);
+            }
+          } else if (MODE == MODE_GEMM) {
             mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
             tma_load_2d(&map_a0, sa, full_bar(s), ks * BLOCK_K, t.m0);
-            if (CL == 1)
-              tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.n0);
-            else  // this CTA fetches its half of the B tile for the whole cluster
-              tma_load_2d_mcast(&map_b, sb + rank * (L::B_BYTES / CL), full_bar(s), ks * BLOCK_K,
-                                t.n0 + rank * (BLOCK_N / CL), CL_MASK);
+            tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.n0);
           } else if (MODE == MODE_CONV) {
             const int tap = ks / P.c_chunks, cc = ks - tap * P.c_chunks;
             const int e = t.z * P.taps + tap;
             mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + L::B_BYTES);
             tma_load_4d(amaps[P.tap_map[e]], sa, full_bar(s), cc * BLOCK_K, t.ow0 + P.tap_dw[e],
                         t.oh0 + P.tap_dh[e], t.img);
-            if (CL == 1)
-              tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.z * P.b_rows_per_z + t.n0);
-            else
-              tma_load_2d_mcast(&map_b, sb + rank * (L::B_BYTES / CL), full_bar(s), ks * BLOCK_K,
-                                t.z * P.b_rows_per_z + t.n0 + rank * (BLOCK_N / CL), CL_MASK);
+            tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.z * P.b_rows_per_z + t.n0);
           } else if (MODE == MODE_GEMM_MN) {
             // k-step = 64 rows of K: A = columns [m0, m0+128) of A[K][M], B = columns [n0, n0+BLOCK_N) of B[K][N]
             const uint32_t box_bytes = 64 * 64 * 2;
@@ -441,9 +498,9 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    if (lane == 0 && leader) {  // pair: one thread of the leader CTA drives the tensor cores of both SMs
       constexpr bool MN_MAJOR = MODE == MODE_WGRAD || MODE == MODE_GEMM_MN;
-      constexpr uint32_t idesc = MN_MAJOR ? make_idesc(BLOCK_M, BLOCK_N, 1, 1) : make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = MN_MAJOR ? make_idesc(BLOCK_M, BLOCK_N, 1, 1) : make_idesc(CL * BLOCK_M, BLOCK_N, 0, 0);
       uint32_t it = 0, tile_iter = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
         const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
@@ -472,16 +529,18 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               da = make_smem_desc(sa + k * 32, 16, 1024);
               db = make_smem_desc(sb + k * 32, 16, 1024);
             }
-            mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (CL == 2) mma_f16_ss_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
             if (MT == 2) {  // rows 128..255 of the tile: next 16 KB of the A stage, same B
               const uint64_t da1 = make_smem_desc(sa + BLOCK_M * BLOCK_K * 2 + k * 32, 16, 1024);
               mma_f16_ss(tmem_d + BLOCK_N, da1, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
             }
           }
-          // frees the stage (here and, under multicast, in the peer) once these MMAs have read it
-          if (CL == 1) mma_commit(empty_bar(s)); else mma_commit_mcast(empty_bar(s), CL_MASK);
+          // frees the stage (in both CTAs of a pair) once these MMAs have read it
+          if (CL == 1) mma_commit(empty_bar(s)); else mma_commit_pair(empty_bar(s), CL_MASK);
         }
-        mma_commit(tmem_full_bar(acc));  // accumulator of this tile complete
+        // accumulator of this tile complete (pair: both halves, each CTA's epilogue waits on its own copy)
+        if (CL == 1) mma_commit(tmem_full_bar(acc)); else mma_commit_pair(tmem_full_bar(acc), CL_MASK);
       }
     }
   } else {
@@ -627,18 +686,20 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
       }  // sub
       // this thread's TMEM reads of the tile are complete (tcgen05.wait::ld in tmem_ld32): release the buffer
-      __syncwarp();
       tc_fence_before();
-      mbar_arrive(tmem_empty_bar(acc));
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(tmem_empty_bar(acc)); else mbar_arrive_cluster(mapa_rank(tmem_empty_bar(acc), 0));
+      }
     }
   }
 
-  // ---- teardown (a CTA may not exit while its peer can still multicast into it or signal its barriers) ----
+  // ---- teardown (a CTA may not exit while its peer can still read its shared memory or signal its barriers) ----
   tc_fence_before();
   if (CL == 1) __syncthreads(); else cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc<CL>(tmem_base, TMEM_COLS);
   }
 }
 

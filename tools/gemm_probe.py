@@ -6,18 +6,20 @@ import torch
 from adaptsegnet_b200 import ops, prof
 
 res = {}
-for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 4096), (14400, 688, 2048), (2048, 14400, 688), (8192, 256, 8192), (8192, 128, 8192)]:
+shapes = [(4096, 4096, 4096), (8192, 8192, 4096), (14400, 688, 2048), (14400, 688, 1024), (8192, 688, 2048), (8192, 688, 1024),
+          (2048, 14400, 688), (1024, 8192, 688), (8192, 256, 8192), (8192, 128, 8192)]
+for (M, N, K) in shapes:
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     ops.gemm_bf16_tn(a, b)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10):
+    for _ in range(20):
         ops.gemm_bf16_tn(a, b)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    ms = e0.elapsed_time(e1) / 20
     ref = None
     e0.record()
     for _ in range(10):
