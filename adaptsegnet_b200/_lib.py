@@ -55,6 +55,15 @@ SIGNATURES = {
                             c_void_p, c_size_t, c_void_p]),
     "asn_fcd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PP, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_size_t, c_void_p]),
+    "asn_upsample_ce_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "asn_upsample_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "asn_upsample_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "asn_fcd_workspace_bytes_lowres": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "asn_fcd_fwd_lowres": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_size_t, c_void_p]),
+    "asn_fcd_bwd_lowres": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, PP, c_int, c_int,
+                                   c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "asn_gemm_bf16_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "asn_gemm_bf16_nt_mn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

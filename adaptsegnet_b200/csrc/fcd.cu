@@ -12,6 +12,7 @@
 //                     dPre_l; epilogue multiplies by the LeakyReLU mask of A_{l-1}
 //   wgrad    conv l : MODE_WGRAD (pixels are the reduction), one CTA column per tap, split-K
 //   classifier (512 -> 1) and its gradients: CUDA-core reductions (GEMV-shaped).
+#include "lazy_up.cuh"
 #include "umma_host.cuh"
 
 namespace asn {
@@ -861,10 +862,14 @@ extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, 
   return ASN_OK;
 }
 
-extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpack, void* acts, float* out, int N,
-                           int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
+// x_h x x_w = resolution of x: equal to H x W (x is what the reference hands to the discriminator), or lower -- then x
+// holds low-res LOGITS and bilinear upsample + softmax happen inside the input pack (lazy_up.cu).
+static int fcd_fwd_impl(const float* x_nchw, int x_is_logits, int x_h, int x_w, const void* wpack, void* acts,
+                        float* out, int N, int n_cls, int ndf, int H, int W, void* stream) {
   ASN_CHECK_ARG(x_nchw && wpack && acts && out, "asn_fcd_fwd: null pointer");
+  const bool lowres = x_h != H || x_w != W;
+  ASN_CHECK_ARG(!lowres || (x_is_logits && lazy::supported(n_cls, x_h, x_w, H, W)),
+                "asn_fcd_fwd_lowres: needs logits of %d classes at a resolution <= %dx%d (got %dx%d)", 19, H, W, x_h, x_w);
   FcdPlan p;
   int rc = make_plan(p, N, n_cls, ndf, H, W);
   if (rc) return rc;
@@ -873,7 +878,9 @@ extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpa
   uint8_t* ab = static_cast<uint8_t*>(acts);
   __nv_bfloat16* A[5];
   for (int l = 0; l <= 4; ++l) A[l] = reinterpret_cast<__nv_bfloat16*>(ab + p.act_off[l]);
-  {
+  if (lowres) {
+    if ((rc = lazy::pack_input(x_nchw, A[0], N, n_cls, x_h, x_w, H, W, p.W0p, st))) return rc;
+  } else {
     prof::Scope ps("fcd_pack_input", 0, (double)N * H * W * (4.0 * n_cls + 64.0), st);
     // (4 pixels per thread measured slower on B200: 178 registers halve the occupancy)
     if (false && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0)
@@ -898,15 +905,38 @@ extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpa
   return ASN_OK;
 }
 
-extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void* wpack, const void* acts,
-                           float* dx_nchw, float* const* dparams_host, int N, int n_cls, int ndf, int H, int W,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpack, void* acts, float* out, int N,
+                           int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  return fcd_fwd_impl(x_nchw, x_is_logits, H, W, wpack, acts, out, N, n_cls, ndf, H, W, stream);
+}
+
+extern "C" int asn_fcd_fwd_lowres(const float* z_low, int x_h, int x_w, const void* wpack, void* acts, float* out,
+                                  int N, int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  return fcd_fwd_impl(z_low, 1, x_h, x_w, wpack, acts, out, N, n_cls, ndf, H, W, stream);
+}
+
+extern "C" size_t asn_fcd_workspace_bytes_lowres(int N, int n_cls, int ndf, int H, int W, int x_h, int x_w) {
+  FcdPlan p;
+  if (make_plan(p, N, n_cls, ndf, H, W) || !lazy::supported(n_cls, x_h, x_w, H, W)) return 0;
+  return p.ws_total + lazy::partial_bytes(N, n_cls, x_h, x_w, H, W);
+}
+
+static int fcd_bwd_impl(const float* dout, const float* x_logits, int x_h, int x_w, const void* wpack,
+                        const void* acts, float* dx_nchw, float* const* dparams_host, int N, int n_cls, int ndf, int H,
+                        int W, void* workspace, size_t workspace_bytes, void* stream) {
   ASN_CHECK_ARG(dout && wpack && acts && workspace, "asn_fcd_bwd: null pointer");
+  const bool lowres = x_h != H || x_w != W;
+  ASN_CHECK_ARG(!lowres || !dx_nchw || (x_logits && lazy::supported(n_cls, x_h, x_w, H, W)),
+                "asn_fcd_bwd_lowres: needs the low-res logits the forward saw");
   FcdPlan p;
   int rc = make_plan(p, N, n_cls, ndf, H, W);
   if (rc) return rc;
-  if (workspace_bytes < p.ws_total) {
-    set_error("asn_fcd_bwd: workspace %zu < %zu", workspace_bytes, p.ws_total);
+  const size_t need = p.ws_total + (lowres && dx_nchw ? lazy::partial_bytes(N, n_cls, x_h, x_w, H, W) : 0);
+  if (workspace_bytes < need) {
+    set_error("asn_fcd_bwd: workspace %zu < %zu", workspace_bytes, need);
     return ASN_EWORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -962,7 +992,11 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
     }
   }
   if (dparams_host && (rc = reduce_all(p, R, st))) return rc;
-  if (dx_nchw) {
+  if (dx_nchw && lowres) {
+    rc = lazy::unpack_dx(dA0, x_logits, dx_nchw, N, n_cls, x_h, x_w, H, W, p.W0p, ws + p.ws_total,
+                         workspace_bytes - p.ws_total, st);
+    if (rc) return rc;
+  } else if (dx_nchw) {
     prof::Scope ps("fcd_unpack_dx", 0, (double)N * H * W * (64.0 + 4.0 * n_cls * (x_logits ? 2 : 1)), st);
     // (2 pixels per thread measured slower on B200: 211 registers)
     if (false && W % 2 == 0 && ((reinterpret_cast<uintptr_t>(dx_nchw) | reinterpret_cast<uintptr_t>(x_logits)) & 7) == 0)
@@ -974,4 +1008,18 @@ extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void*
     ASN_LAUNCH_CHECK();
   }
   return ASN_OK;
+}
+
+extern "C" int asn_fcd_bwd(const float* dout, const float* x_logits, const void* wpack, const void* acts,
+                           float* dx_nchw, float* const* dparams_host, int N, int n_cls, int ndf, int H, int W,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return fcd_bwd_impl(dout, x_logits, H, W, wpack, acts, dx_nchw, dparams_host, N, n_cls, ndf, H, W, workspace,
+                      workspace_bytes, stream);
+}
+
+extern "C" int asn_fcd_bwd_lowres(const float* dout, const float* z_low, int x_h, int x_w, const void* wpack,
+                                  const void* acts, float* dz_low, float* const* dparams_host, int N, int n_cls,
+                                  int ndf, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  return fcd_bwd_impl(dout, z_low, x_h, x_w, wpack, acts, dz_low, dparams_host, N, n_cls, ndf, H, W, workspace,
+                      workspace_bytes, stream);
 }

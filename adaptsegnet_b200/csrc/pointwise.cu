@@ -4,25 +4,11 @@
 // request is a fully coalesced 512-byte segment; the C values per pixel stay in registers
 // (C = 19 is specialised; other class counts take a three-pass generic kernel).
 #include "common.cuh"
+#include "ce_common.cuh"
 
 namespace asn {
 
 constexpr int PW_THREADS = 128;
-
-struct CeStats {
-  double loss_sum;
-  double weight_sum;
-  long long n_valid;
-  long long n_bad;
-};
-
-// label classification shared by fwd and bwd:  1 = contributes, 0 = ignored, -1 = out of bounds
-__device__ __forceinline__ int classify_label(long long y, int C, int ignore, int mask_negative) {
-  if (y == (long long)ignore) return 0;
-  if (mask_negative && y < 0) return 0;
-  if (y < 0 || y >= C) return -1;
-  return 1;
-}
 
 template <int VEC>
 struct PixVec;

@@ -28,11 +28,14 @@ class FCDiscriminator(nn.Module):
             out += [conv.weight, conv.bias]
         return out
 
-    def forward(self, x, from_logits=False, return_saved=False):
+    def forward(self, x, from_logits=False, return_saved=False, up_size=None):
         """x: (N, num_classes, H, W) fp32 -> (N, 1, H/32, W/32) logits.  ``from_logits=True`` fuses the
         channel softmax the training script applies before calling D (train...:617-618).
+        ``up_size=(H, W)`` (with ``from_logits``): x are the low-res logits of the segmentation heads and the
+        bilinear upsample to the input resolution is fused in as well (nothing full-res is materialised).
         ``return_saved=True`` also returns a handle for :meth:`replay`."""
-        return ops.fcd_forward(x, self._params(), self._pack, x_is_logits=from_logits, return_saved=return_saved)
+        return ops.fcd_forward(x, self._params(), self._pack, x_is_logits=from_logits, return_saved=return_saved,
+                               up_size=up_size)
 
     def replay(self, saved):
         """D(x) for the same x and the same (unchanged) weights as the forward that produced ``saved``:

@@ -181,6 +181,62 @@ def softmax_cross_entropy(z, y, ignore_label=255, mask_negative=False, weight=No
     return (loss, stats) if return_stats else loss
 
 
+class _UpsampleCE(torch.autograd.Function):
+    """asn_upsample_ce_fwd_bwd: loss and d loss / d z_low in one pass; backward only scales the saved gradient."""
+
+    @staticmethod
+    def forward(ctx, z_low, size, y, ignore_label, mask_negative, weight, size_average):
+        z_low = _req(z_low, torch.float32, "predict")
+        y = _req(y, torch.int64, "target")
+        N, Cc, h, w = z_low.shape
+        H, W = size
+        lib = _lib.load()
+        stats = torch.empty(4, dtype=torch.int64, device=z_low.device)
+        loss = torch.empty((), dtype=torch.float32, device=z_low.device)
+        dz = torch.empty_like(z_low)
+        nbytes = lib.asn_upsample_ce_workspace_bytes(N, Cc, h, w, H, W)
+        ws = _ws(nbytes, z_low.device)
+        wptr = _req(weight, torch.float32, "weight").data_ptr() if weight is not None else None
+        check(lib.asn_upsample_ce_fwd_bwd(z_low.data_ptr(), y.data_ptr(), N, Cc, h, w, H, W, ignore_label,
+                                          int(mask_negative), wptr, int(size_average), stats.data_ptr(), loss.data_ptr(),
+                                          dz.data_ptr(), ws.data_ptr(), nbytes, _stream()), "asn_upsample_ce_fwd_bwd")
+        _count(2)
+        ctx.save_for_backward(dz)
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, gloss, _gstats):
+        (dz,) = ctx.saved_tensors
+        return dz * gloss.to(torch.float32), None, None, None, None, None, None
+
+
+def upsample_ce_supported(z_low, size) -> bool:
+    N, Cc, h, w = z_low.shape
+    return precision_ok_for_lazy() and bool(_lib.load().asn_upsample_ce_supported(Cc, h, w, int(size[0]), int(size[1])))
+
+
+def precision_ok_for_lazy() -> bool:
+    return True  # the lazy kernels are fp32 CUDA-core code: valid in both precision modes
+
+
+def upsample_softmax_cross_entropy(z_low, size, y, ignore_label=255, mask_negative=False, weight=None,
+                                   size_average=True, return_stats=False):
+    """CrossEntropyLoss(ignore_index)(interp(z_low), y) without materialising interp(z_low) (Tier-B):
+    model/deeplab_multi.py:188-189 + train_gta2cityscapes_multi.py:599-600 in one kernel, forward and backward.
+    Falls back to the two unfused kernels for shapes the fused kernel does not cover."""
+    size = (int(size[0]), int(size[1]))
+    if tuple(y.shape[-2:]) != size:
+        raise ValueError(f"target {tuple(y.shape)} does not match the upsampled size {size}")
+    if not upsample_ce_supported(z_low, size):
+        return softmax_cross_entropy(upsample_bilinear(z_low, size), y, ignore_label, mask_negative, weight,
+                                     size_average, return_stats)
+    loss, stats = _UpsampleCE.apply(z_low, size, y, int(ignore_label), bool(mask_negative), weight, bool(size_average))
+    if os.environ.get("ASN_STRICT_LABELS") == "1" and int(stats[3].item()) != 0:
+        raise IndexError("Target out of bounds")
+    return (loss, stats) if return_stats else loss
+
+
 # --------------------------------------------------------------------------------------
 # K4 softmax over channels
 # --------------------------------------------------------------------------------------
@@ -503,9 +559,10 @@ class _FcdTC(torch.autograd.Function):
     """tcgen05 path: asn_fcd_fwd / asn_fcd_bwd.  params = (conv1.w, conv1.b, ..., classifier.w, classifier.b)"""
 
     @staticmethod
-    def forward(ctx, x, pack, x_is_logits, *params):
+    def forward(ctx, x, pack, x_is_logits, up_size, *params):
         x = _req(x, torch.float32, "x")
-        N, n_cls, H, W = x.shape
+        N, n_cls, xh, xw = x.shape
+        H, W = up_size if up_size is not None else (xh, xw)   # what the discriminator sees
         ndf = params[0].shape[0]
         lib = _lib.load()
         wpack = pack.get(params, n_cls, ndf)
@@ -516,31 +573,44 @@ class _FcdTC(torch.autograd.Function):
         for _ in range(5):
             oh, ow = (oh + 2 - 4) // 2 + 1, (ow + 2 - 4) // 2 + 1
         out = torch.empty((N, 1, oh, ow), dtype=torch.float32, device=x.device)
-        check(lib.asn_fcd_fwd(x.data_ptr(), int(x_is_logits), wpack.data_ptr(), acts.data_ptr(), out.data_ptr(), N,
-                              n_cls, ndf, H, W, None, 0, _stream()), "asn_fcd_fwd")
+        if (xh, xw) != (H, W):  # Tier-B: upsample + softmax inside the input pack
+            if not x_is_logits:
+                raise _lib.AsnError("a low-res discriminator input must be logits (from_logits=True)")
+            check(lib.asn_fcd_fwd_lowres(x.data_ptr(), xh, xw, wpack.data_ptr(), acts.data_ptr(), out.data_ptr(), N,
+                                         n_cls, ndf, H, W, None, 0, _stream()), "asn_fcd_fwd_lowres")
+        else:
+            check(lib.asn_fcd_fwd(x.data_ptr(), int(x_is_logits), wpack.data_ptr(), acts.data_ptr(), out.data_ptr(),
+                                  N, n_cls, ndf, H, W, None, 0, _stream()), "asn_fcd_fwd")
         _count(6)
         ctx.save_for_backward(x if x_is_logits else torch.empty(0, device=x.device), wpack, acts)
-        ctx.cfg = (N, n_cls, ndf, H, W, bool(x_is_logits), tuple(p.shape for p in params))
+        ctx.cfg = (N, n_cls, ndf, H, W, bool(x_is_logits), tuple(p.shape for p in params), (xh, xw))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, wpack, acts = ctx.saved_tensors
-        N, n_cls, ndf, H, W, x_is_logits, pshapes = ctx.cfg
+        N, n_cls, ndf, H, W, x_is_logits, pshapes, (xh, xw) = ctx.cfg
         dout = _req(dout, torch.float32, "dout")
         lib = _lib.load()
         need_x = ctx.needs_input_grad[0]
-        need_p = any(ctx.needs_input_grad[3:])
-        nbytes = lib.asn_fcd_workspace_bytes(N, n_cls, ndf, H, W)
+        need_p = any(ctx.needs_input_grad[4:])
+        lowres = (xh, xw) != (H, W)
+        nbytes = (lib.asn_fcd_workspace_bytes_lowres(N, n_cls, ndf, H, W, xh, xw) if lowres
+                  else lib.asn_fcd_workspace_bytes(N, n_cls, ndf, H, W))
         ws = _ws(nbytes, dout.device)
-        dx = torch.empty((N, n_cls, H, W), dtype=torch.float32, device=dout.device) if need_x else None
+        dx = torch.empty((N, n_cls, xh, xw), dtype=torch.float32, device=dout.device) if need_x else None
         dps = [torch.empty(s, dtype=torch.float32, device=dout.device) for s in pshapes] if need_p else None
-        check(lib.asn_fcd_bwd(dout.data_ptr(), x.data_ptr() if x_is_logits else None, wpack.data_ptr(),
-                              acts.data_ptr(), dx.data_ptr() if need_x else None,
-                              _lib.ptr_array([t.data_ptr() for t in dps]) if need_p else None, N, n_cls, ndf, H, W,
-                              ws.data_ptr(), nbytes, _stream()), "asn_fcd_bwd")
-        _count(1 + (3 if need_p else 0) + 4 * (4 if need_p else 0) + 4 + (1 if need_x else 0))
-        return (dx, None, None, *(dps if need_p else [None] * len(pshapes)))
+        pp = _lib.ptr_array([t.data_ptr() for t in dps]) if need_p else None
+        if lowres:
+            check(lib.asn_fcd_bwd_lowres(dout.data_ptr(), x.data_ptr(), xh, xw, wpack.data_ptr(), acts.data_ptr(),
+                                         dx.data_ptr() if need_x else None, pp, N, n_cls, ndf, H, W, ws.data_ptr(),
+                                         nbytes, _stream()), "asn_fcd_bwd_lowres")
+        else:
+            check(lib.asn_fcd_bwd(dout.data_ptr(), x.data_ptr() if x_is_logits else None, wpack.data_ptr(),
+                                  acts.data_ptr(), dx.data_ptr() if need_x else None, pp, N, n_cls, ndf, H, W,
+                                  ws.data_ptr(), nbytes, _stream()), "asn_fcd_bwd")
+        _count(1 + (3 if need_p else 0) + 4 * (4 if need_p else 0) + 4 + ((2 if lowres else 1) if need_x else 0))
+        return (dx, None, None, None, *(dps if need_p else [None] * len(pshapes)))
 
 
 class FcdSaved:
@@ -565,7 +635,7 @@ class _FcdReplay(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         sv = ctx.saved
-        N, n_cls, ndf, H, W, x_is_logits, _ = sv.cfg
+        N, n_cls, ndf, H, W = sv.cfg[:5]
         dout = _req(dout, torch.float32, "dout")
         lib = _lib.load()
         nbytes = lib.asn_fcd_workspace_bytes(N, n_cls, ndf, H, W)
@@ -642,18 +712,30 @@ def fcd_saved_activations(out: torch.Tensor):
     return res
 
 
-def fcd_forward(x, params, pack: FcdWeightPack | None = None, x_is_logits: bool = False, return_saved: bool = False):
+def fcd_forward(x, params, pack: FcdWeightPack | None = None, x_is_logits: bool = False, return_saved: bool = False,
+                up_size=None):
     """FCDiscriminator.forward (model/discriminator.py:21-34).  With x_is_logits the channel softmax
     F.softmax(x) of train_gta2cityscapes_multi.py:617-618 is fused into the input pack (bf16 path).
+    up_size=(H, W): x holds LOW-RES logits and the discriminator sees softmax(interp(x, (H, W))) -- the bilinear
+    upsample of model/deeplab_multi.py:188-189 happens inside the input pack too (Tier-B; needs x_is_logits).
     return_saved: also return an FcdSaved handle for fcd_replay (tensor-core path; None in fp32 mode)."""
     params = tuple(params)
+    if up_size is not None:
+        up_size = (int(up_size[0]), int(up_size[1]))
+        if up_size == tuple(x.shape[-2:]):
+            up_size = None
+    lazy_ok = up_size is not None and x_is_logits and precision_mode() != "fp32" and \
+        bool(_lib.load().asn_upsample_ce_supported(x.shape[1], x.shape[2], x.shape[3], up_size[0], up_size[1]))
+    if up_size is not None and not lazy_ok:
+        x = upsample_bilinear(x, up_size)
+        up_size = None
     if precision_mode() == "fp32":
         if x_is_logits:
             x = softmax_channels(x)
         out = _FcdF32.apply(x, *params)
         return (out, None) if return_saved else out
     pack = pack if pack is not None else FcdWeightPack()
-    out = _FcdTC.apply(x, pack, bool(x_is_logits), *params)
+    out = _FcdTC.apply(x, pack, bool(x_is_logits), up_size, *params)
     if not return_saved:
         return out
     fn = out.grad_fn

@@ -41,6 +41,10 @@ class TrainConfig:
     level: str = "multi-level"  # or "single-level"
     fuse_softmax: bool = True   # D(softmax(pred)) with the softmax fused into D's input pack
     reuse_target_forward: bool = True  # D-step on the target reuses the G-step's D(softmax(pred_target)) activations
+    # Tier-B: the heads' low-res logits go straight into the fused upsample+softmax+CE kernel and into
+    # the discriminators' input pack (upsample + softmax inside); no full-resolution logits / probabilities exist.
+    # Same mathematics as the reference's interp -> loss / interp -> softmax -> D chains.  Needs fuse_softmax.
+    lazy_upsample: bool = False
 
 
 def lr_poly(base_lr, it, max_iter, power):
@@ -127,9 +131,9 @@ class AdaptSegTrainer:
             if opt is not None:
                 opt.param_groups[0]["lr"] = lr_d
 
-    def _d_out(self, D, pred):
+    def _d_out(self, D, pred, up_size=None):
         if self.cfg.fuse_softmax:
-            return D(pred, from_logits=True)
+            return D(pred, from_logits=True, up_size=up_size)
         return D(ops.softmax_channels(pred))
 
     @staticmethod
@@ -159,10 +163,22 @@ class AdaptSegTrainer:
         if self.channels_last:
             src_images = src_images.contiguous(memory_format=torch.channels_last)
             tgt_images = tgt_images.contiguous(memory_format=torch.channels_last)
-        pred1, pred2 = self.model(src_images)
-        loss_seg2 = self.seg_loss(pred2, src_labels)
+        lazy = cfg.lazy_upsample and cfg.fuse_softmax
+        up_s = tuple(src_images.shape[-2:]) if lazy else None   # where the consumers upsample to (Tier-B)
+        up_t = tuple(tgt_images.shape[-2:]) if lazy else None
+        if lazy:
+            pred1, pred2 = self.model.low_res_logits(src_images)
+
+            def seg(z):
+                return ops.upsample_softmax_cross_entropy(z, up_s, src_labels, ignore_label=255)
+        else:
+            pred1, pred2 = self.model(src_images)
+
+            def seg(z):
+                return self.seg_loss(z, src_labels)
+        loss_seg2 = seg(pred2)
         if self.multi:
-            loss_seg1 = self.seg_loss(pred1, src_labels)
+            loss_seg1 = seg(pred1)
             loss = loss_seg2 + cfg.lambda_seg * loss_seg1
             out["loss_seg1"] = loss_seg1.detach() / it
         else:
@@ -170,15 +186,15 @@ class AdaptSegTrainer:
         (loss / it).backward()
         out["loss_seg2"] = loss_seg2.detach() / it
 
-        pred_target1, pred_target2 = self.model(tgt_images)
+        pred_target1, pred_target2 = self.model.low_res_logits(tgt_images) if lazy else self.model(tgt_images)
         reuse = cfg.reuse_target_forward and cfg.fuse_softmax and ops.precision_mode() == "bf16"
         saved = {}
 
         def d_target(D, pred, key):
             if reuse:
-                out, saved[key] = D(pred, from_logits=True, return_saved=True)
+                out, saved[key] = D(pred, from_logits=True, return_saved=True, up_size=up_t)
                 return out
-            return self._d_out(D, pred)
+            return self._d_out(D, pred, up_t)
 
         loss_adv2 = self.bce_loss(d_target(self.model_D2, pred_target2, "D2"), SOURCE_LABEL)
         loss = cfg.lambda_adv_target2 * loss_adv2
@@ -196,11 +212,11 @@ class AdaptSegTrainer:
         if self.multi:
             levels.insert(0, (self.model_D1, pred1, pred_target1, "loss_D1", "D1"))
         for D, p_src, p_tgt, name, key in levels:
-            l_src = self.bce_loss(self._d_out(D, p_src.detach()), SOURCE_LABEL) / it / 2
+            l_src = self.bce_loss(self._d_out(D, p_src.detach(), up_s), SOURCE_LABEL) / it / 2
             l_src.backward()
             # train...:665-666 recomputes D(softmax(pred_target)) with unchanged weights and input; the replay
             # re-attaches the G-step's output (and activations) to D's parameters instead
-            d_tgt = D.replay(saved[key]) if saved.get(key) is not None else self._d_out(D, p_tgt.detach())
+            d_tgt = D.replay(saved[key]) if saved.get(key) is not None else self._d_out(D, p_tgt.detach(), up_t)
             l_tgt = self.bce_loss(d_tgt, TARGET_LABEL) / it / 2
             l_tgt.backward()
             out[name] = l_src.detach() + l_tgt.detach()

@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-kernel-events", action="store_true", help="skip the per-kernel event pass (ncu runs)")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--tier", default="B", choices=["A", "B"],
+                    help="B: low-res logits feed the fused upsample+softmax+CE kernel and the discriminators' input pack "
+                         "(no full-res logits in HBM, SURVEY.md 8d); A: the reference's tensor-by-tensor chain")
     return ap.parse_args()
 
 
@@ -177,6 +180,8 @@ def workload_config(args, world):
                               if args.cuda_graph else "eager"),
                 "trunk": ("ResNet-101 as PyTorch modules on cuDNN (TF32" + (", channels_last" if args.channels_last else "")
                           + "), timed, not rewritten"),
+                "tier": ("B: upsample fused into its consumers (CE loss, discriminator input pack); no full-res logits in HBM"
+                         if args.tier == "B" else "A: interp -> loss / softmax -> D tensor by tensor, as the reference"),
                 "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed"})
     return cfg
 
@@ -202,7 +207,7 @@ def run_b200(args):
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)  # train_gta2cityscapes_multi.py:228
 
     torch.manual_seed(SEED)  # identical replicas
-    trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan), device=dev,
+    trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"), device=dev,
                               use_cuda_graph=bool(args.cuda_graph), channels_last=bool(args.channels_last))
     src_h, lab_h, tgt_h = TR.synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
     src_h, lab_h, tgt_h = src_h.pin_memory(), lab_h.pin_memory(), tgt_h.pin_memory()

@@ -115,6 +115,24 @@ ASN_API int asn_softmax_ce_bwd(const float* z, const int64_t* y, int N, int C, i
                        const void* stats, const float* gscale, float* dz, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K2+K3 fused ("Tier-B"): bilinear upsample (align_corners=True) of LOW-RES logits to
+ * (H,W) -> softmax -> cross entropy with ignore label, forward AND the gradient w.r.t. the low-res
+ * logits in one pass over the labels; the full-resolution logits are never written.
+ *   replaces: interp(x) model/deeplab_multi.py:188-189 followed by CrossEntropyLoss(ignore_index=255)
+ *   train_gta2cityscapes_multi.py:599-600 (or utils/loss.py:7-36) and their autograd.
+ *   stats / loss / flags as asn_softmax_ce_fwd.  dz_low (N,C,h,w) = d loss / d z_low for an upstream
+ *   gradient of 1 (scale it by the upstream scalar).  Deterministic (fixed summation order) except
+ *   for the last bits of the double statistics.  asn_upsample_ce_supported: C == 19, H >= h, W >= w;
+ *   other cases return ASN_EUNSUPPORTED (compose asn_upsample_bilinear_fwd + asn_softmax_ce_*).
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_upsample_ce_supported(int C, int h, int w, int H, int W);
+ASN_API size_t asn_upsample_ce_workspace_bytes(int N, int C, int h, int w, int H, int W);
+ASN_API int asn_upsample_ce_fwd_bwd(const float* z_low, const int64_t* y, int N, int C, int h, int w, int H, int W,
+                            int ignore_label, int mask_negative, const float* class_weight, int size_average,
+                            void* stats, float* loss, float* dz_low, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K4  softmax over dim 1 of (N,C,H,W).  replaces: F.softmax(pred) (implicit dim = 1)
  *   train_gta2cityscapes_multi.py:423,442,454,617-618,645-646,665-666 and its autograd.
  * ---------------------------------------------------------------------------------- */
@@ -212,6 +230,17 @@ ASN_API int asn_fcd_fwd(const float* x_nchw, int x_is_logits, const void* wpack,
 ASN_API int asn_fcd_bwd(const float* dout, const float* x_logits, const void* wpack, const void* acts, float* dx_nchw,
                 float* const* dparams_host, int N, int n_cls, int ndf, int H, int W,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* Tier-B flavour: the discriminator sees softmax(interp(z_low)) at H x W, computed inside the input pack from the
+ * LOW-RES logits z_low (N,n_cls,x_h,x_w) -- replaces interp + F.softmax + D(...) (train...:617-618,645-646,665-666)
+ * without materialising the (N,C,H,W) tensors; bwd returns dz_low (N,n_cls,x_h,x_w).  Same acts / wpack as above;
+ * the workspace additionally holds the partial sums of the transposed interpolation. */
+ASN_API size_t asn_fcd_workspace_bytes_lowres(int N, int n_cls, int ndf, int H, int W, int x_h, int x_w);
+ASN_API int asn_fcd_fwd_lowres(const float* z_low, int x_h, int x_w, const void* wpack, void* acts, float* out,
+                       int N, int n_cls, int ndf, int H, int W, void* workspace, size_t workspace_bytes,
+                       void* stream);
+ASN_API int asn_fcd_bwd_lowres(const float* dout, const float* z_low, int x_h, int x_w, const void* wpack,
+                       const void* acts, float* dz_low, float* const* dparams_host, int N, int n_cls, int ndf,
+                       int H, int W, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * raw tcgen05 GEMM (exposed for tests / benchmarking of the tensor-core core):
