@@ -131,6 +131,8 @@ __device__ __forceinline__ void store_px32(__nv_bfloat16* dst, const float* v) {
   }
 }
 
+constexpr float LOG2E_F = 1.4426950408889634f;  // exp(x - m) = exp2(x * log2e - m * log2e): one FFMA + ex2
+
 template <int PV>
 __global__ void __launch_bounds__(128)
 fcd_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a0, int N, int C, int H, int W,
@@ -170,7 +172,7 @@ fcd_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (c < C) { v[k][c] = expf(v[k][c] - m); s += v[k][c]; }
+          if (c < C) { v[k][c] = exp2f(fmaf(v[k][c], LOG2E_F, -m * LOG2E_F)); s += v[k][c]; }  // as lazy_up.cu
         const float inv = 1.f / s;
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[k][c] *= inv;
@@ -244,7 +246,7 @@ fcd_unpack_dx_kernel(const __nv_bfloat16* __restrict__ da0, const float* __restr
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (c < C) { z[k][c] = expf(z[k][c] - m); s += z[k][c]; }
+          if (c < C) { z[k][c] = exp2f(fmaf(z[k][c], LOG2E_F, -m * LOG2E_F)); s += z[k][c]; }
         const float inv = 1.f / s;
         float dot = 0.f;
 #pragma unroll

@@ -27,7 +27,7 @@ namespace asn {
 namespace lazy {
 
 constexpr int LZ_COLS = 128;   // full-res columns per CTA = threads per CTA
-constexpr int LZ_MAX_SH = 8;   // full-res rows per strip (upper bound)
+constexpr int LZ_MAX_SH = 9;   // full-res rows per strip (upper bound)
 constexpr int LZ_R = 3;        // low-res rows a strip may touch
 
 enum { F_CE = 0, F_PACK = 1, F_DBWD = 2 };
@@ -38,17 +38,32 @@ struct Geom {
   int SH, strips, xblocks, JB;
 };
 
-static Geom make_geom(int N, int h, int w, int H, int W) {
+// `slots` = CTAs of the strip kernel the device keeps resident (0: unknown).  A strip costs about SH + 2.3 row-times
+// (interpolation of the low-res rows and the x-transpose are per strip), the grid runs in ceil(CTAs / slots) rounds:
+// SH is the admissible value with the cheapest total (e.g. 720 x 1280 on 444 slots: 9 rows = 2 rounds, 8 rows = 3).
+static Geom make_geom(int N, int h, int w, int H, int W, int slots = 0) {
   Geom g;
   g.N = N; g.h = h; g.w = w; g.H = H; g.W = W;
   g.sy = lerp_scale(h, H);
   g.sx = lerp_scale(w, W);
   // rows Y0 .. Y0+SH-1 must not span more than two values of floor(sy*Y): sy * (SH - 1) <= 1
   int sh = g.sy > 0.f ? 1 + (int)floorf(1.f / g.sy) : LZ_MAX_SH;
-  g.SH = sh > LZ_MAX_SH ? LZ_MAX_SH : (sh < 1 ? 1 : sh);
-  while (g.SH > 1 && g.sy * (float)(g.SH - 1) > 1.f) --g.SH;
-  g.strips = cdiv(H, g.SH);
+  sh = sh > LZ_MAX_SH ? LZ_MAX_SH : (sh < 1 ? 1 : sh);
+  while (sh > 1 && g.sy * (float)(sh - 1) > 1.f) --sh;
   g.xblocks = cdiv(W, LZ_COLS);
+  g.SH = sh;
+  if (slots > 0) {
+    double best = 0.0;
+    for (int cand = sh; cand >= (sh > 3 ? 3 : 1); --cand) {
+      const long long ctas = (long long)N * cdiv(H, cand) * g.xblocks;
+      const double cost = (double)cdiv(ctas, (long long)slots) * (cand + 2.3);
+      if (cand == sh || cost < best) {
+        best = cost;
+        g.SH = cand;
+      }
+    }
+  }
+  g.strips = cdiv(H, g.SH);
   g.JB = (int)ceilf(g.sx * (float)(LZ_COLS - 1)) + 3;  // low-res columns a block of LZ_COLS columns may touch
   return g;
 }
@@ -57,9 +72,11 @@ bool supported(int C, int h, int w, int H, int W) {
   return C == 19 && h >= 1 && w >= 1 && H >= h && W >= w;
 }
 
+// sized for the smallest strip height make_geom may choose (the choice depends on the device)
 size_t partial_bytes(int N, int C, int h, int w, int H, int W) {
   const Geom g = make_geom(N, h, w, H, W);
-  return (size_t)N * g.strips * g.xblocks * LZ_R * C * g.JB * sizeof(float);
+  const int sh_min = g.SH > 3 ? 3 : 1;
+  return (size_t)N * cdiv(H, sh_min) * g.xblocks * LZ_R * C * g.JB * sizeof(float);
 }
 
 struct Args {
@@ -142,31 +159,32 @@ lazy_strip_kernel(const Args a) {
       v[c] = ly.l0 * sa[c * (LZ_COLS + 1)] + ly.l1 * sb[c * (LZ_COLS + 1)];
       m = fmaxf(m, v[c]);
     }
+    // exp(v - m) as one FFMA + ex2 (2 ulp; the kernels' tolerance is 1e-5 norm-wise)
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float mb = m * LOG2E;
     float s = 0.f;
     if (FUNC == F_CE) {
-      float e[C];  // the logits stay in v: the loss needs z_y
-#pragma unroll
-      for (int c = 0; c < C; ++c) { e[c] = expf(v[c] - m); s += e[c]; }
       const long long lab = col_ok ? __ldg(a.y + ((int64_t)n * g.H + Y) * g.W + X) : (long long)a.ignore;
       const int cls = classify_label(lab, C, a.ignore, a.mask_negative);
-      const int yi = cls == 1 ? (int)lab : -1;
+      const int yi = cls == 1 ? (int)lab : 0;
       const float wgt = cls == 1 ? (a.cw ? __ldg(a.cw + yi) : 1.f) : 0.f;
-      if (cls == 1) {
-        float zy = 0.f;
+      // the logit of the labelled class, re-interpolated with a dynamic class index (shared memory, not registers)
+      const float zy = ly.l0 * sa[yi * (LZ_COLS + 1)] + ly.l1 * sb[yi * (LZ_COLS + 1)];
 #pragma unroll
-        for (int c = 0; c < C; ++c) zy = (c == yi) ? v[c] : zy;
+      for (int c = 0; c < C; ++c) { v[c] = exp2f(fmaf(v[c], LOG2E, -mb)); s += v[c]; }
+      if (cls == 1) {
         loss += (double)(wgt * ((m + logf(s)) - zy));
         wsum += (double)wgt;
         ++nvalid;
       } else if (cls < 0 && col_ok) {
         ++nbad;
       }
-      const float inv = 1.f / s;
+      const float winv = wgt / s;  // 0 for ignored pixels: their gradient vanishes without a branch
 #pragma unroll
-      for (int c = 0; c < C; ++c) v[c] = cls == 1 ? wgt * (e[c] * inv - (c == yi ? 1.f : 0.f)) : 0.f;
+      for (int c = 0; c < C; ++c) v[c] = fmaf(v[c], winv, c == yi ? -wgt : 0.f);
     } else {
 #pragma unroll
-      for (int c = 0; c < C; ++c) { v[c] = expf(v[c] - m); s += v[c]; }
+      for (int c = 0; c < C; ++c) { v[c] = exp2f(fmaf(v[c], LOG2E, -mb)); s += v[c]; }
       const float inv = 1.f / s;
 #pragma unroll
       for (int c = 0; c < C; ++c) v[c] *= inv;  // probabilities
@@ -273,6 +291,22 @@ lazy_strip_kernel(const Args a) {
   }
 }
 
+// resident CTAs of a strip kernel (queried once per kernel)
+template <int C, int FUNC>
+static int strip_slots() {
+  static int slots = 0;
+  if (!slots) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lazy_strip_kernel<C, FUNC>, LZ_COLS, 0) != cudaSuccess ||
+        per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 2;
+    }
+    slots = per_sm * sm_count();
+  }
+  return slots;
+}
+
 // dz_low[n][c][i][j] = scale * sum over the strips / column blocks whose partial block contains node (i, j), in a fixed
 // order.  CE: scale = 1 / weight_sum when size_average (read from the statistics the strip kernel produced), and
 // thread 0 finalises the loss.
@@ -324,7 +358,7 @@ int pack_input(const float* z_low, __nv_bfloat16* a0, int N, int C, int h, int w
   ASN_CHECK_ARG(supported(C, h, w, H, W), "lazy::pack_input: unsupported shape C=%d %dx%d -> %dx%d", C, h, w, H, W);
   Args a;
   memset(&a, 0, sizeof(a));
-  a.g = make_geom(N, h, w, H, W);
+  a.g = make_geom(N, h, w, H, W, strip_slots<19, F_PACK>());
   a.z = z_low;
   a.a0 = a0;
   a.W0p = W0p;
@@ -343,7 +377,7 @@ int unpack_dx(const __nv_bfloat16* da0, const float* z_low, float* dz_low, int N
   }
   Args a;
   memset(&a, 0, sizeof(a));
-  a.g = make_geom(N, h, w, H, W);
+  a.g = make_geom(N, h, w, H, W, strip_slots<19, F_DBWD>());
   a.z = z_low;
   a.a0 = const_cast<__nv_bfloat16*>(da0);
   a.W0p = W0p;
@@ -391,7 +425,7 @@ extern "C" int asn_upsample_ce_fwd_bwd(const float* z_low, const int64_t* y, int
   ASN_CUDA(cudaMemsetAsync(stats, 0, sizeof(CeStats), st));
   lazy::Args a;
   memset(&a, 0, sizeof(a));
-  a.g = lazy::make_geom(N, h, w, H, W);
+  a.g = lazy::make_geom(N, h, w, H, W, lazy::strip_slots<19, lazy::F_CE>());
   a.z = z_low;
   a.y = reinterpret_cast<const long long*>(y);
   a.ignore = ignore_label;
