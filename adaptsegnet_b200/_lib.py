@@ -64,6 +64,10 @@ SIGNATURES = {
                                    c_int, c_void_p, c_size_t, c_void_p]),
     "asn_fcd_bwd_lowres": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, PP, c_int, c_int,
                                    c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "asn_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                             C.POINTER(c_float), c_int, c_float, c_float, c_int, c_void_p]),
+    "asn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                              c_int64, c_void_p]),
     "asn_gemm_bf16_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "asn_gemm_bf16_nt_mn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

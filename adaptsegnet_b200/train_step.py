@@ -90,15 +90,17 @@ class AdaptSegTrainer:
     """Holds G (DeeplabMulti), D1/D2 (FCDiscriminator), their optimizers and runs iterations."""
 
     def __init__(self, cfg: TrainConfig | None = None, device="cuda", model=None, model_D1=None, model_D2=None,
-                 use_cuda_graph=False, channels_last=False):
+                 use_cuda_graph=False, channels_last=False, fused_optimizers=None):
         """``use_cuda_graph``: capture everything of an iteration up to the gradients (both G forwards/backwards,
         all discriminator passes, ~2 300 kernel launches) into one CUDA graph and replay it; the gradient
         all-reduce and the three optimizer steps stay eager.  Same kernels, same order, no per-launch CPU cost."""
         self.cfg = cfg = cfg or TrainConfig()
+        self.device = torch.device(device)
+        # fused optimizer steps on flat parameter buffers (optim.py) wherever the CUDA library runs; torch.optim on CPU
+        self.fused_optimizers = (self.device.type == "cuda") if fused_optimizers is None else bool(fused_optimizers)
         self.use_cuda_graph = bool(use_cuda_graph)
         self.channels_last = bool(channels_last)
         self._graph = None
-        self.device = torch.device(device)
         self.multi = cfg.level == "multi-level"
         self.model = (model or DeeplabMulti(cfg.num_classes)).to(self.device).train()
         if self.channels_last:
@@ -108,17 +110,27 @@ class AdaptSegTrainer:
                 getattr(self.model, name).to(memory_format=torch.channels_last)
         self.model_D2 = (model_D2 or FCDiscriminator(cfg.num_classes)).to(self.device).train()
         self.model_D1 = (model_D1 or FCDiscriminator(cfg.num_classes)).to(self.device).train() if self.multi else None
-        # optimizers exactly as train...:532-540 (the duplicated trunk parameters included, Q11)
-        self.optimizer = torch.optim.SGD(self.model.optim_parameters(cfg), lr=cfg.learning_rate,
-                                         momentum=cfg.momentum, weight_decay=cfg.weight_decay)
-        self.optimizer_D2 = torch.optim.Adam(self.model_D2.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
-        self.optimizer_D1 = (torch.optim.Adam(self.model_D1.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
-                             if self.multi else None)
         self.bce_loss = GANLoss(cfg.gan)
         self.seg_loss = SegCrossEntropy(ignore_index=255)
-        self.flat_G = FlatGrads(self.model.parameters())
-        self.flat_D2 = FlatGrads(self.model_D2.parameters())
-        self.flat_D1 = FlatGrads(self.model_D1.parameters()) if self.multi else None
+        # optimizers exactly as train...:532-540 (the duplicated trunk parameters included, Q11)
+        if self.fused_optimizers:
+            from .optim import FlatParams, FusedAdam, FusedSGD
+            self.flat_G = FlatParams(self.model.parameters())
+            self.flat_D2 = FlatParams(self.model_D2.parameters())
+            self.flat_D1 = FlatParams(self.model_D1.parameters()) if self.multi else None
+            self.optimizer = FusedSGD(self.flat_G, self.model.optim_parameters(cfg), lr=cfg.learning_rate,
+                                      momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+            self.optimizer_D2 = FusedAdam(self.flat_D2, lr=cfg.learning_rate_D, betas=(0.9, 0.99))
+            self.optimizer_D1 = FusedAdam(self.flat_D1, lr=cfg.learning_rate_D, betas=(0.9, 0.99)) if self.multi else None
+        else:
+            self.optimizer = torch.optim.SGD(self.model.optim_parameters(cfg), lr=cfg.learning_rate,
+                                             momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+            self.optimizer_D2 = torch.optim.Adam(self.model_D2.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
+            self.optimizer_D1 = (torch.optim.Adam(self.model_D1.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
+                                 if self.multi else None)
+            self.flat_G = FlatGrads(self.model.parameters())
+            self.flat_D2 = FlatGrads(self.model_D2.parameters())
+            self.flat_D1 = FlatGrads(self.model_D1.parameters()) if self.multi else None
 
     # ---- pieces of the loop ------------------------------------------------------------------
     def _adjust_lr(self, i_iter):

@@ -243,6 +243,27 @@ ASN_API int asn_fcd_bwd_lowres(const float* dout, const float* z_low, int x_h, i
                        int H, int W, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Fused optimizer steps over flat fp32 buffers, one launch each.
+ *   asn_sgd_step: torch.optim.SGD(momentum, weight_decay) train_gta2cityscapes_multi.py:244,347,532,
+ *   stepped at :681.  The flat buffers hold n elements (n % 4 == 0) cut into n_seg segments
+ *   [seg_begin[s], seg_begin[s+1]) (device arrays; begins are multiples of 4); segment s uses the
+ *   learning rate group_lr_host[seg_group[s]] (host array, passed by value) and receives the update
+ *   seg_repeat[s] times in sequence -- the reference's parameter groups name most trunk parameters
+ *   several times (model/deeplab_multi.py:196-218) and a sequential optimizer then
+ *   steps them that often.  first_step != 0: momentum buffers do not exist yet -- every mention
+ *   starts from buf = d_p and the last one is kept (what torch.optim.SGD's sequential path does on
+ *   its first step()); afterwards buf = momentum * buf + d_p per mention.
+ *   asn_adam_step: torch.optim.Adam(lr, betas, eps) train...:351-355,538-540, stepped at :682-683;
+ *   `step` is the 1-based step count (bias corrections).
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n,
+                 const int64_t* seg_begin, const int* seg_group, const int* seg_repeat, int n_seg,
+                 const float* group_lr_host, int n_groups, float momentum, float weight_decay,
+                 int first_step, void* stream);
+ASN_API int asn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * raw tcgen05 GEMM (exposed for tests / benchmarking of the tensor-core core):
  *   C[M,N] (fp32, row major, ldc) = A[M,K] . B[N,K]^T, A and B bf16 row major (K contiguous),
  *   lda/ldb in elements and multiples of 8.  split_k > 1 writes split_k partial matrices
