@@ -279,10 +279,34 @@ struct FcdParamPtrs {
 // forward pack  Wf_l[co][k]:  l >= 2: k = (kh*4+kw)*Cin + ci ; l == 1: k = (kh*2+pw)*64 + kwl*32 + c, kw = 2*pw + kwl
 // dgrad pack    Wd_l[z=(rh,rw)][ci][k], k = (th*2+tw)*Cout + co with kh = kh(rh, th), kw = kw(rw, tw):
 //               rh = 0 -> kh in {1,3}, rh = 1 -> kh in {0,2}
-__global__ void __launch_bounds__(256)
-fcd_pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, __nv_bfloat16* __restrict__ wf,
-                     __nv_bfloat16* __restrict__ wd, float* __restrict__ bias, int l, int Cout, int Cin_real,
-                     int Cin_rows) {
+struct PackArgs {  // blockIdx.y = 0..3: conv1..conv4, 4: classifier -- one launch packs the whole discriminator
+  const float* w[5];
+  const float* b[5];
+  __nv_bfloat16* wf[4];
+  __nv_bfloat16* wd[4];
+  float* bias[4];
+  int Cout[4], Cin_real[4], Cin_rows[4];
+  float* wc;
+  float* bc;
+  int C4;
+};
+
+__global__ void __launch_bounds__(256) fcd_pack_all_kernel(const PackArgs a) {
+  if (blockIdx.y == 4) {  // classifier weights [1][C][4][4] -> fp32 [16][C]
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < 16 * a.C4; i += gridDim.x * 256) {
+      const int t = i / a.C4, c = i % a.C4;
+      a.wc[i] = __ldg(a.w[4] + (int64_t)c * 16 + t);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.bc[0] = __ldg(a.b[4]);
+    return;
+  }
+  const int l = blockIdx.y + 1;
+  const float* __restrict__ w = a.w[blockIdx.y];
+  const float* __restrict__ b = a.b[blockIdx.y];
+  __nv_bfloat16* __restrict__ wf = a.wf[blockIdx.y];
+  __nv_bfloat16* __restrict__ wd = a.wd[blockIdx.y];
+  float* __restrict__ bias = a.bias[blockIdx.y];
+  const int Cout = a.Cout[blockIdx.y], Cin_real = a.Cin_real[blockIdx.y], Cin_rows = a.Cin_rows[blockIdx.y];
   const int Kf = l == 1 ? 512 : 16 * Cin_real;
   const int64_t nf = (int64_t)Cout * Kf;
   const int Kd = 4 * Cout;
@@ -322,17 +346,6 @@ fcd_pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, _
       bias[co] = __ldg(b + co);
     }
   }
-}
-
-// classifier weights [1][C][4][4] -> fp32 [16][C]
-__global__ void __launch_bounds__(256)
-fcd_pack_cls_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wc,
-                    float* __restrict__ bc, int C) {
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < 16 * C; i += gridDim.x * 256) {
-    const int t = i / C, c = i % C;
-    wc[i] = __ldg(w + (int64_t)c * 16 + t);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) bc[0] = __ldg(b);
 }
 
 // ---- classifier (N = 1 output channel): CUDA-core reductions ------------------------------------
@@ -404,29 +417,66 @@ fcd_cls_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w
 }
 
 // dwc[0][c][kh][kw] = sum_{n,oh,ow} dout * A4[n][2oh-1+kh][2ow-1+kw][c].
-// grid (16 taps, C/64, CLS_SLICES): thread = (channel, 1 of 4 pixel phases); coalesced 128-byte reads of A4
-// along the channels, shared-memory reduce over the phases, one fp32 atomic per (channel, tap, slice).
-constexpr int CLS_SLICES = 8;
+// grid (CLS_SLICES, C/64): thread = (channel, 1 of 4 pixel phases).  Every INPUT pixel of the slice is read once
+// (coalesced 128-byte rows along the channels) and feeds the <= 4 taps whose stride-2 footprint contains it -- which
+// taps is a matter of the pixel's row/column parity, uniform over the CTA, so the 16 accumulators stay in registers.
+// Shared-memory reduce over the phases, one fp32 atomic per (channel, tap, slice).
+constexpr int CLS_SLICES = 64;
+
+template <int KH, int KW>
+__device__ __forceinline__ void cls_tap(float (&acc)[16], float v, const float* __restrict__ dout, int n, int ih, int iw,
+                                        int H5, int W5) {
+  // output pixel that sees input (ih, iw) through tap (KH, KW): ih = 2*oh - 1 + KH
+  const int oh2 = ih + 1 - KH, ow2 = iw + 1 - KW;
+  if (oh2 < 0 || ow2 < 0) return;
+  const int oh = oh2 >> 1, ow = ow2 >> 1;
+  if (oh >= H5 || ow >= W5) return;
+  acc[KH * 4 + KW] = fmaf(__ldg(dout + ((int64_t)n * H5 + oh) * W5 + ow), v, acc[KH * 4 + KW]);
+}
+
 __global__ void __launch_bounds__(256)
 fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a4, float* __restrict__ dw,
                      int N, int H4, int W4, int C, int H5, int W5) {
-  __shared__ float red[4][64];
-  const int t = blockIdx.x, kh = t / 4, kw = t % 4;
+  __shared__ float red[4][16][64];
   const int cl = threadIdx.x & 63, ph = threadIdx.x >> 6;
   const int c = blockIdx.y * 64 + cl;
-  const int n_out = N * H5 * W5;
-  float acc = 0.f;
+  const int n_in = N * H4 * W4;
+  float acc[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t] = 0.f;
   if (c < C) {
-    for (int o = blockIdx.z * 4 + ph; o < n_out; o += 4 * CLS_SLICES) {
-      const int ow = o % W5, oh = (o / W5) % H5, n = o / (W5 * H5);
-      const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
-      if ((unsigned)ih < (unsigned)H4 && (unsigned)iw < (unsigned)W4)
-        acc = fmaf(__ldg(dout + o), __bfloat162float(a4[(((int64_t)n * H4 + ih) * W4 + iw) * C + c]), acc);
+    for (int i = blockIdx.x * 4 + ph; i < n_in; i += 4 * CLS_SLICES) {
+      const int iw = i % W4, ih = (i / W4) % H4, n = i / (W4 * H4);
+      const float v = __bfloat162float(a4[(int64_t)i * C + c]);
+      // kh = ih + 1 (mod 2), kw = iw + 1 (mod 2)
+      if (ih & 1) {
+        if (iw & 1) {
+          cls_tap<0, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<0, 2>(acc, v, dout, n, ih, iw, H5, W5);
+          cls_tap<2, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<2, 2>(acc, v, dout, n, ih, iw, H5, W5);
+        } else {
+          cls_tap<0, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<0, 3>(acc, v, dout, n, ih, iw, H5, W5);
+          cls_tap<2, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<2, 3>(acc, v, dout, n, ih, iw, H5, W5);
+        }
+      } else {
+        if (iw & 1) {
+          cls_tap<1, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<1, 2>(acc, v, dout, n, ih, iw, H5, W5);
+          cls_tap<3, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<3, 2>(acc, v, dout, n, ih, iw, H5, W5);
+        } else {
+          cls_tap<1, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<1, 3>(acc, v, dout, n, ih, iw, H5, W5);
+          cls_tap<3, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<3, 3>(acc, v, dout, n, ih, iw, H5, W5);
+        }
+      }
     }
   }
-  red[ph][cl] = acc;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) red[ph][t][cl] = acc[t];
   __syncthreads();
-  if (ph == 0 && c < C) atomicAdd(dw + (int64_t)c * 16 + t, red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]);
+  // 64 channels x 16 taps = 1024 sums over the 4 phases; consecutive threads -> consecutive taps of one channel
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+    const int ch = e >> 4, t = e & 15;
+    if (blockIdx.y * 64 + ch < C)
+      atomicAdd(dw + (int64_t)(blockIdx.y * 64 + ch) * 16 + t, red[0][t][ch] + red[1][t][ch] + red[2][t][ch] + red[3][t][ch]);
+  }
 }
 
 // ---- reductions at the end of the backward: one launch each for the four conv layers (blockIdx.y = layer) ----
@@ -443,7 +493,7 @@ struct LayerReduce {
   int S[4], Cout[4], Cin_real[4], Ncols[4];
 };
 
-// partial[cta * nsub + sub][c] = sum of this CTA's row slice (fixed order -> deterministic)
+// partial[cta][c] = sum of this CTA's row slice (fixed order -> deterministic)
 __global__ void __launch_bounds__(256) fcd_colsum_partial_kernel(LayerReduce R) {
   const int l = blockIdx.y;
   if ((int)blockIdx.x >= R.ctas[l]) return;
@@ -455,17 +505,35 @@ __global__ void __launch_bounds__(256) fcd_colsum_partial_kernel(LayerReduce R) 
   const int tpr = pairs < 256 ? pairs : 256;
   const int nsub = 256 / tpr;
   const int sub = threadIdx.x / tpr;
-  if (sub >= nsub) return;
-  for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {
+  __shared__ float sm[512];  // [sub][channel] when several row phases share the CTA (C <= 256: nsub * C = 512)
+  for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {   // (a single pass: tpr = min(pairs, 256) and pairs <= 256)
     float a0 = 0.f, a1 = 0.f;
     for (long long r = r0 + sub; r < r1; r += nsub) {
       const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * C + cp * 2);
       a0 += __low2float(v);
       a1 += __high2float(v);
     }
-    float* dst = R.db_partial[l] + ((long long)blockIdx.x * nsub + sub) * C + cp * 2;
-    dst[0] = a0;
-    dst[1] = a1;
+    float* dst = R.db_partial[l] + (long long)blockIdx.x * C + cp * 2;
+    if (nsub == 1) {
+      dst[0] = a0;
+      dst[1] = a1;
+    } else {
+      // fold the nsub row phases of this CTA in a fixed order: one partial row per CTA
+      float* s0 = sm + (sub * tpr + cp) * 2;
+      s0[0] = a0;
+      s0[1] = a1;
+      __syncthreads();
+      if (sub == 0) {
+        float t0 = 0.f, t1 = 0.f;
+        for (int k = 0; k < nsub; ++k) {
+          const float* sk = sm + (k * tpr + cp) * 2;
+          t0 += sk[0];
+          t1 += sk[1];
+        }
+        dst[0] = t0;
+        dst[1] = t1;
+      }
+    }
   }
 }
 // db[c] = sum_r partial[r][c]: 32 channels per CTA (lane = channel), 8 warps split the partial rows
@@ -474,8 +542,7 @@ __global__ void __launch_bounds__(256) fcd_colsum_final_kernel(LayerReduce R) {
   const int l = blockIdx.y;
   const int C = R.C[l];
   if ((int)blockIdx.x * 32 >= C) return;
-  const int tpr = C / 2 < 256 ? C / 2 : 256;
-  const int rows = R.ctas[l] * (256 / tpr);
+  const int rows = R.ctas[l];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
@@ -491,28 +558,39 @@ __global__ void __launch_bounds__(256) fcd_colsum_final_kernel(LayerReduce R) {
   }
 }
 
-// dW_l[co][ci][kh][kw] = sum_z part[z][tap][co][col]
+// dW_l[co][ci][kh][kw] = sum_z part[z][tap][co][col].  One CTA per (co, chunk of 64 columns): the partials are read as
+// 256-byte row segments (col fastest), summed over the splits, transposed through shared memory and written as one
+// contiguous run of dW (tap fastest) -- both sides coalesced.
 __global__ void __launch_bounds__(256) fcd_wgrad_reduce_kernel(LayerReduce R) {
   const int l = blockIdx.y;           // 0..3 <-> conv1..conv4
   const int Cout = R.Cout[l], Cin_real = R.Cin_real[l], Ncols = R.Ncols[l], S = R.S[l];
   const int taps = l == 0 ? 8 : 16;
-  const long long total = (long long)Cout * Cin_real * 16;
+  const int chunks = (Ncols + 63) / 64;
+  if ((int)blockIdx.x >= Cout * chunks) return;
+  const int co = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  __shared__ float t[16][65];
   const float* part = R.part[l];
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int kw = (int)(i % 4), kh = (int)((i / 4) % 4);
-    const int ci = (int)((i / 16) % Cin_real);
-    const int co = (int)(i / ((long long)16 * Cin_real));
-    int tap, col;
-    if (l == 0) {
-      tap = kh * 2 + kw / 2;
-      col = (kw % 2) * 32 + ci;
-    } else {
-      tap = kh * 4 + kw;
-      col = ci;
-    }
+  for (int e = threadIdx.x; e < taps * 64; e += 256) {
+    const int tap = e >> 6, cl = e & 63;
+    const int col = chunk * 64 + cl;
     float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += __ldg(part + (((long long)s * taps + tap) * Cout + co) * Ncols + col);
-    R.dw[l][i] = acc;
+    if (col < Ncols)
+      for (int s = 0; s < S; ++s) acc += __ldg(part + (((long long)s * taps + tap) * Cout + co) * Ncols + col);
+    t[tap][cl] = acc;
+  }
+  __syncthreads();
+  if (l == 0) {
+    // conv1: a k-step holds two horizontally adjacent taps x 32 (padded) channels: tap = kh*2 + kw/2, col = (kw%2)*32 + ci
+    for (int e = threadIdx.x; e < Cin_real * 16; e += 256) {
+      const int ci = e >> 4, kh = (e >> 2) & 3, kw = e & 3;
+      R.dw[l][((long long)co * Cin_real + ci) * 16 + (e & 15)] = t[kh * 2 + (kw >> 1)][(kw & 1) * 32 + ci];
+    }
+  } else {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int cl = e >> 4, k = e & 15;
+      const int ci = chunk * 64 + cl;
+      if (ci < Cin_real) R.dw[l][((long long)co * Cin_real + ci) * 16 + k] = t[k][cl];
+    }
   }
 }
 
@@ -759,7 +837,6 @@ static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
 // merged end-of-backward reductions: bias gradients (2 launches) and split-K weight gradients (1 launch)
 static int reduce_all(const FcdPlan& p, LayerReduce& R, cudaStream_t st) {
   int max_ctas = 1, max_c = 1;
-  long long max_dw = 1;
   double db_bytes = 0, dw_bytes = 0;
   for (int i = 0; i < 4; ++i) {
     const int l = i + 1;
@@ -778,8 +855,6 @@ static int reduce_all(const FcdPlan& p, LayerReduce& R, cudaStream_t st) {
     R.C[i] = C;
     if (R.ctas[i] > max_ctas) max_ctas = R.ctas[i];
     if (C > max_c) max_c = C;
-    const long long ndw = (long long)R.Cout[i] * R.Cin_real[i] * 16;
-    if (ndw > max_dw) max_dw = ndw;
     db_bytes += 2.0 * P * C;
     dw_bytes += 4.0 * (R.S[i] + 1.0) * (i == 0 ? 8 : 16) * R.Cout[i] * R.Ncols[i];
   }
@@ -795,8 +870,9 @@ static int reduce_all(const FcdPlan& p, LayerReduce& R, cudaStream_t st) {
   }
   {
     prof::Scope ps("fcd_wgrad_reduce", 0, dw_bytes, st);
-    const long long blocks = (max_dw + 255) / 256;
-    fcd_wgrad_reduce_kernel<<<dim3((unsigned)(blocks < 4096 ? blocks : 4096), 4), 256, 0, st>>>(R);
+    int blocks = 1;
+    for (int i = 0; i < 4; ++i) blocks = max(blocks, R.Cout[i] * cdiv(R.Ncols[i], 64));
+    fcd_wgrad_reduce_kernel<<<dim3((unsigned)blocks, 4), 256, 0, st>>>(R);
     ASN_LAUNCH_CHECK();
   }
   return ASN_OK;
@@ -843,6 +919,10 @@ extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, 
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* base = static_cast<uint8_t*>(wpack);
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  int64_t max_total = 16 * (int64_t)p.C[4];
+  double bytes = 0;
   for (int l = 1; l <= 4; ++l) {
     const float* w = params_host[2 * (l - 1)];
     const float* b = params_host[2 * (l - 1) + 1];
@@ -850,16 +930,26 @@ extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, 
     const int cin_real = l == 1 ? n_cls : p.C[l - 1];
     const int rows = l == 1 ? 32 : p.C[l - 1];
     const int64_t total = (int64_t)p.C[l] * (l == 1 ? 512 : 16 * cin_real) + (int64_t)16 * rows * p.C[l] + p.C[l];
-    prof::Scope ps("fcd_pack_weights", 0, 4.0 * p.C[l] * cin_real * 16 + 2.0 * total, st);
-    fcd_pack_conv_kernel<<<full_grid(total, 256), 256, 0, st>>>(
-        w, b, reinterpret_cast<__nv_bfloat16*>(base + p.wf_off[l]), reinterpret_cast<__nv_bfloat16*>(base + p.wd_off[l]),
-        reinterpret_cast<float*>(base + p.bias_off[l]), l, p.C[l], cin_real, rows);
-    ASN_LAUNCH_CHECK();
+    a.w[l - 1] = w;
+    a.b[l - 1] = b;
+    a.wf[l - 1] = reinterpret_cast<__nv_bfloat16*>(base + p.wf_off[l]);
+    a.wd[l - 1] = reinterpret_cast<__nv_bfloat16*>(base + p.wd_off[l]);
+    a.bias[l - 1] = reinterpret_cast<float*>(base + p.bias_off[l]);
+    a.Cout[l - 1] = p.C[l];
+    a.Cin_real[l - 1] = cin_real;
+    a.Cin_rows[l - 1] = rows;
+    if (total > max_total) max_total = total;
+    bytes += 4.0 * p.C[l] * cin_real * 16 + 2.0 * total;
   }
   ASN_CHECK_ARG(params_host[8] && params_host[9], "asn_fcd_pack_weights: null classifier parameter");
-  fcd_pack_cls_kernel<<<cdiv(16 * p.C[4], 256), 256, 0, st>>>(params_host[8], params_host[9],
-                                                               reinterpret_cast<float*>(base + p.wc_off),
-                                                               reinterpret_cast<float*>(base + p.bc_off), p.C[4]);
+  a.w[4] = params_host[8];
+  a.b[4] = params_host[9];
+  a.wc = reinterpret_cast<float*>(base + p.wc_off);
+  a.bc = reinterpret_cast<float*>(base + p.bc_off);
+  a.C4 = p.C[4];
+  prof::Scope ps("fcd_pack_weights", 0, bytes, st);
+  // grid.x sized for the largest layer (conv4), grid-stride elsewhere
+  fcd_pack_all_kernel<<<dim3((unsigned)cdiv(cdiv(max_total, 256), 4), 5), 256, 0, st>>>(a);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -965,7 +1055,7 @@ static int fcd_bwd_impl(const float* dout, const float* x_logits, int x_h, int x
     {
       prof::Scope ps("fcd_classifier_wgrad", 2.0 * N * p.H[5] * p.W[5] * 16 * p.C[4], 0, st);
       ASN_CUDA(cudaMemsetAsync(dparams_host[8], 0, (size_t)16 * p.C[4] * sizeof(float), st));
-      fcd_cls_wgrad_kernel<<<dim3(16, cdiv(p.C[4], 64), CLS_SLICES), 256, 0, st>>>(dout, A[4], dparams_host[8], N, p.H[4],
+      fcd_cls_wgrad_kernel<<<dim3(CLS_SLICES, cdiv(p.C[4], 64)), 256, 0, st>>>(dout, A[4], dparams_host[8], N, p.H[4],
                                                                                    p.W[4], p.C[4], p.H[5], p.W[5]);
       ASN_LAUNCH_CHECK();
     }

@@ -550,7 +550,7 @@ class FcdWeightPack:
             ps = [_req(p.detach(), torch.float32, "parameter") for p in params]
             check(lib.asn_fcd_pack_weights(_lib.ptr_array([p.data_ptr() for p in ps]), n_cls, ndf,
                                            self.buf.data_ptr(), _stream()), "asn_fcd_pack_weights")
-            _count(5)
+            _count(1)
             self.key = key
         return self.buf
 
