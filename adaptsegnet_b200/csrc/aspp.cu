@@ -300,15 +300,21 @@ struct AsppWs {
   int NP, S;
 };
 
-constexpr int ASPP_WGRAD_BN = 192;  // MN-major B tiles are made of 64-column boxes: 4 x 192 >= 688
+// MN-major B tiles are made of 64-column boxes.  CTA pairs (256 x 256 tiles, each CTA loading 128 of the 256 columns):
+// 3 x 256 >= 688; single CTAs: 4 x 192.
+static int aspp_wgrad_bn(int Cin) {
+  return umma::cluster_size(umma::MODE_GEMM_MN, 256) == 2 && cdiv(Cin, 128) % 2 == 0 ? 256 : 192;
+}
 
 static AsppWs aspp_ws(int N, int Cin, int H, int W, int n_cls, int n_active) {
   AsppWs w;
   const int64_t P = (int64_t)N * H * W;
   w.NP = (int)round_up((int64_t)9 * n_active * n_cls, 16);
   // split-K of the wgrad GEMM: one wave of persistent CTAs
-  const int tiles = cdiv(Cin, 128) * cdiv(w.NP, ASPP_WGRAD_BN);
-  int S = (sm_count() + tiles - 1) / tiles;
+  const int bn = aspp_wgrad_bn(Cin);
+  const int tiles = bn == 256 ? cdiv(Cin, 256) * cdiv(w.NP, bn) : cdiv(Cin, 128) * cdiv(w.NP, bn);  // (pair) tiles
+  const int slots = bn == 256 ? sm_count() / 2 : sm_count();
+  int S = slots / tiles;
   const int k_steps = cdiv(P, 64);
   if (S > k_steps / 4) S = k_steps / 4;
   if (S < 1) S = 1;
@@ -450,7 +456,7 @@ extern "C" int asn_aspp_bwd(const void* x_bf16, int dx_channels_last, const void
     // dWp[Cin][NP] = X[N*P][Cin]^T . dYcol[N*P][NP]: both operands as they are (MN-major), split-K over the pixels
     float* part = reinterpret_cast<float*>(base + ws.dwpart);
     rc = umma::gemm_nt_mn(x_bf16, dycol, part, Cin, ws.NP, N * P, Cin, ws.NP, ws.NP, ws.S, (long long)Cin * ws.NP,
-                          ASPP_WGRAD_BN, st, "aspp_wgrad_gemm", flops);
+                          aspp_wgrad_bn(Cin), st, "aspp_wgrad_gemm", flops);
     if (rc) return rc;
     GradPtrs gp{};
     for (int b = 0; b < n_active; ++b) gp.w[b] = dw_oihw[b];

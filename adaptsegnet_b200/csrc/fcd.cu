@@ -92,9 +92,11 @@ static int make_plan(FcdPlan& p, int N, int n_cls, int ndf, int H, int W) {
     const int nn = wgrad_n(p, l);
     const int bn = nn >= 256 ? 256 : nn;
     const int ctas = cdiv(p.C[l], 128) * cdiv(nn, bn) * wgrad_taps(l);
-    // one wave of the persistent grid (two CTAs per SM when BLOCK_N <= 128)
-    const int slots = sm_count() * (bn <= 128 ? 2 : 1);
-    int S = (slots + ctas - 1) / ctas;
+    // one wave of the persistent grid: CTA pairs (one per TPC) where the layer has an even number of 128-row M tiles,
+    // else single CTAs (two per SM when BLOCK_N <= 128)
+    const bool pair = umma::cluster_size(umma::MODE_WGRAD, bn) == 2 && cdiv(p.C[l], 128) % 2 == 0;
+    const int slots = pair ? sm_count() / 2 : sm_count() * (bn <= 128 ? 2 : 1);
+    int S = pair ? slots / (ctas / 2) : (slots + ctas - 1) / ctas;
     if (S > k_steps / 2) S = k_steps / 2;
     if (S < 1) S = 1;
     const int sps = cdiv(k_steps, S);

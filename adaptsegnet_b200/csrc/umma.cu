@@ -100,7 +100,10 @@ struct Shape {
 int cluster_size(int mode, int block_n) {
   static const bool off = getenv("ASN_PAIR") != nullptr && getenv("ASN_PAIR")[0] == '0';
   if (off) return 1;
-  return (mode == MODE_GEMM || mode == MODE_CONV) && block_n >= 128 ? 2 : 1;
+  if (mode == MODE_GEMM || mode == MODE_CONV) return block_n >= 128 ? 2 : 1;
+  // MN-major modes: each CTA of the pair holds block_n / 2 channels of B as 64-channel boxes; callers additionally
+  // need an even number of 128-row M tiles (pairs are x-neighbours) and 128 rows of A per CTA
+  return block_n % 128 == 0 ? 2 : 1;
 }
 
 template <int MODE, int BLOCK_N, int CL, int MT>
@@ -167,7 +170,7 @@ bool block_n_supported(int mode, int block_n) {
     case MODE_GEMM: return block_n == 128 || block_n == 176 || block_n == 256;
     case MODE_CONV: return block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256;
     case MODE_WGRAD: return block_n == 64 || block_n == 128 || block_n == 256;
-    case MODE_GEMM_MN: return block_n == 128 || block_n == 192;
+    case MODE_GEMM_MN: return block_n == 128 || block_n == 192 || block_n == 256;
   }
   return false;
 }
@@ -184,7 +187,9 @@ int rows_per_cta(int mode, long long m_tiles_128, long long other) {
 
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
            const char* prof_name, double prof_flops, double prof_bytes, int rows) {
-  const int cl = rows == BLOCK_M ? cluster_size(mode, block_n) : 1;
+  int cl = rows == BLOCK_M ? cluster_size(mode, block_n) : 1;
+  // MN-major pairs are two x-neighbouring 128-row M tiles of the same N tile: needs an even number of M tiles
+  if ((mode == MODE_WGRAD || mode == MODE_GEMM_MN) && (cdiv(P.M, BLOCK_M) % 2 != 0)) cl = 1;
   const int mt = rows / BLOCK_M;
 #define ASN_CASE(MODE, BN, CLS, MTS) \
   if (mode == MODE && block_n == BN && cl == CLS && mt == MTS)  \
@@ -211,8 +216,13 @@ int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, di
   ASN_CASE(MODE_WGRAD, 64, 1, 1)
   ASN_CASE(MODE_WGRAD, 128, 1, 1)
   ASN_CASE(MODE_WGRAD, 256, 1, 1)
+  ASN_CASE(MODE_WGRAD, 128, 2, 1)
+  ASN_CASE(MODE_WGRAD, 256, 2, 1)
   ASN_CASE(MODE_GEMM_MN, 192, 1, 1)
   ASN_CASE(MODE_GEMM_MN, 128, 1, 1)
+  ASN_CASE(MODE_GEMM_MN, 256, 1, 1)
+  ASN_CASE(MODE_GEMM_MN, 128, 2, 1)
+  ASN_CASE(MODE_GEMM_MN, 256, 2, 1)
 #undef ASN_CASE
   set_error("umma::launch: no kernel for mode %d block_n %d rows %d", mode, block_n, rows);
   return ASN_EUNSUPPORTED;

@@ -378,8 +378,9 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   constexpr int TMEM_COLS = TmemCols<BLOCK_N, MT>::value;
   constexpr int NACC = TmemCols<BLOCK_N, MT>::nacc;
   static_assert(MT == 1 || (MODE != MODE_WGRAD && MODE != MODE_GEMM_MN), "MN-major tiles are 128 rows tall");
-  static_assert(CL == 1 || (MT == 1 && EW == 8 && BLOCK_N % 16 == 0 && (MODE == MODE_GEMM || MODE == MODE_CONV)),
-                "pair mode: K-major modes, one CTA per SM, 256 x BLOCK_N MMAs (BLOCK_N a multiple of 16)");
+  static_assert(CL == 1 || (MT == 1 && EW == 8 && BLOCK_N % 16 == 0), "pair mode: one CTA per SM, 256 x BLOCK_N MMAs");
+  static_assert(CL == 1 || (MODE != MODE_WGRAD && MODE != MODE_GEMM_MN) || BLOCK_N % 128 == 0,
+                "pair mode, MN-major: each CTA holds BLOCK_N / 2 channels of B as 64-channel boxes");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
@@ -449,7 +450,24 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const uint32_t lbar = mapa_rank(full_bar(s), 0);
             if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * (L::A_BYTES + L::B_BYTES));
             const int nb = t.n0 + rank * (BLOCK_N / 2);
-            if (MODE == MODE_GEMM) {
+            if (MODE == MODE_GEMM_MN) {
+              // (the leader armed 2 x (A + B) bytes: both CTAs load P.a_boxes boxes of A -- callers keep M > 64)
+              for (int a = 0; a < 2; ++a)
+                tma_load_2d_pair(&map_a0, sa + a * 8192, lbar, t.m0 + a * 64, ks * BLOCK_K);
+#pragma unroll
+              for (int b = 0; b < BLOCK_N / 128; ++b)
+                tma_load_2d_pair(&map_b, sb + b * 8192, lbar, nb + b * 64, ks * BLOCK_K);
+            } else if (MODE == MODE_WGRAD) {
+              const int bx = ks % P.tiles_w, by = (ks / P.tiles_w) % P.tiles_h, im = ks / (P.tiles_w * P.tiles_h);
+              for (int a = 0; a < 2; ++a)
+                tma_load_4d_pair(&map_a0, sa + a * 8192, lbar, t.m0 + a * 64, bx * P.tw, by * P.th, im);
+              const int mi = P.tap_map[t.wg_tap];
+              const CUtensorMap* bm = mi == 0 ? &map_b : mi == 1 ? &map_a1 : mi == 2 ? &map_a2 : &map_a3;
+#pragma unroll
+              for (int b = 0; b < BLOCK_N / 128; ++b)
+                tma_load_4d_pair(bm, sb + b * 8192, lbar, nb + b * 64, bx * P.tw + P.tap_dw[t.wg_tap],
+                                 by * P.th + P.tap_dh[t.wg_tap], im);
+            } else if (MODE == MODE_GEMM) {
               tma_load_2d_pair(&map_a0, sa, lbar, ks * BLOCK_K, t.m0);
               tma_load_2d_pair(&map_b, sb, lbar, ks * BLOCK_K, nb);
             } else {
@@ -500,7 +518,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     // =============================== MMA issuer ===============================
     if (lane == 0 && leader) {  // pair: one thread of the leader CTA drives the tensor cores of both SMs
       constexpr bool MN_MAJOR = MODE == MODE_WGRAD || MODE == MODE_GEMM_MN;
-      constexpr uint32_t idesc = MN_MAJOR ? make_idesc(BLOCK_M, BLOCK_N, 1, 1) : make_idesc(CL * BLOCK_M, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = MN_MAJOR ? make_idesc(CL * BLOCK_M, BLOCK_N, 1, 1) : make_idesc(CL * BLOCK_M, BLOCK_N, 0, 0);
       uint32_t it = 0, tile_iter = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
         const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
