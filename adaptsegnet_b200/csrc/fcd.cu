@@ -37,6 +37,21 @@ struct FcdPlan {
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// Tile shape of a layer's weight-gradient kernel (M = Cout, N = nn input channels per tap, K = pixels):
+//   pair: CTA pairs on 256-row M tiles where Cout has an even number of 128-row tiles and nn % 128 == 0 (conv3, conv4);
+//   nt  : otherwise, taps computed per CTA from ONE dY tile (A is re-used, 4 x 64 or 2 x 128 accumulator columns) --
+//         the thin layers (conv1, conv2) move half the operand bytes per MAC this way.  ASN_WGRAD_TAPS=1 disables it.
+static void wgrad_cfg(int Cout, int nn, int* bn, int* nt, bool* pair) {
+  static const int taps_env = getenv("ASN_WGRAD_TAPS") ? atoi(getenv("ASN_WGRAD_TAPS")) : 0;
+  *bn = nn >= 256 ? 256 : nn;
+  *pair = umma::cluster_size(umma::MODE_WGRAD, *bn) == 2 && cdiv(Cout, 128) % 2 == 0;
+  *nt = 1;
+  if (!*pair && taps_env != 1) {
+    if (*bn == 64) *nt = taps_env == 2 ? 2 : 4;
+    else if (*bn == 128) *nt = 2;
+  }
+}
+
 static void pick_tile(int OH, int OW, int px, int* th, int* tw) {
   int64_t best = -1;
   for (int h = 1; h <= px; h *= 2) {
@@ -90,12 +105,13 @@ static int make_plan(FcdPlan& p, int N, int n_cls, int ndf, int H, int W) {
     pick_tile(p.H[l], p.W[l], 64, &th, &tw);
     const int k_steps = N * cdiv(p.H[l], th) * cdiv(p.W[l], tw);
     const int nn = wgrad_n(p, l);
-    const int bn = nn >= 256 ? 256 : nn;
-    const int ctas = cdiv(p.C[l], 128) * cdiv(nn, bn) * wgrad_taps(l);
-    // one wave of the persistent grid: CTA pairs (one per TPC) where the layer has an even number of 128-row M tiles,
-    // else single CTAs (two per SM when BLOCK_N <= 128)
-    const bool pair = umma::cluster_size(umma::MODE_WGRAD, bn) == 2 && cdiv(p.C[l], 128) % 2 == 0;
-    const int slots = pair ? sm_count() / 2 : sm_count() * (bn <= 128 ? 2 : 1);
+    int bn, nt;
+    bool pair;
+    wgrad_cfg(p.C[l], nn, &bn, &nt, &pair);
+    const int ctas = cdiv(p.C[l], 128) * cdiv(nn, bn) * (wgrad_taps(l) / nt);
+    // one wave of the persistent grid: CTA pairs (one per TPC), multi-tap CTAs (one per SM) or plain single CTAs
+    // (two per SM when BLOCK_N <= 128)
+    const int slots = pair ? sm_count() / 2 : sm_count() * (nt == 1 && bn <= 128 ? 2 : 1);
     int S = pair ? slots / (ctas / 2) : (slots + ctas - 1) / ctas;
     if (S > k_steps / 2) S = k_steps / 2;
     if (S < 1) S = 1;
@@ -576,8 +592,12 @@ __global__ void __launch_bounds__(256) fcd_wgrad_reduce_kernel(LayerReduce R) {
     const int tap = e >> 6, cl = e & 63;
     const int col = chunk * 64 + cl;
     float acc = 0.f;
-    if (col < Ncols)
-      for (int s = 0; s < S; ++s) acc += __ldg(part + (((long long)s * taps + tap) * Cout + co) * Ncols + col);
+    if (col < Ncols) {
+      const float* src = part + ((long long)tap * Cout + co) * Ncols + col;
+      const long long zs = (long long)taps * Cout * Ncols;  // elements between split-K partials
+#pragma unroll 8
+      for (int s = 0; s < S; ++s) acc += __ldg(src + s * zs);
+    }
     t[tap][cl] = acc;
   }
   __syncthreads();
@@ -812,7 +832,9 @@ static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
         P.tap_dw[kh * 4 + kw] = tap_a(kw);
       }
   }
-  const int bn = nn >= 256 ? 256 : nn;
+  int bn, nt;
+  bool pair;
+  wgrad_cfg(Cout, nn, &bn, &nt, &pair);
   P.M = Cout;
   P.N = nn;
   P.tw = tw; P.th = th;
@@ -827,10 +849,10 @@ static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   P.tap_stride_out = (long long)Cout * nn;
   P.z_stride_out = (long long)P.taps * Cout * nn;
   P.slope = 1.f;
-  dim3 grid(cdiv(Cout, 128) * cdiv(nn, bn), P.taps, S);
+  dim3 grid(cdiv(Cout, 128) * cdiv(nn, bn), P.taps / nt, S);
   static const char* names[5] = {"", "fcd_conv1_wgrad", "fcd_conv2_wgrad", "fcd_conv3_wgrad", "fcd_conv4_wgrad"};
   if ((rc = launch(MODE_WGRAD, bn, maps, P, grid, st, names[l], layer_flops(p, l),
-                   layer_bytes(p, l, 0) + 4.0 * S * P.taps * Cout * nn)))
+                   layer_bytes(p, l, 0) + 4.0 * S * P.taps * Cout * nn, nt * 128)))
     return rc;
   *S_out = S;
   return ASN_OK;

@@ -89,7 +89,9 @@ struct Shape {
       (MT == 1 && CL == 1 && ((MODE == MODE_WGRAD && BLOCK_N <= 128) || (MODE == MODE_CONV && BLOCK_N <= 32))) ? 4 : 8;
   static_assert(MODE != MODE_GEMM_MN || BLOCK_N % 64 == 0, "MN-major B tiles are made of 64-column boxes");
   static constexpr int ctas_per_sm = EW == 4 ? 2 : 1;
-  static constexpr int stage = MT * 16384 + (((BLOCK_N / CL) * 128 + 1023) / 1024) * 1024;
+  static constexpr int b_tile = (((BLOCK_N / CL) * 128 + 1023) / 1024) * 1024;
+  // K-major modes: MT row tiles of A per B tile; WGRAD: MT taps' B tiles per A tile
+  static constexpr int stage = MODE == MODE_WGRAD ? 16384 + MT * b_tile : MT * 16384 + b_tile;
   static constexpr int fit = ((EW == 4 ? 100 : 184) * 1024) / stage;
   static constexpr int stages = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
@@ -100,7 +102,8 @@ struct Shape {
 int cluster_size(int mode, int block_n) {
   static const bool off = getenv("ASN_PAIR") != nullptr && getenv("ASN_PAIR")[0] == '0';
   if (off) return 1;
-  if (mode == MODE_GEMM || mode == MODE_CONV) return block_n >= 128 ? 2 : 1;
+  static const int min_bn = getenv("ASN_PAIR_MIN_BN") ? atoi(getenv("ASN_PAIR_MIN_BN")) : 128;
+  if (mode == MODE_GEMM || mode == MODE_CONV) return block_n >= min_bn && block_n >= 64 ? 2 : 1;
   // MN-major modes: each CTA of the pair holds block_n / 2 channels of B as 64-channel boxes; callers additionally
   // need an even number of 128-row M tiles (pairs are x-neighbours) and 128 rows of A per CTA
   return block_n % 128 == 0 ? 2 : 1;
@@ -111,7 +114,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
                     double flops, double bytes) {
   using Sh = Shape<MODE, BLOCK_N, MT, CL>;
   constexpr int STAGES = Sh::stages, EW = Sh::EW, NUM_THREADS = EpiCfg<EW>::threads;
-  using L = SmemLayout<BLOCK_N, STAGES, MT, EW, CL>;
+  using L = KernelSmem<MODE, BLOCK_N, STAGES, CL, MT, EW>;
   auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL, MT, EW>;
   static bool configured = false;
   static int max_clusters = 0;  // CL = 2: CTA pairs the device can keep resident at once (one per TPC)
@@ -207,6 +210,7 @@ int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, di
   ASN_CASE(MODE_CONV, 64, 1, 1)
   ASN_CASE(MODE_CONV, 128, 1, 1)
   ASN_CASE(MODE_CONV, 256, 1, 1)
+  ASN_CASE(MODE_CONV, 64, 2, 1)
   ASN_CASE(MODE_CONV, 128, 2, 1)
   ASN_CASE(MODE_CONV, 256, 2, 1)
   ASN_CASE(MODE_CONV, 32, 1, 2)
@@ -216,6 +220,9 @@ int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, di
   ASN_CASE(MODE_WGRAD, 64, 1, 1)
   ASN_CASE(MODE_WGRAD, 128, 1, 1)
   ASN_CASE(MODE_WGRAD, 256, 1, 1)
+  ASN_CASE(MODE_WGRAD, 64, 1, 2)
+  ASN_CASE(MODE_WGRAD, 64, 1, 4)
+  ASN_CASE(MODE_WGRAD, 128, 1, 2)
   ASN_CASE(MODE_WGRAD, 128, 2, 1)
   ASN_CASE(MODE_WGRAD, 256, 2, 1)
   ASN_CASE(MODE_GEMM_MN, 192, 1, 1)

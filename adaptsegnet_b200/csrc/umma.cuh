@@ -313,16 +313,24 @@ struct EpiCfg {
   static constexpr int threads = 64 + 32 * EW;      // TMA producer warp + MMA warp + epilogue warps
 };
 
-template <int BLOCK_N, int STAGES, int MT = 1, int EW = 8, int CL = 1>
+// AT / BT = A / B tiles per stage: K-major modes may stack AT = 2 row tiles on one B tile (MT = 2); the pixel-reduction
+// WGRAD mode may feed BT = 2 or 4 taps' B tiles from one A tile.
+template <int BLOCK_N, int STAGES, int AT = 1, int EW = 8, int CL = 1, int BT = 1>
 struct SmemLayout {
-  static constexpr int A_BYTES = MT * BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
-  static constexpr int B_BYTES = (BLOCK_N / CL) * BLOCK_K * 2;  // a pair keeps half of the B tile in each CTA
-  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int A_BYTES = AT * BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
+  static constexpr int B_BYTES = (BLOCK_N / CL) * BLOCK_K * 2;  // one B tile; a pair keeps half of it in each CTA
+  static constexpr int B_TILE = ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + BT * B_TILE;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int STG_OFFSET = BAR_OFFSET + 256;                     // barriers take <= 21 x 8 B
   static constexpr int ROW_OFFSET = STG_OFFSET + EW * 32 * EpiCfg<EW>::pitch * 4;  // per-warp [32][pitch] fp32
   static constexpr int TOTAL = ROW_OFFSET + EW * 32 * 8 + 1024;                    // + row tables + alignment slack
 };
+
+// the stage layout of umma_kernel<MODE, BLOCK_N, STAGES, CL, MT, EW> (shared with the launcher)
+template <int MODE, int BLOCK_N, int STAGES, int CL, int MT, int EW>
+using KernelSmem = SmemLayout<BLOCK_N, STAGES, (MODE == MODE_WGRAD && MT > 1 ? 1 : MT), EW, CL,
+                              (MODE == MODE_WGRAD && MT > 1 ? MT : 1)>;
 
 struct TileCoord {
   int z, n0, m0, img, oh0, ow0, wg_tap, ks_begin, nsteps;
@@ -335,6 +343,7 @@ struct TileCoord {
 template <int MODE, int BLOCK_N, int CL, int MT>
 __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int rank) {
   TileCoord t;
+  constexpr int TAPS = MODE == MODE_WGRAD ? MT : 1;  // WGRAD: MT counts the taps a CTA computes from one A tile
   const int gx = CL == 1 ? P.grid_x : (P.grid_x + 1) / 2;
   const int bx = CL == 1 ? tile % gx : 2 * (tile % gx) + rank;
   const int by = (tile / gx) % P.grid_y;
@@ -358,7 +367,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int 
     const int m_tiles = (P.M + BLOCK_M - 1) / BLOCK_M;
     t.m0 = (bx % m_tiles) * BLOCK_M;
     t.n0 = (bx / m_tiles) * BLOCK_N;
-    t.wg_tap = by;
+    t.wg_tap = by * TAPS;  // first tap of the group
     t.ks_begin = t.z * P.steps_per_split;
     ks_end = min(P.k_steps, t.ks_begin + P.steps_per_split);
   }
@@ -371,13 +380,15 @@ __global__ void __launch_bounds__(EpiCfg<EW>::threads, (EW == 4 ? 2 : 1))
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
-  using L = SmemLayout<BLOCK_N, STAGES, MT, EW, CL>;
+  constexpr bool MULTI_TAP = MODE == MODE_WGRAD && MT > 1;
+  using L = KernelSmem<MODE, BLOCK_N, STAGES, CL, MT, EW>;
+  static_assert(!MULTI_TAP || CL == 1, "multi-tap weight-gradient tiles run on single CTAs");
   constexpr int EPI_CHUNK = EpiCfg<EW>::chunk, EPI_PITCH = EpiCfg<EW>::pitch;
   constexpr int CPL = EPI_CHUNK / 4;  // columns per lane on the way out (8 or 4)
   static_assert(EW == 8 || 2 * TmemCols<BLOCK_N, MT>::value <= 512, "two CTAs per SM need <= 256 TMEM columns each");
   constexpr int TMEM_COLS = TmemCols<BLOCK_N, MT>::value;
   constexpr int NACC = TmemCols<BLOCK_N, MT>::nacc;
-  static_assert(MT == 1 || (MODE != MODE_WGRAD && MODE != MODE_GEMM_MN), "MN-major tiles are 128 rows tall");
+  static_assert(MT == 1 || MODE != MODE_GEMM_MN, "MN-major tiles are 128 rows tall (WGRAD: MT = taps per CTA)");
   static_assert(CL == 1 || (MT == 1 && EW == 8 && BLOCK_N % 16 == 0), "pair mode: one CTA per SM, 256 x BLOCK_N MMAs");
   static_assert(CL == 1 || (MODE != MODE_WGRAD && MODE != MODE_GEMM_MN) || BLOCK_N % 128 == 0,
                 "pair mode, MN-major: each CTA holds BLOCK_N / 2 channels of B as 64-channel boxes");
@@ -501,15 +512,20 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             // k-step = one box of 64 pixels: A = dY channels [m0, m0+128), B = X@tap channels [n0, n0+BLOCK_N)
             const int bx = ks % P.tiles_w, by = (ks / P.tiles_w) % P.tiles_h, im = ks / (P.tiles_w * P.tiles_h);
             const uint32_t box_bytes = 64 * 64 * 2;
-            mbar_arrive_expect_tx(full_bar(s), (P.a_boxes + BLOCK_N / 64) * box_bytes);
+            constexpr int TAPS = MULTI_TAP ? MT : 1;  // taps fed from this one A tile
+            mbar_arrive_expect_tx(full_bar(s), (P.a_boxes + TAPS * (BLOCK_N / 64)) * box_bytes);
             for (int a = 0; a < P.a_boxes; ++a)
               tma_load_4d(&map_a0, sa + a * box_bytes, full_bar(s), t.m0 + a * 64, bx * P.tw, by * P.th, im);
-            const int mi = P.tap_map[t.wg_tap];
-            const CUtensorMap* bm = mi == 0 ? &map_b : mi == 1 ? &map_a1 : mi == 2 ? &map_a2 : &map_a3;
 #pragma unroll
-            for (int b = 0; b < BLOCK_N / 64; ++b)
-              tma_load_4d(bm, sb + b * box_bytes, full_bar(s), t.n0 + b * 64, bx * P.tw + P.tap_dw[t.wg_tap],
-                          by * P.th + P.tap_dh[t.wg_tap], im);
+            for (int j = 0; j < TAPS; ++j) {
+              const int tap = t.wg_tap + j;
+              const int mi = P.tap_map[tap];
+              const CUtensorMap* bm = mi == 0 ? &map_b : mi == 1 ? &map_a1 : mi == 2 ? &map_a2 : &map_a3;
+#pragma unroll
+              for (int b = 0; b < BLOCK_N / 64; ++b)
+                tma_load_4d(bm, sb + j * L::B_TILE + b * box_bytes, full_bar(s), t.n0 + b * 64,
+                            bx * P.tw + P.tap_dw[tap], by * P.th + P.tap_dh[tap], im);
+            }
           }
         }
       }
@@ -549,7 +565,13 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             }
             if (CL == 2) mma_f16_ss_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
             else mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            if (MT == 2) {  // rows 128..255 of the tile: next 16 KB of the A stage, same B
+            if (MULTI_TAP) {  // the other taps of the group: same A (dY), their own B (X at the tap) and accumulator
+#pragma unroll
+              for (int j = 1; j < MT; ++j) {
+                const uint64_t dbj = make_smem_desc(sb + j * L::B_TILE + k * 2048, 8192, 1024);
+                mma_f16_ss(tmem_d + j * BLOCK_N, da, dbj, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              }
+            } else if (MT == 2) {  // rows 128..255 of the tile: next 16 KB of the A stage, same B
               const uint64_t da1 = make_smem_desc(sa + BLOCK_M * BLOCK_K * 2 + k * 32, 16, 1024);
               mma_f16_ss(tmem_d + BLOCK_N, da1, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
             }
@@ -588,7 +610,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       for (int sub = 0; sub < MT; ++sub) {
         const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N) + sub * BLOCK_N;
         {  // row table: thread = row
-          const int r = sub * BLOCK_M + q * 32 + lane;
+          const int r = (MULTI_TAP ? 0 : sub * BLOCK_M) + q * 32 + lane;
           bool row_ok;
           long long row_off;
           if (MODE == MODE_GEMM || MODE == MODE_GEMM_MN) {
@@ -602,7 +624,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             row_off = (((long long)t.img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
           } else {
             row_ok = (t.m0 + r) < P.M;
-            row_off = (long long)t.z * P.z_stride_out + (long long)t.wg_tap * P.tap_stride_out +
+            row_off = (long long)t.z * P.z_stride_out + (long long)(t.wg_tap + sub) * P.tap_stride_out +
                       (long long)(t.m0 + r) * P.ld_out;
           }
           __syncwarp();
