@@ -102,8 +102,11 @@ struct Shape {
 int cluster_size(int mode, int block_n) {
   static const bool off = getenv("ASN_PAIR") != nullptr && getenv("ASN_PAIR")[0] == '0';
   if (off) return 1;
-  static const int min_bn = getenv("ASN_PAIR_MIN_BN") ? atoi(getenv("ASN_PAIR_MIN_BN")) : 128;
-  if (mode == MODE_GEMM || mode == MODE_CONV) return block_n >= min_bn && block_n >= 64 ? 2 : 1;
+  // measured on B200 (profiles/README.md): pairs pay for the GEMMs (ASPP forward / dgrad: +5-10 %) and the MN-major
+  // weight gradients (+25-50 %), not for the implicit-GEMM convolutions, whose 4-D activation boxes bound them
+  static const bool conv_pairs = getenv("ASN_PAIR_CONV") != nullptr && getenv("ASN_PAIR_CONV")[0] == '1';
+  if (mode == MODE_CONV) return conv_pairs && block_n >= 64 ? 2 : 1;
+  if (mode == MODE_GEMM) return block_n >= 128 ? 2 : 1;
   // MN-major modes: each CTA of the pair holds block_n / 2 channels of B as 64-channel boxes; callers additionally
   // need an even number of 128-row M tiles (pairs are x-neighbours) and 128 rows of A per CTA
   return block_n % 128 == 0 ? 2 : 1;

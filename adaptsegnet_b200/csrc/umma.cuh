@@ -658,6 +658,28 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < CPL; ++i) bv[i] = i < n_ok ? __ldg(P.bias + n + i) : 0.f;
           }
+          // LeakyReLU masks of this lane's four rows, fetched up front: issued back to back, their (HBM) latencies
+          // overlap instead of adding up between the stores of the row loop below
+          uint32_t mpre[4][CPL / 2];
+          if (P.epi == EPI_BF16 && P.mask_src) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const long long off = row_tab[j * 8 + rr];
+#pragma unroll
+              for (int i = 0; i < CPL / 2; ++i) mpre[j][i] = 0u;
+              if (off < 0) continue;
+              const __nv_bfloat16* ms = P.mask_src + off + n;
+              const bool vec = full && (((reinterpret_cast<uintptr_t>(P.out) + 2 * (off + n)) & (2 * CPL - 1)) == 0);
+              if (!vec) continue;
+              if (CPL == 8) {
+                const uint4 m = __ldg(reinterpret_cast<const uint4*>(ms));
+                mpre[j][0] = m.x; mpre[j][1] = m.y; mpre[j][CPL / 2 - 2] = m.z; mpre[j][CPL / 2 - 1] = m.w;
+              } else {
+                const uint2 m = __ldg(reinterpret_cast<const uint2*>(ms));
+                mpre[j][0] = m.x; mpre[j][1] = m.y;
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rl = j * 8 + rr;
@@ -690,13 +712,8 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               if (P.mask_src) {
                 const __nv_bfloat16* ms = P.mask_src + off + n;
                 if (vec) {
-                  if (CPL == 8) {
-                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(ms));
-                    mw[0] = m.x; mw[1] = m.y; mw[CPL / 2 - 2] = m.z; mw[CPL / 2 - 1] = m.w;
-                  } else {
-                    const uint2 m = __ldg(reinterpret_cast<const uint2*>(ms));
-                    mw[0] = m.x; mw[1] = m.y;
-                  }
+#pragma unroll
+                  for (int i = 0; i < CPL / 2; ++i) mw[i] = mpre[j][i];
 #pragma unroll
                   for (int i = 0; i < CPL / 2; ++i) {  // bf16 > 0  <=>  sign bit clear and not zero
                     const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;

@@ -22,19 +22,47 @@ lab[:, :40] = 255
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
 
+head5 = Classifier_Module(1024, [6, 12, 18, 24], [6, 12, 18, 24], 19).to(dev)
+f3 = (torch.randn(1, 1024, h, w, device=dev).abs() * 4.4).requires_grad_(True)
+f4cl = f4.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+from adaptsegnet_b200.optim import FlatParams, FusedAdam, FusedSGD
+flatD = FlatParams(D.parameters())
+adam = FusedAdam(flatD, lr=1e-4, betas=(0.9, 0.99))
+flatH = FlatParams(list(head.parameters()) + list(head5.parameters()))
+sgd = FusedSGD(flatH, [{"params": list(head.parameters()) + list(head5.parameters()), "lr": 2.5e-3}], lr=2.5e-3,
+               momentum=0.9, weight_decay=5e-4)
+
+
+tier_b_only = "--tier-b" in sys.argv
+
+
 def one_pass():
-    logits = head(f4)
-    up = ops.upsample_bilinear(logits, (H, W))
-    loss = ops.softmax_cross_entropy(up, lab)
-    loss.backward()
-    up2 = up.detach().requires_grad_(True)
-    d = D(up2, from_logits=True)
-    l2 = ops.gan_loss(d, 0.0, ops.GAN_BCE)
-    l2.backward()
-    p = ops.softmax_channels(up.detach())
+    loss = None
+    if not tier_b_only:
+        # Tier-A chain (full-resolution logits materialised) on the layer4 head
+        logits = head(f4)
+        up = ops.upsample_bilinear(logits, (H, W))
+        loss = ops.softmax_cross_entropy(up, lab)
+        loss.backward()
+        up2 = up.detach().requires_grad_(True)
+        d = D(up2, from_logits=True)
+        l2 = ops.gan_loss(d, 0.0, ops.GAN_BCE)
+        l2.backward()
+        p = ops.softmax_channels(up.detach())
+    # Tier-B chain (what the trainer runs): channels_last features, low-res logits into the fused consumers
+    z5 = head5(f3)
+    z6 = head(f4cl)
+    lb = ops.upsample_softmax_cross_entropy(z6, (H, W), lab) + 0.1 * ops.upsample_softmax_cross_entropy(z5, (H, W), lab)
+    lb.backward()
+    zd = z6.detach().requires_grad_(True)
+    dd = D(zd, from_logits=True, up_size=(H, W))
+    ops.gan_loss(dd, 1.0, ops.GAN_BCE).backward()
+    sgd.step()
+    adam.step()
+    # evaluation kernels
     hist, _ = ops.fast_hist(lab.reshape(-1), torch.zeros(H * W, dtype=torch.uint8, device=dev), 19)
-    pred = ops.upsample_argmax(logits.detach(), (H, W))
-    return loss
+    pred = ops.upsample_argmax(z6.detach(), (H, W))
+    return lb if loss is None else loss
 
 
 one_pass()
