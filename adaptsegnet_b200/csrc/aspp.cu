@@ -157,7 +157,9 @@ aspp_gather_kernel(const float* __restrict__ Z, const float* __restrict__ bias_s
 __global__ void __launch_bounds__(256)
 aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYcol, int N, int H, int W, int n_cls,
                    int NP, AsppTaps taps) {
-  extern __shared__ __nv_bfloat16 tile[];  // [32][NP]
+  extern __shared__ __nv_bfloat16 tile[];  // [32][NP + 2]: an odd number of 32-bit words per row -> lanes (= rows) hit
+  const int TP = NP + 2;                   // 32 different banks when a warp writes one column
+
   const int P = H * W;
   const int groups_per_img = (P + 31) / 32;
   const int n = blockIdx.x / groups_per_img;
@@ -168,7 +170,7 @@ aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYc
   const int qh = q / W, qw = q - qh * W;
   const float* dyn = dy + (int64_t)n * n_cls * P;
   // zero the padding columns [J, NP) once
-  for (int idx = threadIdx.x; idx < (NP - J) * 32; idx += 256) tile[(idx & 31) * NP + J + (idx >> 5)] = __float2bfloat16(0.f);
+  for (int idx = threadIdx.x; idx < (NP - J) * 32; idx += 256) tile[(idx & 31) * TP + J + (idx >> 5)] = __float2bfloat16(0.f);
   for (int t = threadIdx.x >> 5; t < taps.n_taps; t += 8) {   // warp = tap
     const int h = qh - taps.dh[t], w = qw - taps.dw[t];
     const bool ok = q < P && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
@@ -176,16 +178,19 @@ aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYc
     for (int c = 0; c < n_cls; ++c) {
       const __nv_bfloat16 bv = __float2bfloat16(ok ? __ldg(src + (int64_t)c * P) : 0.f);
       const int j = t * n_cls + c;
-      tile[ql * NP + j] = bv;
+      tile[ql * TP + j] = bv;
     }
   }
   __syncthreads();
-  // rows q0..q0+31 of dYcol are contiguous: NP*2 bytes each, NP % 8 == 0 -> 16-byte vectors
-  const int vec_per_row = NP / 8;
-  const uint4* srcv = reinterpret_cast<const uint4*>(tile);
-  uint4* dst = reinterpret_cast<uint4*>(dYcol + ((int64_t)n * P + q0) * NP);
+  // rows q0..q0+31 of dYcol are contiguous (NP*2 bytes each): 32-bit words, a warp writes 128 contiguous bytes
+  const int wpr = NP / 2;
+  const uint32_t* srcw = reinterpret_cast<const uint32_t*>(tile);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(dYcol + ((int64_t)n * P + q0) * NP);
   const int rows = min(32, P - q0);
-  for (int i = threadIdx.x; i < rows * vec_per_row; i += 256) dst[i] = srcv[i];
+  for (int i = threadIdx.x; i < rows * wpr; i += 256) {
+    const int r = i / wpr, w = i - r * wpr;
+    dst[i] = srcw[r * (TP / 2) + w];
+  }
 }
 
 // Wp[j][ci] (bf16, j = t*n_cls + c, rows >= J zero) and WpT[ci][j] from the fp32 OIHW branch weights
@@ -215,21 +220,31 @@ aspp_pack_kernel(WeightPtrs wp, __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* _
 struct GradPtrs {
   float* w[4];
 };
+// dW_b[c][ci][k] = sum_s part[s][ci][(b*9 + k)*n_cls + c].  One CTA per UDW_CI input channels: their rows of the
+// partials are read coalesced (NP contiguous floats each) and summed over the splits into shared memory; the output is
+// written as runs of UDW_CI * 9 contiguous floats per (branch, class).
+constexpr int UDW_CI = 2;
 __global__ void __launch_bounds__(256)
 aspp_unpack_dw_kernel(const float* __restrict__ part, int S, GradPtrs gp, int n_active, int n_cls, int Cin,
                       int NP) {
-  const int64_t per_branch = (int64_t)n_cls * Cin * 9;
-  const int64_t total = per_branch * n_active;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    const int b = (int)(i / per_branch);
-    const int64_t r = i - (int64_t)b * per_branch;
-    const int k = (int)(r % 9);
-    const int ci = (int)((r / 9) % Cin);
-    const int c = (int)(r / (9 * (int64_t)Cin));
-    const int j = (b * 9 + k) * n_cls + c;
+  extern __shared__ float t[];  // [UDW_CI][NP]
+  const int ci0 = blockIdx.x * UDW_CI;
+  const int nci = min(UDW_CI, Cin - ci0);
+  const int64_t zs = (int64_t)Cin * NP;  // elements between split-K partials
+  for (int e = threadIdx.x; e < nci * NP; e += 256) {
+    const float* src = part + (int64_t)ci0 * NP + e;
     float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += __ldg(part + ((int64_t)s * Cin + ci) * NP + j);
-    if (gp.w[b]) gp.w[b][r] = acc;
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) acc += __ldg(src + s * zs);
+    t[e] = acc;
+  }
+  __syncthreads();
+  const int run = nci * 9;
+  for (int e = threadIdx.x; e < n_active * n_cls * run; e += 256) {
+    const int bc = e / run, r = e - bc * run;   // r = ci_local * 9 + k
+    const int b = bc / n_cls, c = bc - b * n_cls;
+    const int cl = r / 9, k = r - cl * 9;
+    if (gp.w[b]) gp.w[b][((int64_t)c * Cin + ci0) * 9 + r] = t[cl * NP + (b * 9 + k) * n_cls + c];
   }
 }
 
@@ -241,7 +256,16 @@ nchw_channel_sum_kernel(const float* __restrict__ src, float* __restrict__ out, 
   double acc = 0.0;
   for (int n = 0; n < N; ++n) {
     const float* s = src + ((int64_t)n * O + o) * P;
-    for (int i = threadIdx.x; i < P; i += 256) acc += (double)s[i];
+    if ((P & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+      // 16-byte loads, four independent fp32 partial sums per thread folded into the double accumulator per load
+#pragma unroll 4
+      for (int i = threadIdx.x; i < P / 4; i += 256) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+        acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < P; i += 256) acc += (double)s[i];
+    }
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
@@ -432,7 +456,7 @@ extern "C" int asn_aspp_bwd(const void* x_bf16, int dx_channels_last, const void
   make_taps(taps, dil_host, n_active, W);
   const double flops = 2.0 * N * P * (9.0 * n_active * n_cls) * Cin;
   if (dx_nchw || dw_oihw) {
-    const size_t smem = (size_t)32 * ws.NP * 2;
+    const size_t smem = (size_t)32 * (ws.NP + 2) * 2;
     if (smem > 48 * 1024)
       ASN_CUDA(cudaFuncSetAttribute(aspp_dycols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof::Scope ps("aspp_dy_cols", 0, 2.0 * N * P * ws.NP + 4.0 * N * P * n_cls, st);
@@ -461,7 +485,7 @@ extern "C" int asn_aspp_bwd(const void* x_bf16, int dx_channels_last, const void
     GradPtrs gp{};
     for (int b = 0; b < n_active; ++b) gp.w[b] = dw_oihw[b];
     prof::Scope ps("aspp_unpack_dw", 0, 4.0 * Cin * ws.NP * (ws.S + 1), st);
-    aspp_unpack_dw_kernel<<<full_grid((int64_t)n_active * n_cls * Cin * 9, 256), 256, 0, st>>>(
+    aspp_unpack_dw_kernel<<<cdiv(Cin, UDW_CI), 256, (size_t)UDW_CI * ws.NP * sizeof(float), st>>>(
         part, ws.S, gp, n_active, n_cls, Cin, ws.NP);
     ASN_LAUNCH_CHECK();
   }

@@ -309,6 +309,10 @@ struct PackArgs {  // blockIdx.y = 0..3: conv1..conv4, 4: classifier -- one laun
   int C4;
 };
 
+// One CTA per (32 output channels x 16 input channels) block of a layer: its 32 x 16 x 16 fp32 weights are read as
+// 1 KB contiguous runs into shared memory and leave as 32- / 64-byte runs of the two bf16 layouts (ci fastest in Wf, co
+// fastest in Wd) -- every global access of the pack is a full sector.
+constexpr int PK_CO = 32, PK_CI = 16;
 __global__ void __launch_bounds__(256) fcd_pack_all_kernel(const PackArgs a) {
   if (blockIdx.y == 4) {  // classifier weights [1][C][4][4] -> fp32 [16][C]
     for (int i = blockIdx.x * 256 + threadIdx.x; i < 16 * a.C4; i += gridDim.x * 256) {
@@ -318,51 +322,43 @@ __global__ void __launch_bounds__(256) fcd_pack_all_kernel(const PackArgs a) {
     if (blockIdx.x == 0 && threadIdx.x == 0) a.bc[0] = __ldg(a.b[4]);
     return;
   }
-  const int l = blockIdx.y + 1;
-  const float* __restrict__ w = a.w[blockIdx.y];
-  const float* __restrict__ b = a.b[blockIdx.y];
-  __nv_bfloat16* __restrict__ wf = a.wf[blockIdx.y];
-  __nv_bfloat16* __restrict__ wd = a.wd[blockIdx.y];
-  float* __restrict__ bias = a.bias[blockIdx.y];
-  const int Cout = a.Cout[blockIdx.y], Cin_real = a.Cin_real[blockIdx.y], Cin_rows = a.Cin_rows[blockIdx.y];
+  const int li = blockIdx.y, l = li + 1;
+  const float* __restrict__ w = a.w[li];
+  __nv_bfloat16* __restrict__ wf = a.wf[li];
+  __nv_bfloat16* __restrict__ wd = a.wd[li];
+  const int Cout = a.Cout[li], Cin_real = a.Cin_real[li], Cin_rows = a.Cin_rows[li];
+  const int ci_blocks = (Cin_rows + PK_CI - 1) / PK_CI, co_blocks = Cout / PK_CO;  // Cout is a multiple of 64
+  if ((int)blockIdx.x >= ci_blocks * co_blocks) return;
+  const int co0 = (blockIdx.x / ci_blocks) * PK_CO, ci0 = (blockIdx.x % ci_blocks) * PK_CI;
+  __shared__ float t[PK_CO][PK_CI * 16 + 1];  // [co][ci * 16 + kh * 4 + kw]
+  for (int e = threadIdx.x; e < PK_CO * PK_CI * 16; e += 256) {
+    const int col = e % (PK_CI * 16), co = e / (PK_CI * 16);
+    const int ci = ci0 + col / 16;
+    t[co][col] = ci < Cin_real ? __ldg(w + ((int64_t)(co0 + co) * Cin_real + ci0) * 16 + col) : 0.f;  // padded channels: 0
+  }
+  if (blockIdx.x % ci_blocks == 0 && threadIdx.x < PK_CO) a.bias[li][co0 + threadIdx.x] = __ldg(a.b[li] + co0 + threadIdx.x);
+  __syncthreads();
+  // forward pack Wf[co][k]: conv1 k = (kh*2 + kw/2)*64 + (kw%2)*32 + ci (512 per row); else k = (kh*4 + kw)*Cin + ci
   const int Kf = l == 1 ? 512 : 16 * Cin_real;
-  const int64_t nf = (int64_t)Cout * Kf;
+  for (int e = threadIdx.x; e < PK_CO * 16 * PK_CI; e += 256) {
+    const int cil = e % PK_CI, tap = (e / PK_CI) % 16, co = e / (PK_CI * 16);
+    const int kh = tap >> 2, kw = tap & 3;
+    const int ci = ci0 + cil;
+    if (ci >= Cin_rows) continue;
+    const int k = l == 1 ? (kh * 2 + (kw >> 1)) * 64 + (kw & 1) * 32 + ci : tap * Cin_real + ci;
+    wf[(int64_t)(co0 + co) * Kf + k] = __float2bfloat16(t[co][cil * 16 + tap]);
+  }
+  // dgrad pack Wd[z = (rh,rw)][ci][(th*2 + tw)*Cout + co], kh = kh(rh, th): rh = 0 -> {1,3}, rh = 1 -> {0,2}
   const int Kd = 4 * Cout;
-  const int64_t nd = (int64_t)4 * Cin_rows * Kd;
-  const int64_t total = nf + nd + Cout;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    if (i < nf) {
-      const int co = (int)(i / Kf), k = (int)(i % Kf);
-      int ci, kh, kw;
-      if (l == 1) {
-        const int t = k / 64, r = k % 64;
-        kh = t / 2;
-        kw = (t % 2) * 2 + r / 32;
-        ci = r % 32;
-      } else {
-        const int t = k / Cin_real;
-        ci = k % Cin_real;
-        kh = t / 4;
-        kw = t % 4;
-      }
-      float v = ci < Cin_real ? __ldg(w + (((int64_t)co * Cin_real + ci) * 4 + kh) * 4 + kw) : 0.f;
-      wf[i] = __float2bfloat16(v);
-    } else if (i < nf + nd) {
-      const int64_t j = i - nf;
-      const int k = (int)(j % Kd);
-      const int ci = (int)((j / Kd) % Cin_rows);
-      const int z = (int)(j / ((int64_t)Kd * Cin_rows));
-      const int rh = z / 2, rw = z % 2;
-      const int t = k / Cout, co = k % Cout;
-      const int th = t / 2, tw = t % 2;
-      const int kh = rh == 0 ? (th == 0 ? 1 : 3) : (th == 0 ? 0 : 2);
-      const int kw = rw == 0 ? (tw == 0 ? 1 : 3) : (tw == 0 ? 0 : 2);
-      float v = ci < Cin_real ? __ldg(w + (((int64_t)co * Cin_real + ci) * 4 + kh) * 4 + kw) : 0.f;
-      wd[j] = __float2bfloat16(v);
-    } else {
-      const int co = (int)(i - nf - nd);
-      bias[co] = __ldg(b + co);
-    }
+  for (int e = threadIdx.x; e < 16 * PK_CI * PK_CO; e += 256) {
+    const int col = e % PK_CO, cil = (e / PK_CO) % PK_CI, zt = e / (PK_CO * PK_CI);   // zt = z*4 + t
+    const int z = zt >> 2, tt = zt & 3;
+    const int rh = z >> 1, rw = z & 1, th = tt >> 1, tw = tt & 1;
+    const int kh = rh == 0 ? (th == 0 ? 1 : 3) : (th == 0 ? 0 : 2);
+    const int kw = rw == 0 ? (tw == 0 ? 1 : 3) : (tw == 0 ? 0 : 2);
+    const int ci = ci0 + cil;
+    if (ci >= Cin_rows) continue;
+    wd[((int64_t)z * Cin_rows + ci) * Kd + tt * Cout + co0 + col] = __float2bfloat16(t[col][cil * 16 + kh * 4 + kw]);
   }
 }
 
@@ -972,8 +968,10 @@ extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, 
   a.bc = reinterpret_cast<float*>(base + p.bc_off);
   a.C4 = p.C[4];
   prof::Scope ps("fcd_pack_weights", 0, bytes, st);
-  // grid.x sized for the largest layer (conv4), grid-stride elsewhere
-  fcd_pack_all_kernel<<<dim3((unsigned)cdiv(cdiv(max_total, 256), 4), 5), 256, 0, st>>>(a);
+  (void)max_total;
+  int blocks = 1;
+  for (int i = 0; i < 4; ++i) blocks = max(blocks, (a.Cout[i] / PK_CO) * cdiv(a.Cin_rows[i], PK_CI));
+  fcd_pack_all_kernel<<<dim3((unsigned)blocks, 5), 256, 0, st>>>(a);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }

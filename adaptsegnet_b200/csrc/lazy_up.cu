@@ -91,7 +91,7 @@ struct Args {
   __nv_bfloat16* a0;         // PACK: out [N][H][W0p][32];  DBWD: in (dA0)
   int W0p;
   // CE / DBWD
-  float* partial;            // [N][strips][xblocks][JB][3*C]
+  float* partial;            // [N][strips][xblocks][3*C][JB]
 };
 
 __device__ __forceinline__ void store_px32_bf16(__nv_bfloat16* dst, const float* v) {
@@ -260,14 +260,23 @@ lazy_strip_kernel(const Args a) {
         for (int jl = li + 1; jl <= g.JB; ++jl) xs[jl] = LZ_COLS;
     }
     __syncthreads();
+    // partial block layout [k*C + c][jl] (jl fastest: what the reduce kernel's neighbouring threads read); staged in
+    // shared memory when it is small (the 8x upsampling of the training shapes: JB = 19) so that it leaves coalesced
+    constexpr int STAGE_JB = 24;
+    __shared__ float outs[LZ_R * C * STAGE_JB];
     float* part = a.partial + (((int64_t)n * g.strips + strip) * g.xblocks + xb) * (int64_t)(LZ_R * C * g.JB);
+    const bool staged = g.JB <= STAGE_JB;
     for (int item = tid; item < LZ_R * C * g.JB; item += LZ_COLS) {
       const int ck = item % (LZ_R * C), jl = item / (LZ_R * C);  // a warp walks one x-range over 32 rows of S
       float sum = 0.f;
       for (int x = xs[jl]; x < xs[jl + 1]; ++x) sum += s_l0[x] * S[ck][x];
       if (jl > 0)
         for (int x = xs[jl - 1]; x < xs[jl]; ++x) sum += s_l1[x] * S[ck][x];
-      part[item] = sum;
+      if (staged) outs[ck * g.JB + jl] = sum; else part[ck * g.JB + jl] = sum;
+    }
+    if (staged) {
+      __syncthreads();
+      for (int e = tid; e < LZ_R * C * g.JB; e += LZ_COLS) part[e] = outs[e];
     }
 
     if (FUNC == F_CE) {
@@ -345,7 +354,7 @@ lazy_reduce_kernel(const Geom g, const float* __restrict__ partial, float* __res
       const int jl = j - lerp_at(min(b * LZ_COLS, g.W - 1), g.sx, g.w).i0;
       if (jl < 0 || jl >= g.JB) continue;
       sum += __ldg(partial + (((int64_t)n * g.strips + s) * g.xblocks + b) * (int64_t)(LZ_R * C * g.JB) +
-                   (int64_t)jl * (LZ_R * C) + (k * C + c));
+                   (int64_t)(k * C + c) * g.JB + jl);
     }
   }
   float scale = 1.f;
