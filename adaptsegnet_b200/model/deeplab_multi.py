@@ -117,8 +117,19 @@ class ResNetMulti(nn.Module):
     def _make_pred_layer(self, block, inplanes, dilation_series, padding_series, num_classes):
         return block(inplanes, list(dilation_series), list(padding_series), num_classes)
 
+    # Execution mode of the (unchanged) trunk modules, SURVEY.md 8f row 1: run them under torch.autocast(bfloat16).
+    # Off by default -- the reference computes the trunk in fp32 (TF32 on the GPU); the heads always receive fp32 features.
+    trunk_autocast = False
+
     def trunk(self, x):
         """ResNet-101 features: (layer3 output, layer4 output), both H/8 x W/8."""
+        if self.trunk_autocast and x.is_cuda:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                f3, f4 = self._trunk(x)
+            return f3.float(), f4.float()
+        return self._trunk(x)
+
+    def _trunk(self, x):
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         f3 = self.layer3(self.layer2(self.layer1(x)))
         return f3, self.layer4(f3)

@@ -90,7 +90,7 @@ class AdaptSegTrainer:
     """Holds G (DeeplabMulti), D1/D2 (FCDiscriminator), their optimizers and runs iterations."""
 
     def __init__(self, cfg: TrainConfig | None = None, device="cuda", model=None, model_D1=None, model_D2=None,
-                 use_cuda_graph=False, channels_last=False, fused_optimizers=None):
+                 use_cuda_graph=False, channels_last=False, fused_optimizers=None, trunk_bf16=False):
         """``use_cuda_graph``: capture everything of an iteration up to the gradients (both G forwards/backwards,
         all discriminator passes, ~2 300 kernel launches) into one CUDA graph and replay it; the gradient
         all-reduce and the three optimizer steps stay eager.  Same kernels, same order, no per-launch CPU cost."""
@@ -103,6 +103,8 @@ class AdaptSegTrainer:
         self._graph = None
         self.multi = cfg.level == "multi-level"
         self.model = (model or DeeplabMulti(cfg.num_classes)).to(self.device).train()
+        if trunk_bf16:   # execution mode of the untouched trunk; the hot path is unaffected
+            self.model.trunk_autocast = True
         if self.channels_last:
             # execution detail of the unchanged trunk: cuDNN's sm_100 kernels are NHWC, so an NCHW trunk spends a
             # quarter of its time in layout conversions; the head kernels take the channels_last features as they are

@@ -49,6 +49,12 @@ def parse():
     ap.add_argument("--no-kernel-events", action="store_true", help="skip the per-kernel event pass (ncu runs)")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--trunk-dtype", default="tf32", choices=["tf32", "bf16"],
+                    help="tf32: the trunk as the reference's GPU path computes it; bf16: the trunk modules under "
+                         "torch.autocast(bfloat16) (execution mode of the untouched trunk, SURVEY.md 8f row 1)")
+    ap.add_argument("--also-trunk-bf16", type=int, default=1,
+                    help="after the headline measurement, time the same step once more with the trunk under bf16 autocast "
+                         "and report it under 'trunk_bf16_autocast' (never the headline)")
     ap.add_argument("--tier", default="B", choices=["A", "B"],
                     help="B: low-res logits feed the fused upsample+softmax+CE kernel and the discriminators' input pack "
                          "(no full-res logits in HBM, SURVEY.md 8d); A: the reference's tensor-by-tensor chain")
@@ -178,8 +184,8 @@ def workload_config(args, world):
                 "hot_path": "libasn_b200 sm_100a kernels (tcgen05 heads + discriminators, fused losses)",
                 "execution": ("forward/backward of the iteration replayed as one CUDA graph; all-reduce + optimizers eager"
                               if args.cuda_graph else "eager"),
-                "trunk": ("ResNet-101 as PyTorch modules on cuDNN (TF32" + (", channels_last" if args.channels_last else "")
-                          + "), timed, not rewritten"),
+                "trunk": ("ResNet-101 as PyTorch modules on cuDNN (" + ("bf16 autocast" if args.trunk_dtype == "bf16" else "TF32")
+                          + (", channels_last" if args.channels_last else "") + "), timed, not rewritten"),
                 "tier": ("B: upsample fused into its consumers (CE loss, discriminator input pack); no full-res logits in HBM"
                          if args.tier == "B" else "A: interp -> loss / softmax -> D tensor by tensor, as the reference"),
                 "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed"})
@@ -208,7 +214,8 @@ def run_b200(args):
 
     torch.manual_seed(SEED)  # identical replicas
     trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"), device=dev,
-                              use_cuda_graph=bool(args.cuda_graph), channels_last=bool(args.channels_last))
+                              use_cuda_graph=bool(args.cuda_graph), channels_last=bool(args.channels_last),
+                              trunk_bf16=args.trunk_dtype == "bf16")
     src_h, lab_h, tgt_h = TR.synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
     src_h, lab_h, tgt_h = src_h.pin_memory(), lab_h.pin_memory(), tgt_h.pin_memory()
     src, lab, tgt = src_h.to(dev), lab_h.to(dev), tgt_h.to(dev)
@@ -361,6 +368,28 @@ def run_b200(args):
                 "hot_path_ms_per_step": hot_ms, "hot_path_kernels": breakdown}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan)
+    # ---- extra (never the headline): the same step with the untouched trunk under bf16 autocast ----
+    extra = None
+    if args.also_trunk_bf16 and args.trunk_dtype != "bf16":
+        try:
+            del trainer
+            torch.cuda.empty_cache()
+            torch.manual_seed(SEED)
+            trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"),
+                                      device=dev, use_cuda_graph=bool(args.cuda_graph),
+                                      channels_last=bool(args.channels_last), trunk_bf16=True)
+            for _ in range(max(args.warmup, 3) + 1):
+                step_resident(0)
+            ms_bf16 = timed(args.steps, step_resident)
+            extra = {"value": world * 1000.0 / (ms_bf16 / args.steps), "unit": UNIT, "ms_per_step": ms_bf16 / args.steps,
+                     "note": "ResNet-101 trunk modules under torch.autocast(bfloat16) (SURVEY.md 8f row 1); hot path "
+                             "unchanged (fp32 features in, same kernels).  Reported for information: the headline runs the "
+                             "trunk in TF32 like the reference's own GPU path"}
+        except Exception as exc:  # noqa: BLE001
+            extra = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+    if rank == 0:
+        if extra is not None:
+            line["trunk_bf16_autocast"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

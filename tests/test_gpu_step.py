@@ -134,3 +134,24 @@ def test_cuda_graph_replay_equals_eager():
         eager.optimizer.step()       # move every weight so that the next replay must re-pack them
         eager.optimizer_D1.step()
         eager.optimizer_D2.step()
+
+
+def test_trunk_bf16_autocast_mode():
+    """Execution mode of the untouched trunk: its modules under torch.autocast(bfloat16).  The hot
+    path still receives fp32 features and runs the same kernels.  The trunk itself is outside the parity contract (its
+    arithmetic is torch's); this only checks that the mode is wired correctly: finite losses close to the TF32 run
+    (bf16 rounding through 101 layers with batch-1 BatchNorm at random init: a few per cent) and gradients everywhere."""
+    from adaptsegnet_b200.train_step import AdaptSegTrainer, TrainConfig
+    outs = []
+    for bf16 in (False, True):
+        torch.manual_seed(0)
+        tr = AdaptSegTrainer(TrainConfig(lazy_upsample=True), device="cuda", channels_last=True, trunk_bf16=bf16)
+        src, lab, tgt = (t.cuda() for t in TR.synthetic_batch(SEED, (129, 257), (97, 193)))
+        out = tr.step(src, lab, tgt, do_optimizer_step=False)
+        torch.cuda.synchronize()
+        outs.append({k: v.item() for k, v in out.items()})
+        assert tr.flat_G.flat.isfinite().all() and tr.flat_G.flat.abs().sum().item() > 0
+        assert tr.model.conv1.weight.dtype == torch.float32 and tr.model.conv1.weight.grad.dtype == torch.float32
+    for k in outs[0]:
+        assert np.isfinite(outs[1][k])
+        assert abs(outs[1][k] - outs[0][k]) <= 0.15 * abs(outs[0][k]) + 1e-3, (k, outs[0][k], outs[1][k])
