@@ -773,6 +773,29 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
     P.ox[z] = rw + (l == 1 ? 1 : 0);  // packed input: pixel w lives at padded column w + 1
   }
   P.b_rows_per_z = rows;
+  // Thin layers (<= 64 input channels), opt-in with ASN_DGRAD4=1: all four parity classes in one CTA (MODE_DGRAD4).
+  // The 16 (class, tap) products read only NINE distinct shifts of dPre; each shifted tile is fetched once and feeds
+  // every class that uses it (-29 % operand bytes into the SM).  Parity-tested, but measured 2x SLOWER on B200
+  // (conv2 dgrad 0.24 -> 0.47 ms/step): the stage grows to 48 KB, only three fit, and these layers run at
+  // bytes-in-flight / latency -- see profiles/README.md.  Off by default.
+  static const bool d4_on = getenv("ASN_DGRAD4") != nullptr && getenv("ASN_DGRAD4")[0] == '1';
+  const bool d4 = d4_on && tile_rows == 128 && rows == bn && (bn == 32 || bn == 64);
+  if (d4) {
+    for (int sh = 0; sh < 9; ++sh) {
+      const int dh = sh / 3 - 1, dw = sh % 3 - 1;
+      int n = 0;
+      for (int z = 0; z < 4; ++z)
+        for (int t = 0; t < 4; ++t)
+          if (P.tap_dh[z * 4 + t] == dh && P.tap_dw[z * 4 + t] == dw) {
+            P.d4_z[sh][n] = z;
+            P.d4_t[sh][n] = t;
+            ++n;
+          }
+      P.d4_n[sh] = n;
+    }
+    P.k_steps = 9 * P.c_chunks;
+    P.steps_per_split = P.k_steps;
+  }
   P.epi = EPI_BF16;
   P.out = din;
   P.ld_out = rows;
@@ -786,8 +809,12 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(rows, bn), 4);
   static const char* names[5] = {"", "fcd_conv1_dgrad", "fcd_conv2_dgrad", "fcd_conv3_dgrad", "fcd_conv4_dgrad"};
   // reads dPre_l and the mask source A_{l-1}, writes dIn (same size as A_{l-1})
-  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l),
-                layer_bytes(p, l, 0) + (l > 1 ? layer_bytes(p, l, 1) : 0.0) + 2.0 * 4 * rows * K, tile_rows);
+  const double bytes = layer_bytes(p, l, 0) + (l > 1 ? layer_bytes(p, l, 1) : 0.0) + 2.0 * 4 * rows * K;
+  if (d4) {
+    dim3 grid4(p.N * P.tiles_h * P.tiles_w, 1, 1);
+    return launch(MODE_DGRAD4, bn, maps, P, grid4, st, names[l], layer_flops(p, l), bytes, 4 * 128);
+  }
+  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l), bytes, tile_rows);
 }
 
 static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* act_in, float* part,

@@ -91,7 +91,7 @@ struct Shape {
   static constexpr int ctas_per_sm = EW == 4 ? 2 : 1;
   static constexpr int b_tile = (((BLOCK_N / CL) * 128 + 1023) / 1024) * 1024;
   // K-major modes: MT row tiles of A per B tile; WGRAD: MT taps' B tiles per A tile
-  static constexpr int stage = MODE == MODE_WGRAD ? 16384 + MT * b_tile : MT * 16384 + b_tile;
+  static constexpr int stage = (MODE == MODE_WGRAD || MODE == MODE_DGRAD4) ? 16384 + MT * b_tile : MT * 16384 + b_tile;
   static constexpr int fit = ((EW == 4 ? 100 : 184) * 1024) / stage;
   static constexpr int stages = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
@@ -177,6 +177,7 @@ bool block_n_supported(int mode, int block_n) {
     case MODE_CONV: return block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256;
     case MODE_WGRAD: return block_n == 64 || block_n == 128 || block_n == 256;
     case MODE_GEMM_MN: return block_n == 128 || block_n == 192 || block_n == 256;
+    case MODE_DGRAD4: return block_n == 32 || block_n == 64;
   }
   return false;
 }
@@ -223,6 +224,8 @@ int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, di
   ASN_CASE(MODE_WGRAD, 64, 1, 1)
   ASN_CASE(MODE_WGRAD, 128, 1, 1)
   ASN_CASE(MODE_WGRAD, 256, 1, 1)
+  ASN_CASE(MODE_DGRAD4, 32, 1, 4)
+  ASN_CASE(MODE_DGRAD4, 64, 1, 4)
   ASN_CASE(MODE_WGRAD, 64, 1, 2)
   ASN_CASE(MODE_WGRAD, 64, 1, 4)
   ASN_CASE(MODE_WGRAD, 128, 1, 2)

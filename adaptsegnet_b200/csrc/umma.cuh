@@ -245,7 +245,9 @@ enum {
   MODE_GEMM = 0,     // C = A[M][K] . B[N][K]^T, both K-contiguous
   MODE_CONV = 1,
   MODE_WGRAD = 2,
-  MODE_GEMM_MN = 3   // C = A^T . B for A[K][M], B[K][N] (M / N contiguous): 2-D flavour of the WGRAD operand fetch
+  MODE_GEMM_MN = 3,  // C = A^T . B for A[K][M], B[K][N] (M / N contiguous): 2-D flavour of the WGRAD operand fetch
+  MODE_DGRAD4 = 4    // stride-2 transposed conv, all four output-parity classes in one CTA: k-steps walk the NINE
+                     // distinct input shifts; each shifted A tile feeds the 1, 2 or 4 classes that use it
 };
 enum {
   EPI_F32 = 0,   // fp32 store
@@ -270,6 +272,8 @@ struct Params {
   int tap_dh[MAX_Z * MAX_TAPS];  // box origin offset (rows) of the tap
   int tap_dw[MAX_Z * MAX_TAPS];  // box origin offset (cols) of the tap
   int b_rows_per_z;              // CONV: row offset of B per blockIdx.z (dgrad parity classes)
+  // DGRAD4: for input shift s = (dh+1)*3 + (dw+1): the classes z that read it and the tap index t of that class
+  int d4_n[9], d4_z[9][4], d4_t[9][4];
   int a_boxes;                   // WGRAD: 64-channel boxes of A actually loaded (1 or 2)
   // ---- epilogue ----
   int epi;
@@ -329,8 +333,8 @@ struct SmemLayout {
 
 // the stage layout of umma_kernel<MODE, BLOCK_N, STAGES, CL, MT, EW> (shared with the launcher)
 template <int MODE, int BLOCK_N, int STAGES, int CL, int MT, int EW>
-using KernelSmem = SmemLayout<BLOCK_N, STAGES, (MODE == MODE_WGRAD && MT > 1 ? 1 : MT), EW, CL,
-                              (MODE == MODE_WGRAD && MT > 1 ? MT : 1)>;
+using KernelSmem = SmemLayout<BLOCK_N, STAGES, (((MODE == MODE_WGRAD && MT > 1) || MODE == MODE_DGRAD4) ? 1 : MT), EW, CL,
+                              (((MODE == MODE_WGRAD && MT > 1) || MODE == MODE_DGRAD4) ? MT : 1)>;
 
 struct TileCoord {
   int z, n0, m0, img, oh0, ow0, wg_tap, ks_begin, nsteps;
@@ -357,7 +361,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int 
     t.n0 = by * BLOCK_N;
     t.ks_begin = t.z * P.steps_per_split;
     ks_end = min(P.k_steps, t.ks_begin + P.steps_per_split);
-  } else if (MODE == MODE_CONV) {
+  } else if (MODE == MODE_CONV || MODE == MODE_DGRAD4) {
     t.ow0 = (bx % P.tiles_w) * P.tw;
     t.oh0 = ((bx / P.tiles_w) % P.tiles_h) * P.th;
     t.img = bx / (P.tiles_w * P.tiles_h);
@@ -381,8 +385,10 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
   constexpr bool MULTI_TAP = MODE == MODE_WGRAD && MT > 1;
+  constexpr bool MULTI_B = MULTI_TAP || MODE == MODE_DGRAD4;  // MT accumulators fed by MT B tiles from one A tile
   using L = KernelSmem<MODE, BLOCK_N, STAGES, CL, MT, EW>;
-  static_assert(!MULTI_TAP || CL == 1, "multi-tap weight-gradient tiles run on single CTAs");
+  static_assert(!MULTI_B || CL == 1, "multi-accumulator tiles run on single CTAs");
+  static_assert(MODE != MODE_DGRAD4 || MT == 4, "DGRAD4: one accumulator per output-parity class");
   constexpr int EPI_CHUNK = EpiCfg<EW>::chunk, EPI_PITCH = EpiCfg<EW>::pitch;
   constexpr int CPL = EPI_CHUNK / 4;  // columns per lane on the way out (8 or 4)
   static_assert(EW == 8 || 2 * TmemCols<BLOCK_N, MT>::value <= 512, "two CTAs per SM need <= 256 TMEM columns each");
@@ -499,6 +505,14 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             tma_load_4d(amaps[P.tap_map[e]], sa, full_bar(s), cc * BLOCK_K, t.ow0 + P.tap_dw[e],
                         t.oh0 + P.tap_dh[e], t.img);
             tma_load_2d(&map_b, sb, full_bar(s), ks * BLOCK_K, t.z * P.b_rows_per_z + t.n0);
+          } else if (MODE == MODE_DGRAD4) {
+            const int sh = ks / P.c_chunks, cc = ks - sh * P.c_chunks;
+            const int nb = P.d4_n[sh];
+            mbar_arrive_expect_tx(full_bar(s), L::A_BYTES + nb * L::B_BYTES);
+            tma_load_4d(&map_a0, sa, full_bar(s), cc * BLOCK_K, t.ow0 + (sh % 3) - 1, t.oh0 + (sh / 3) - 1, t.img);
+            for (int j = 0; j < nb; ++j)
+              tma_load_2d(&map_b, sb + j * L::B_TILE, full_bar(s), (P.d4_t[sh][j] * P.c_chunks + cc) * BLOCK_K,
+                          P.d4_z[sh][j] * P.b_rows_per_z + t.n0);
           } else if (MODE == MODE_GEMM_MN) {
             // k-step = 64 rows of K: A = columns [m0, m0+128) of A[K][M], B = columns [n0, n0+BLOCK_N) of B[K][N]
             const uint32_t box_bytes = 64 * 64 * 2;
@@ -543,6 +557,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N);
+        uint32_t started = 0;  // DGRAD4: classes whose accumulator already holds a partial sum
         for (int i = 0; i < t.nsteps; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -550,34 +565,51 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
+          if constexpr (MODE == MODE_DGRAD4) {
+            const int sh = (t.ks_begin + i) / P.c_chunks;
+            const int nb = P.d4_n[sh];
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            uint64_t da, db;
-            if (MN_MAJOR) {
-              // MN-major, SW128: 64-channel chunks LBO = 64 px * 128 B apart, 8-pixel groups SBO = 1 KB apart;
-              // advancing K by 16 pixels = 2 KB
-              da = make_smem_desc(sa + k * 2048, 8192, 1024);
-              db = make_smem_desc(sb + k * 2048, 8192, 1024);
-            } else {
-              // K-major, SW128: 8-row groups SBO = 1 KB apart; advancing K by 16 elements = 32 B inside the row
-              da = make_smem_desc(sa + k * 32, 16, 1024);
-              db = make_smem_desc(sb + k * 32, 16, 1024);
-            }
-            if (CL == 2) mma_f16_ss_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            else mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            if (MULTI_TAP) {  // the other taps of the group: same A (dY), their own B (X at the tap) and accumulator
-#pragma unroll
-              for (int j = 1; j < MT; ++j) {
-                const uint64_t dbj = make_smem_desc(sb + j * L::B_TILE + k * 2048, 8192, 1024);
-                mma_f16_ss(tmem_d + j * BLOCK_N, da, dbj, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
+              for (int j = 0; j < nb; ++j) {
+                const int z = P.d4_z[sh][j];
+                const uint64_t dbj = make_smem_desc(sb + j * L::B_TILE + k * 32, 16, 1024);
+                mma_f16_ss(tmem_d + z * BLOCK_N, da, dbj, idesc, (((started >> z) & 1u) || k > 0) ? 1u : 0u);
               }
-            } else if (MT == 2) {  // rows 128..255 of the tile: next 16 KB of the A stage, same B
-              const uint64_t da1 = make_smem_desc(sa + BLOCK_M * BLOCK_K * 2 + k * 32, 16, 1024);
-              mma_f16_ss(tmem_d + BLOCK_N, da1, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
             }
+            for (int j = 0; j < nb; ++j) started |= 1u << P.d4_z[sh][j];
+            mma_commit(empty_bar(s));
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              uint64_t da, db;
+              if (MN_MAJOR) {
+                // MN-major, SW128: 64-channel chunks LBO = 64 px * 128 B apart, 8-pixel groups SBO = 1 KB apart;
+                // advancing K by 16 pixels = 2 KB
+                da = make_smem_desc(sa + k * 2048, 8192, 1024);
+                db = make_smem_desc(sb + k * 2048, 8192, 1024);
+              } else {
+                // K-major, SW128: 8-row groups SBO = 1 KB apart; advancing K by 16 elements = 32 B inside the row
+                da = make_smem_desc(sa + k * 32, 16, 1024);
+                db = make_smem_desc(sb + k * 32, 16, 1024);
+              }
+              if (CL == 2) mma_f16_ss_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              else mma_f16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              if (MULTI_TAP) {  // the other taps of the group: same A (dY), their own B (X at the tap) and accumulator
+#pragma unroll
+                for (int j = 1; j < MT; ++j) {
+                  const uint64_t dbj = make_smem_desc(sb + j * L::B_TILE + k * 2048, 8192, 1024);
+                  mma_f16_ss(tmem_d + j * BLOCK_N, da, dbj, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+              } else if (MT == 2) {  // rows 128..255 of the tile: next 16 KB of the A stage, same B
+                const uint64_t da1 = make_smem_desc(sa + BLOCK_M * BLOCK_K * 2 + k * 32, 16, 1024);
+                mma_f16_ss(tmem_d + BLOCK_N, da1, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            // frees the stage (in both CTAs of a pair) once these MMAs have read it
+            if (CL == 1) mma_commit(empty_bar(s)); else mma_commit_pair(empty_bar(s), CL_MASK);
+        
           }
-          // frees the stage (in both CTAs of a pair) once these MMAs have read it
-          if (CL == 1) mma_commit(empty_bar(s)); else mma_commit_pair(empty_bar(s), CL_MASK);
         }
         // accumulator of this tile complete (pair: both halves, each CTA's epilogue waits on its own copy)
         if (CL == 1) mma_commit(tmem_full_bar(acc)); else mma_commit_pair(tmem_full_bar(acc), CL_MASK);
@@ -610,17 +642,18 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       for (int sub = 0; sub < MT; ++sub) {
         const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N) + sub * BLOCK_N;
         {  // row table: thread = row
-          const int r = (MULTI_TAP ? 0 : sub * BLOCK_M) + q * 32 + lane;
+          const int r = (MULTI_B ? 0 : sub * BLOCK_M) + q * 32 + lane;
           bool row_ok;
           long long row_off;
           if (MODE == MODE_GEMM || MODE == MODE_GEMM_MN) {
             row_ok = t.valid && (t.m0 + r) < P.M;
             row_off = (long long)t.z * P.z_stride_out + (long long)(t.m0 + r) * P.ld_out;
-          } else if (MODE == MODE_CONV) {
+          } else if (MODE == MODE_CONV || MODE == MODE_DGRAD4) {
+            const int zc = MODE == MODE_DGRAD4 ? sub : t.z;  // output-parity class of this accumulator
             const int dy = r / P.tw, dx = r - dy * P.tw;
             const int oh = t.oh0 + dy, ow = t.ow0 + dx;
-            row_ok = t.valid && oh < P.oh_ext[t.z] && ow < P.ow_ext[t.z];
-            const int fh = oh * P.sy + P.oy[t.z], fw = ow * P.sx + P.ox[t.z];
+            row_ok = t.valid && oh < P.oh_ext[zc] && ow < P.ow_ext[zc];
+            const int fh = oh * P.sy + P.oy[zc], fw = ow * P.sx + P.ox[zc];
             row_off = (((long long)t.img * P.out_h + fh) * P.out_w + fw) * P.ld_out;
           } else {
             row_ok = (t.m0 + r) < P.M;
