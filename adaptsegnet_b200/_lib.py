@@ -23,6 +23,7 @@ SIGNATURES = {
     "asn_prof_enable": (c_int, [c_int]),
     "asn_prof_report": (c_int64, [C.c_char_p, c_int64]),
     "asn_fast_hist": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "asn_fast_hist_lut": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "asn_upsample_bilinear_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "asn_upsample_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "asn_upsample_bilinear_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,

@@ -7,6 +7,8 @@
 // and adds into a warp-private shared-memory histogram.  One 64-bit global
 // atomic per non-zero bin per CTA at the end.  Algorithmic bytes: 2 B/px (u8
 // labels) or 9 B/px (i64 labels, as the reference holds them).
+// Optional 256-entry LUT applied to the labels on the way in: compute_iou.py:24-28 (label_mapping, one full pass over
+// the label image per mapping entry in the reference) fused into the counting.
 #include "common.cuh"
 
 namespace asn {
@@ -19,50 +21,61 @@ struct LabelLoad;  // loads 16 consecutive labels as int (-1 = invalid for any o
 
 template <>
 struct LabelLoad<uint8_t> {
-  static __device__ __forceinline__ void load16(const uint8_t* p, int n, int* a) {
+  static __device__ __forceinline__ void load16(const uint8_t* p, int n, int* a, const uint8_t* lut) {
     uint4 v = ld_stream(reinterpret_cast<const uint4*>(p));
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       int x = (w[i >> 2] >> ((i & 3) * 8)) & 0xff;
+      if (lut) x = lut[x];
       a[i] = x < n ? x : -1;
     }
   }
-  static __device__ __forceinline__ int load1(const uint8_t* p, int n) {
+  static __device__ __forceinline__ int load1(const uint8_t* p, int n, const uint8_t* lut) {
     int x = *p;
+    if (lut) x = lut[x];
     return x < n ? x : -1;
   }
 };
 template <>
 struct LabelLoad<int32_t> {
-  static __device__ __forceinline__ void load16(const int32_t* p, int n, int* a) {
+  // labels outside [0, 256) are not in the LUT: label_mapping leaves them unchanged (and they are invalid anyway)
+  static __device__ __forceinline__ int map1(uint32_t x, int n, const uint8_t* lut) {
+    if (lut && x < 256u) x = lut[x];
+    return x < (uint32_t)n ? (int)x : -1;
+  }
+  static __device__ __forceinline__ void load16(const int32_t* p, int n, int* a, const uint8_t* lut) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[j * 4 + i] = w[i] < (uint32_t)n ? (int)w[i] : -1;
+      for (int i = 0; i < 4; ++i) a[j * 4 + i] = map1(w[i], n, lut);
     }
   }
-  static __device__ __forceinline__ int load1(const int32_t* p, int n) {
-    uint32_t x = (uint32_t)*p;
-    return x < (uint32_t)n ? (int)x : -1;
+  static __device__ __forceinline__ int load1(const int32_t* p, int n, const uint8_t* lut) {
+    return map1((uint32_t)*p, n, lut);
   }
 };
 template <>
 struct LabelLoad<int64_t> {
-  static __device__ __forceinline__ void load16(const int64_t* p, int n, int* a) {
+  static __device__ __forceinline__ int map1(uint32_t lo, uint32_t hi, int n, const uint8_t* lut) {
+    if (hi != 0u) return -1;  // negative or >= 2^32: never valid, never in the LUT
+    if (lut && lo < 256u) lo = lut[lo];
+    return lo < (uint32_t)n ? (int)lo : -1;
+  }
+  static __device__ __forceinline__ void load16(const int64_t* p, int n, int* a, const uint8_t* lut) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
-      // little endian: (x,y) = first int64, (z,w) = second; valid iff high word 0 and low < n
-      a[j * 2 + 0] = (v.y == 0u && v.x < (uint32_t)n) ? (int)v.x : -1;
-      a[j * 2 + 1] = (v.w == 0u && v.z < (uint32_t)n) ? (int)v.z : -1;
+      // little endian: (x,y) = first int64, (z,w) = second; valid iff high word 0 and (mapped) low word < n
+      a[j * 2 + 0] = map1(v.x, v.y, n, lut);
+      a[j * 2 + 1] = map1(v.z, v.w, n, lut);
     }
   }
-  static __device__ __forceinline__ int load1(const int64_t* p, int n) {
-    unsigned long long x = (unsigned long long)*p;
-    return x < (unsigned long long)n ? (int)x : -1;
+  static __device__ __forceinline__ int load1(const int64_t* p, int n, const uint8_t* lut) {
+    const unsigned long long x = (unsigned long long)*p;
+    return map1((uint32_t)x, (uint32_t)(x >> 32), n, lut);
   }
 };
 
@@ -94,10 +107,13 @@ template <typename LabelT>
 __global__ void __launch_bounds__(HIST_THREADS)
 fast_hist_kernel(const LabelT* __restrict__ label, const uint8_t* __restrict__ pred, int64_t n_px,
                  int n_cls, int n_sub, unsigned long long* __restrict__ hist,
-                 unsigned long long* __restrict__ overflow, int vec_ok) {
+                 unsigned long long* __restrict__ overflow, int vec_ok, const uint8_t* __restrict__ lut_g) {
   extern __shared__ uint32_t sh[];
+  __shared__ uint8_t lut_s[256];
   const int nbins = n_cls * n_cls;
   for (int i = threadIdx.x; i < nbins * n_sub; i += HIST_THREADS) sh[i] = 0;
+  if (lut_g) lut_s[threadIdx.x] = lut_g[threadIdx.x];  // HIST_THREADS == 256
+  const uint8_t* lut = lut_g ? lut_s : nullptr;
   __syncthreads();
   uint32_t* myh = sh + ((threadIdx.x >> 5) % n_sub) * nbins;
 
@@ -107,7 +123,7 @@ fast_hist_kernel(const LabelT* __restrict__ label, const uint8_t* __restrict__ p
   int64_t n_vec = vec_ok ? (n_px >> 4) : 0;  // chunks of 16 pixels
   for (int64_t c = tid; c < n_vec; c += nthreads) {
     int a[16];
-    LabelLoad<LabelT>::load16(label + c * 16, n_cls, a);
+    LabelLoad<LabelT>::load16(label + c * 16, n_cls, a, lut);
     uint4 pv = ld_stream(reinterpret_cast<const uint4*>(pred + c * 16));
     uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
@@ -118,7 +134,7 @@ fast_hist_kernel(const LabelT* __restrict__ label, const uint8_t* __restrict__ p
     }
   }
   for (int64_t i = n_vec * 16 + tid; i < n_px; i += nthreads) {
-    int a = LabelLoad<LabelT>::load1(label + i, n_cls);
+    int a = LabelLoad<LabelT>::load1(label + i, n_cls, lut);
     int idx = a >= 0 ? a * n_cls + (int)pred[i] : -1;
     agg.push(idx, myh, nbins);
   }
@@ -134,7 +150,8 @@ fast_hist_kernel(const LabelT* __restrict__ label, const uint8_t* __restrict__ p
 
 template <typename LabelT>
 static int launch_hist(const void* label, const uint8_t* pred, int64_t n_px, int n_cls,
-                       int64_t* hist, int64_t* overflow, cudaStream_t st) {
+                       int64_t* hist, int64_t* overflow, const uint8_t* lut, cudaStream_t st) {
+  static_assert(HIST_THREADS == 256, "the kernel stages the 256-entry LUT with one thread per entry");
   const int nbins = n_cls * n_cls;
   int n_sub = (48 * 1024) / (nbins * 4);
   if (n_sub > HIST_WARPS) n_sub = HIST_WARPS;
@@ -148,15 +165,15 @@ static int launch_hist(const void* label, const uint8_t* pred, int64_t n_px, int
   fast_hist_kernel<LabelT><<<grid, HIST_THREADS, (size_t)n_sub * nbins * 4, st>>>(
       static_cast<const LabelT*>(label), pred, n_px, n_cls, n_sub,
       reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(overflow),
-      vec_ok);
+      vec_ok, lut);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
 
 }  // namespace asn
 
-extern "C" int asn_fast_hist(const void* label, int label_dtype, const uint8_t* pred, int64_t n_px,
-                             int n_cls, int64_t* hist, int64_t* overflow, void* stream) {
+static int fast_hist_impl(const void* label, int label_dtype, const uint8_t* lut, const uint8_t* pred, int64_t n_px,
+                          int n_cls, int64_t* hist, int64_t* overflow, void* stream) {
   using namespace asn;
   ASN_CHECK_ARG(n_px >= 0 && n_cls >= 1 && n_cls <= 255, "asn_fast_hist: bad n_px/n_cls");
   ASN_CHECK_ARG(hist && overflow, "asn_fast_hist: null output");
@@ -164,10 +181,21 @@ extern "C" int asn_fast_hist(const void* label, int label_dtype, const uint8_t* 
   ASN_CHECK_ARG(label && pred, "asn_fast_hist: null input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (label_dtype) {
-    case ASN_LABEL_U8: return launch_hist<uint8_t>(label, pred, n_px, n_cls, hist, overflow, st);
-    case ASN_LABEL_I32: return launch_hist<int32_t>(label, pred, n_px, n_cls, hist, overflow, st);
-    case ASN_LABEL_I64: return launch_hist<int64_t>(label, pred, n_px, n_cls, hist, overflow, st);
+    case ASN_LABEL_U8: return launch_hist<uint8_t>(label, pred, n_px, n_cls, hist, overflow, lut, st);
+    case ASN_LABEL_I32: return launch_hist<int32_t>(label, pred, n_px, n_cls, hist, overflow, lut, st);
+    case ASN_LABEL_I64: return launch_hist<int64_t>(label, pred, n_px, n_cls, hist, overflow, lut, st);
   }
   set_error("asn_fast_hist: unknown label_dtype %d", label_dtype);
   return ASN_EINVAL;
+}
+
+extern "C" int asn_fast_hist(const void* label, int label_dtype, const uint8_t* pred, int64_t n_px,
+                             int n_cls, int64_t* hist, int64_t* overflow, void* stream) {
+  return fast_hist_impl(label, label_dtype, nullptr, pred, n_px, n_cls, hist, overflow, stream);
+}
+
+extern "C" int asn_fast_hist_lut(const void* label, int label_dtype, const uint8_t* lut256, const uint8_t* pred,
+                                 int64_t n_px, int n_cls, int64_t* hist, int64_t* overflow, void* stream) {
+  ASN_CHECK_ARG(lut256, "asn_fast_hist_lut: null LUT");
+  return fast_hist_impl(label, label_dtype, lut256, pred, n_px, n_cls, hist, overflow, stream);
 }

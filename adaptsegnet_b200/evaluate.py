@@ -24,8 +24,10 @@ class ConfusionMatrix:
         self.hist = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=device)
         self.overflow = torch.zeros(1, dtype=torch.int64, device=device)
 
-    def update(self, label: torch.Tensor, pred: torch.Tensor):
-        _, ovf = ops.fast_hist(label.reshape(-1), pred.reshape(-1), self.n, hist=self.hist)
+    def update(self, label: torch.Tensor, pred: torch.Tensor, lut: torch.Tensor | None = None):
+        """``lut`` (ops.mapping_lut): raw dataset ids are mapped to train ids inside the kernel
+        (label_mapping + fast_hist of compute_iou.py:55-57 in one pass over the frame)."""
+        _, ovf = ops.fast_hist(label.reshape(-1), pred.reshape(-1), self.n, hist=self.hist, lut=lut)
         self.overflow += ovf
 
     def all_reduce(self, group=None):

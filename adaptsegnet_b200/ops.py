@@ -60,8 +60,24 @@ def precision_mode() -> str:
 # --------------------------------------------------------------------------------------
 # K7 fast_hist
 # --------------------------------------------------------------------------------------
-def fast_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: torch.Tensor | None = None):
-    """compute_iou.py:15-17 on the device.  Returns (hist int64 [n,n], overflow int64 [1])."""
+def mapping_lut(mapping, device) -> torch.Tensor:
+    """256-entry uint8 LUT of compute_iou.py:24-28 (label_mapping): lut[src] = dst for every (src, dst) row of
+    ``mapping`` (later rows win, as the reference's successive passes over the ORIGINAL labels do), identity elsewhere."""
+    lut = list(range(256))
+    for src, dst in mapping:
+        src, dst = int(src), int(dst)
+        if 0 <= src < 256:
+            if not 0 <= dst < 256:
+                raise ValueError(f"label_mapping target {dst} does not fit the 8-bit LUT")
+            lut[src] = dst
+        # sources outside [0,256) cannot occur in 8-bit label PNGs; wider labels with such ids stay unmapped
+    return torch.tensor(lut, dtype=torch.uint8, device=device)
+
+
+def fast_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: torch.Tensor | None = None,
+              lut: torch.Tensor | None = None):
+    """compute_iou.py:15-17 on the device.  Returns (hist int64 [n,n], overflow int64 [1]).
+    ``lut`` (uint8[256], see mapping_lut): label_mapping (compute_iou.py:24-28) fused into the counting."""
     label = _req(label, None, "label")
     pred = _req(pred, torch.uint8, "pred")
     if label.dtype not in _LABEL_CODE:
@@ -72,8 +88,16 @@ def fast_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: torch.T
         hist = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=label.device)
     overflow = torch.zeros(1, dtype=torch.int64, device=label.device)
     lib = _lib.load()
-    check(lib.asn_fast_hist(label.data_ptr(), _LABEL_CODE[label.dtype], pred.data_ptr(), label.numel(), n_cls,
-                            hist.data_ptr(), overflow.data_ptr(), _stream()), "asn_fast_hist")
+    if lut is not None:
+        lut = _req(lut, torch.uint8, "lut")
+        if lut.numel() != 256:
+            raise ValueError("lut must have 256 entries")
+        check(lib.asn_fast_hist_lut(label.data_ptr(), _LABEL_CODE[label.dtype], lut.data_ptr(), pred.data_ptr(),
+                                    label.numel(), n_cls, hist.data_ptr(), overflow.data_ptr(), _stream()),
+              "asn_fast_hist_lut")
+    else:
+        check(lib.asn_fast_hist(label.data_ptr(), _LABEL_CODE[label.dtype], pred.data_ptr(), label.numel(), n_cls,
+                                hist.data_ptr(), overflow.data_ptr(), _stream()), "asn_fast_hist")
     _count()
     return hist, overflow
 

@@ -77,6 +77,12 @@ ASN_API int64_t asn_prof_report(char* buf_host, int64_t capacity);
  * ---------------------------------------------------------------------------------- */
 ASN_API int asn_fast_hist(const void* label, int label_dtype, const uint8_t* pred, int64_t n_px,
                   int n_cls, int64_t* hist, int64_t* overflow, void* stream);
+/* same with compute_iou.py:24-28 (label_mapping) fused in: labels in [0,256) are replaced by lut256[label]
+ * (device, 256 x uint8; identity for ids the mapping does not mention) before counting; other labels are left as
+ * they are, like the reference's `output[input == src] = dst` passes.  Replaces label_mapping + fast_hist at
+ * compute_iou.py:55-57. */
+ASN_API int asn_fast_hist_lut(const void* label, int label_dtype, const uint8_t* lut256, const uint8_t* pred,
+                      int64_t n_px, int n_cls, int64_t* hist, int64_t* overflow, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K2 / K2b / K9  bilinear resize, align_corners=True.

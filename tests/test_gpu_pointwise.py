@@ -242,3 +242,29 @@ def test_conv_f32_oracle(ops, cfg):
     assert rel_err(host(dx), dxr) < 1e-5
     dw, db = ops.conv2d_wgrad_f32(cuda(x), cuda(dy), w.shape, s, p, d)
     assert rel_err(host(dw), dwr) < 1e-5 and rel_err(host(db), dbr) < 1e-5
+
+
+# ---------------------------------------------------------------- K7 + label_mapping
+CITYSCAPES_LABEL2TRAIN = [[0, 255], [1, 255], [2, 255], [3, 255], [4, 255], [5, 255], [6, 255], [7, 0], [8, 1], [9, 255],
+                          [10, 255], [11, 2], [12, 3], [13, 4], [14, 255], [15, 255], [16, 255], [17, 5], [18, 255], [19, 6],
+                          [20, 7], [21, 8], [22, 9], [23, 10], [24, 11], [25, 12], [26, 13], [27, 14], [28, 15], [29, 255],
+                          [30, 255], [31, 16], [32, 17], [33, 18], [-1, 255]]
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int32, np.int64])
+def test_fast_hist_with_label_mapping(ops, dtype):
+    """label_mapping (compute_iou.py:24-28) fused into fast_hist == the reference's two steps, bit for bit"""
+    rng = np.random.default_rng(21)
+    n_px = 1024 * 2048 + 3
+    raw = rng.integers(0, 34, n_px).astype(np.int64)
+    if dtype != np.uint8:
+        raw[rng.random(n_px) < 0.01] = -1
+        raw[rng.random(n_px) < 0.01] = 300
+    pred = rng.integers(0, 19, n_px).astype(np.uint8)
+    ref = O.fast_hist(O.label_mapping(raw, CITYSCAPES_LABEL2TRAIN), pred, 19)
+    lut = ops.mapping_lut(CITYSCAPES_LABEL2TRAIN, "cuda")
+    hist, ovf = ops.fast_hist(cuda(raw.astype(dtype)), cuda(pred), 19, lut=lut)
+    assert np.array_equal(host(hist), ref) and int(ovf.item()) == 0
+    from adaptsegnet_b200 import compute_iou as CI
+    assert np.array_equal(CI.fast_hist(raw.astype(dtype), pred, 19, mapping=CITYSCAPES_LABEL2TRAIN), ref)
+    assert np.array_equal(CI.label_mapping(raw, CITYSCAPES_LABEL2TRAIN), O.label_mapping(raw, CITYSCAPES_LABEL2TRAIN))
