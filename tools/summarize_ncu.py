@@ -9,11 +9,20 @@ from collections import defaultdict
 
 def short(name):
     name = re.sub(r"\(.*", "", name)
-    m = re.search(r"umma_kernel<\(int\)(\d), \(int\)(\d+), \(int\)(\d+)>", name)
+    m = re.search(r"umma_kernel<\(int\)(\d), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>", name)
     if m:
-        return f"asn::umma::umma_kernel<mode={m.group(1)},BN={m.group(2)},stages={m.group(3)}>"
+        return (f"asn::umma::umma_kernel<mode={m.group(1)},BN={m.group(2)},stages={m.group(3)},CL={m.group(4)},"
+                f"MT={m.group(5)},EW={m.group(6)}>")
     name = re.sub(r"^void ", "", name)
     return name[:110]
+
+
+OURS = re.compile(r"asn::|umma::|lazy::|^(aspp_|fcd_|lazy_|ce_kernel|ce_finalize|ce_generic|softmax_kernel|softmax_generic|"
+                  r"sgd_step|adam_step|upsample_|fast_hist|gan_loss|nchw_|nhwc_)")
+
+
+def is_ours(short_name):
+    return bool(OURS.search(short_name))
 
 
 def main():
@@ -35,7 +44,7 @@ def main():
         a[0] += 1
         a[1] += ns
     total = sum(v[1] for v in agg.values())
-    mine = sum(v[1] for k, v in agg.items() if "asn::" in k)
+    mine = sum(v[1] for k, v in agg.items() if is_ours(k))
     out = [f"# ncu launch list summary: {path}", "",
            f"{len(rows)} launches, {total / 1e6:.2f} ms of serialised device time; "
            f"libasn_b200 kernels {mine / 1e6:.2f} ms = {100 * mine / total:.1f} % of it", "",
