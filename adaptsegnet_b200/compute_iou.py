@@ -41,6 +41,9 @@ def label_mapping(input, mapping):
     lut = ops.mapping_lut(mapping, t.device).to(torch.int64)
     in_range = (t >= 0) & (t < 256)
     out = torch.where(in_range, lut[t.clamp(0, 255)], t)
+    for src, dst in mapping:          # ids an 8-bit label image cannot hold (e.g. Cityscapes' -1): mapped one by one
+        if not 0 <= int(src) < 256:
+            out = torch.where(t == int(src), torch.full_like(out, int(dst)), out)
     return out.cpu().numpy() if as_numpy else out
 
 
