@@ -23,7 +23,7 @@ int rows_per_cta(int mode, long long m_tiles_128, long long other);
 
 // BLOCK_N choices compiled for each mode
 bool block_n_supported(int mode, int block_n);
-// 1 or 2: with 2, encode the B tensor map with box rows block_n / 2 (each CTA of a pair multicasts its half)
+// 1 or 2: with 2 (CTA pairs, cta_group::2), encode the B tensor map with box rows block_n / 2 (each CTA loads its half)
 int cluster_size(int mode, int block_n);
 
 }  // namespace umma

@@ -77,10 +77,21 @@ class FlatParams:
         torch._C._increment_version(self.params)
 
     def all_reduce_mean(self, group=None):
+        self.all_reduce_finish(self.all_reduce_start(group), group)
+
+    def all_reduce_start(self, group=None):
+        """asynchronous SUM all-reduce of the flat gradient buffer (None when there is nothing to reduce)"""
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        return None
+
+    def all_reduce_finish(self, work, group=None):
+        import torch.distributed as dist
+
+        if work is not None:
+            work.wait()
             self.flat.mul_(1.0 / dist.get_world_size(group))
 
 

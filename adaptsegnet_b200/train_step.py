@@ -79,10 +79,21 @@ class FlatGrads:
         self.flat.zero_()
 
     def all_reduce_mean(self, group=None):
+        self.all_reduce_finish(self.all_reduce_start(group), group)
+
+    def all_reduce_start(self, group=None):
+        """asynchronous SUM all-reduce of the flat gradient buffer (None when there is nothing to reduce)"""
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        return None
+
+    def all_reduce_finish(self, work, group=None):
+        import torch.distributed as dist
+
+        if work is not None:
+            work.wait()
             self.flat.mul_(1.0 / dist.get_world_size(group))
 
 
@@ -164,6 +175,13 @@ class AdaptSegTrainer:
 
     def _grads_step(self, src_images, src_labels, tgt_images):
         """Everything of train...:578-679: forwards, losses, backwards; gradients end up in the flat buffers."""
+        out, carry = self._g_part(src_images, src_labels, tgt_images)
+        out.update(self._d_part(carry))
+        return out
+
+    def _g_part(self, src_images, src_labels, tgt_images):
+        """train...:578-633: the generator's two forward/backward passes.  After it the generator's gradient is final.
+        Returns (losses, what the discriminator part needs)."""
         cfg = self.cfg
         it = cfg.iter_size
         self.flat_G.zero()
@@ -218,8 +236,13 @@ class AdaptSegTrainer:
             out["loss_adv_target1"] = loss_adv1.detach() / it
         (loss / it).backward()
         out["loss_adv_target2"] = loss_adv2.detach() / it
+        return out, (pred1.detach(), pred2.detach(), pred_target1.detach(), pred_target2.detach(), saved, up_s, up_t)
 
-        # ---------------- train D (train...:635-679) ----------------
+    def _d_part(self, carry):
+        """train...:635-679: both discriminators on the (detached) source and target predictions."""
+        pred1, pred2, pred_target1, pred_target2, saved, up_s, up_t = carry
+        it = self.cfg.iter_size
+        out = {}
         self._set_requires_grad(self.model_D1, True)
         self._set_requires_grad(self.model_D2, True)
         levels = [(self.model_D2, pred2, pred_target2, "loss_D2", "D2")]
@@ -237,7 +260,9 @@ class AdaptSegTrainer:
         return out
 
     def _capture(self, src_images, src_labels, tgt_images):
-        """warm up on a side stream (cuDNN autotuning, lazy kernel attributes), then capture one _grads_step"""
+        """warm up on a side stream (cuDNN autotuning, lazy kernel attributes), then capture one iteration as TWO graphs
+        sharing a memory pool: the generator part and the discriminator part.  Between their replays step() starts the
+        all-reduce of the (by then final) generator gradient, which overlaps the discriminator part."""
         self._static_in = (src_images.clone(), src_labels.clone(), tgt_images.clone())
         bn_state = {k: v.clone() for k, v in self.model.state_dict().items()
                     if k.endswith(("running_mean", "running_var", "num_batches_tracked"))}
@@ -250,9 +275,15 @@ class AdaptSegTrainer:
         self.model.load_state_dict(bn_state, strict=False)  # the warm-up must not count as training steps
         for pk in self._packs():
             pk.invalidate()                                  # weight packing becomes part of the graph
+        # both captures (and the warm-up above) on ONE stream: autograd ties every parameter's gradient accumulation to
+        # the stream it first ran on
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._static_out = self._grads_step(*self._static_in)
+        with torch.cuda.graph(self._graph, stream=side):
+            out_g, self._carry = self._g_part(*self._static_in)   # (kept alive: the D graph reads these buffers)
+        self._graph_d = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_d, pool=self._graph.pool(), stream=side):
+            out_d = self._d_part(self._carry)
+        self._static_out = {**out_g, **out_d}
         self.model.load_state_dict(bn_state, strict=False)  # capture does not execute, but keep it explicit
 
     def step(self, src_images, src_labels, tgt_images, i_iter=0, group=None, do_optimizer_step=True):
@@ -266,11 +297,15 @@ class AdaptSegTrainer:
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
             self._graph.replay()
+            pending = self.flat_G.all_reduce_start(group)   # 178 MB over NVLink while the discriminators train
+            self._graph_d.replay()
             out = self._static_out
         else:
-            out = self._grads_step(src_images, src_labels, tgt_images)
+            out, carry = self._g_part(src_images, src_labels, tgt_images)
+            pending = self.flat_G.all_reduce_start(group)
+            out.update(self._d_part(carry))
         # ---------------- data-parallel averaging, then the three optimizer steps ----------------
-        self.flat_G.all_reduce_mean(group)
+        self.flat_G.all_reduce_finish(pending, group)
         self.flat_D2.all_reduce_mean(group)
         if self.multi:
             self.flat_D1.all_reduce_mean(group)
