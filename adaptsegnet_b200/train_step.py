@@ -112,6 +112,7 @@ class AdaptSegTrainer:
         self.use_cuda_graph = bool(use_cuda_graph)
         self.channels_last = bool(channels_last)
         self._graph = None
+        self._capture_stream = None   # the stream warm-up and capture ran on (autograd remembers it per parameter)
         self.multi = cfg.level == "multi-level"
         self.model = (model or DeeplabMulti(cfg.num_classes)).to(self.device).train()
         if trunk_bf16:   # execution mode of the untouched trunk; the hot path is unaffected
@@ -266,7 +267,7 @@ class AdaptSegTrainer:
         self._static_in = (src_images.clone(), src_labels.clone(), tgt_images.clone())
         bn_state = {k: v.clone() for k, v in self.model.state_dict().items()
                     if k.endswith(("running_mean", "running_var", "num_batches_tracked"))}
-        side = torch.cuda.Stream()
+        side = self._capture_stream = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):

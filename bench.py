@@ -182,7 +182,8 @@ def workload_config(args, world):
         return cfg
     cfg.update({"parallelism": f"dp{world} (NCCL all-reduce of 3 flat gradient buffers per step)",
                 "hot_path": "libasn_b200 sm_100a kernels (tcgen05 heads + discriminators, fused losses)",
-                "execution": ("forward/backward of the iteration replayed as one CUDA graph; all-reduce + optimizers eager"
+                "execution": ("forward/backward of the iteration replayed as two CUDA graphs (generator part, discriminator "
+                              "part; the generator's gradient all-reduce overlaps the second); fused optimizer steps eager"
                               if args.cuda_graph else "eager"),
                 "trunk": ("ResNet-101 as PyTorch modules on cuDNN (" + ("bf16 autocast" if args.trunk_dtype == "bf16" else "TF32")
                           + (", channels_last" if args.channels_last else "") + "), timed, not rewritten"),
@@ -300,13 +301,19 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     trainer.use_cuda_graph = False
-    step_resident(0)
-    prof.enable(True)
-    launches0 = prof.launch_count()
-    ms_eager = timed(args.steps, step_resident)
-    launches = prof.launch_count() - launches0  # same kernels per step in the graph replays of the timed region
-    kernels = prof.report()
-    prof.enable(False)
+    # on the stream the graphs were captured on: autograd keeps each parameter's gradient accumulation on the stream of
+    # its first backward, and would warn about (and synchronise for) a different one
+    ev_stream = getattr(trainer, "_capture_stream", None) or torch.cuda.current_stream()
+    ev_stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(ev_stream):
+        step_resident(0)
+        prof.enable(True)
+        launches0 = prof.launch_count()
+        ms_eager = timed(args.steps, step_resident)
+        launches = prof.launch_count() - launches0  # same kernels per step in the graph replays of the timed region
+        kernels = prof.report()
+        prof.enable(False)
+    torch.cuda.current_stream().wait_stream(ev_stream)
     trainer.use_cuda_graph = graph_mode
 
     if rank == 0:
