@@ -39,6 +39,19 @@ def _worker(rank, world, port, out_dir):
     flat.all_reduce_mean()
     torch.save({"local": local, "avg": [p.grad.clone() for p in net.parameters() if p.requires_grad]},
                os.path.join(out_dir, f"r{rank}.pt"))
+    # the fused-optimizer storage (parameters AND gradients flat) with the split start / finish all-reduce the trainer
+    # uses to overlap the generator's reduction with the discriminator part
+    from adaptsegnet_b200.optim import FlatParams
+    torch.manual_seed(0)
+    net2 = nn.Sequential(nn.Conv2d(3, 4, 3), nn.Conv2d(4, 2, 1))
+    fp = FlatParams(net2.parameters())
+    torch.manual_seed(200 + rank)
+    net2(torch.randn(2, 3, 8, 8)).square().mean().backward()
+    local2 = fp.flat.clone()
+    pending = fp.all_reduce_start()
+    assert pending is not None
+    fp.all_reduce_finish(pending)
+    torch.save({"local": local2, "avg": fp.flat.clone()}, os.path.join(out_dir, f"f{rank}.pt"))
     # eval: per-rank confusion matrices summed exactly
     rng = np.random.RandomState(rank)
     hist = torch.from_numpy(rng.randint(0, 1000, (19, 19)).astype(np.int64))
@@ -56,5 +69,8 @@ def test_flat_grad_allreduce_and_hist_sum(tmp_path):
         mean = (r[0]["local"][k] + r[1]["local"][k]) / 2
         assert torch.allclose(r[0]["avg"][k], mean, atol=1e-7)
         assert torch.equal(r[0]["avg"][k], r[1]["avg"][k])
+    f = [torch.load(tmp_path / f"f{i}.pt") for i in range(world)]
+    assert torch.allclose(f[0]["avg"], (f[0]["local"] + f[1]["local"]) / 2, atol=1e-7)
+    assert torch.equal(f[0]["avg"], f[1]["avg"])
     h = [torch.load(tmp_path / f"h{i}.pt") for i in range(world)]
     assert torch.equal(h[0]["total"], h[0]["hist"] + h[1]["hist"]) and torch.equal(h[0]["total"], h[1]["total"])
