@@ -189,6 +189,9 @@ def workload_config(args, world):
                           + (", channels_last" if args.channels_last else "") + "), timed, not rewritten"),
                 "tier": ("B: upsample fused into its consumers (CE loss, discriminator input pack); no full-res logits in HBM"
                          if args.tier == "B" else "A: interp -> loss / softmax -> D tensor by tensor, as the reference"),
+                "dedup": "the D-step's forward on the target prediction re-uses the activations of the G-step's identical "
+                         "forward (same weights, same input: train...:617-618 vs :665-666) instead of recomputing them -- "
+                         "SURVEY.md 8d's 544.6 GF variant; every other pass of the reference iteration is executed",
                 "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed"})
     return cfg
 
