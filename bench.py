@@ -205,7 +205,7 @@ def run_b200(args):
 
     from adaptsegnet_b200 import ops, prof
     from adaptsegnet_b200.train_step import AdaptSegTrainer, TrainConfig
-    from oracle import torch_ref as TR  # synthetic_batch only (input generator); never on the timed path
+    from adaptsegnet_b200.utils.synthetic import synthetic_batch   # (this arm never imports oracle/)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,7 +220,7 @@ def run_b200(args):
     trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"), device=dev,
                               use_cuda_graph=bool(args.cuda_graph), channels_last=bool(args.channels_last),
                               trunk_bf16=args.trunk_dtype == "bf16")
-    src_h, lab_h, tgt_h = TR.synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
+    src_h, lab_h, tgt_h = synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
     src_h, lab_h, tgt_h = src_h.pin_memory(), lab_h.pin_memory(), tgt_h.pin_memory()
     src, lab, tgt = src_h.to(dev), lab_h.to(dev), tgt_h.to(dev)
 
