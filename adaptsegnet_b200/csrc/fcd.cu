@@ -662,10 +662,19 @@ static int encode_plain(CUtensorMap* m, const __nv_bfloat16* base, int N, int H,
   return umma::encode_4d(m, base, dims, str, tw, th);
 }
 
+namespace halo {  // halo.cu: conv1 forward from shared-memory halo tiles (ASN_HALO=0 falls back to the ring kernel)
+int conv1_fwd(const __nv_bfloat16* in, const __nv_bfloat16* wf, const float* bias, __nv_bfloat16* out, int N, int H0,
+              int W0p, int OH, int OW, float slope, double flops, double bytes, cudaStream_t st);
+}
+
 static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv_bfloat16* wf, const float* bias,
                     __nv_bfloat16* out, cudaStream_t st) {
   using namespace umma;
   const int OH = p.H[l], OW = p.W[l], Cout = p.C[l];
+  static const bool use_halo = !(getenv("ASN_HALO") != nullptr && getenv("ASN_HALO")[0] == '0');
+  if (use_halo && l == 1 && Cout == 64)
+    return halo::conv1_fwd(in, wf, bias, out, p.N, p.H[0], p.W0p, OH, OW, FCD_SLOPE, layer_flops(p, l),
+                           layer_bytes(p, l, 0) + 2.0 * Cout * 512, st);
   int th = 1, tw = 128;
   pick_tile(OH, OW, 128, &th, &tw);
   const int bn_guess = block_n_for(Cout, (long long)p.N * cdiv(OH, th) * cdiv(OW, tw));
