@@ -229,5 +229,237 @@ int conv1_fwd(const __nv_bfloat16* in, const __nv_bfloat16* wf, const float* bia
   return ASN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// conv2 data gradient (dPre2 [H2][W2][128] -> dPre1 [H1][W1][64], x LeakyReLU mask of A1) with the same construction.
+// The transposed 4x4/s2 convolution splits into four output-parity classes (rh, rw) of 2x2 taps each; the 16
+// (class, tap) products read only the nine shifts (dh, dw) in {-1,0,1}^2 of dPre2.  Per base tile (7 x 16 positions
+// (i, j); class (rh, rw) writes pixel (2i+rh, 2j+rw)) ONE (7+2) x (16+2) halo tile per 64-channel chunk is loaded and
+// every product is an MMA over the 128-row window starting at row (dh+1)*18 + (dw+1).  A CTA owns the two classes of one
+// row parity rh (blockIdx.x & 1): their 2 x 4 taps x 2 chunks of weights (128 KB) stay resident in shared memory, the
+// halo chunks stream through a 3-stage ring, the two class accumulators are double buffered in TMEM (256 columns).
+// Per base tile 2 x 41 KB enter the SMs instead of 672 KB.
+constexpr int D_TH = 7, D_TW = 16, D_PITCH = D_TW + 2;   // 18
+constexpr int D_BOX_H = D_TH + 2;                        // 9
+constexpr int D_BOX_BYTES = D_BOX_H * D_PITCH * 128;     // 162 rows x 128 B = 20736
+constexpr int D_STAGE = 21504;                           // 168 rows: the last window (row 38 + 127 = 165) stays inside
+constexpr int D_NSTAGE = 3;
+constexpr int D_THREADS = 320;                           // producer, MMA issuer, 8 epilogue warps
+constexpr int D_CHUNK = 16, D_EPI_PITCH = 20;            // epilogue staging: 16 columns per pass, 20 floats per row
+
+struct DLayout {
+  static constexpr int A_OFF = 0;
+  static constexpr int W_OFF = D_NSTAGE * D_STAGE;       // 64512 = 63 KB
+  static constexpr int W_BYTES = 16 * 8192;              // 2 classes x 4 taps x 2 chunks x [64 rows][64 k]
+  static constexpr int BAR_OFF = W_OFF + W_BYTES;
+  static constexpr int STG_OFF = BAR_OFF + 128;
+  static constexpr int ROW_OFF = STG_OFF + 8 * 32 * D_EPI_PITCH * 4;
+  static constexpr int TOTAL = ROW_OFF + 8 * 32 * 8 + 1024;
+};
+static_assert(DLayout::W_OFF % 1024 == 0 && D_STAGE % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned bases");
+static_assert(DLayout::TOTAL <= 227 * 1024, "shared memory budget");
+
+struct DArgs {
+  int N, Hin, Win, tiles_h, tiles_w;   // Hin x Win = size of dPre1 (= A1); tiles over the base grid ceil(Hin/2) x ceil(Win/2)
+  const __nv_bfloat16* mask_src;       // A1 (post-LeakyReLU activation): gradient x (A1 > 0 ? 1 : mask_slope)
+  float mask_slope;
+  __nv_bfloat16* out;                  // dPre1 [N][Hin][Win][64]
+};
+
+__global__ void __launch_bounds__(D_THREADS, 1)
+conv2_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const DArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar = base + DLayout::BAR_OFF;
+  const uint32_t w_bar = bar;
+  auto full_bar = [&](int s) { return bar + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar + 8u * (4 + s); };
+  auto tfull_bar = [&](int s) { return bar + 8u * (7 + s); };
+  auto tempty_bar = [&](int s) { return bar + 8u * (9 + s); };
+  const uint32_t holder = bar + 8u * 11;
+  volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen + DLayout::BAR_OFF + 88);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rh = blockIdx.x & 1;                       // the row parity whose two classes (rw = 0, 1) this CTA computes
+  const int first_tile = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
+  const int total_tiles = a.N * a.tiles_h * a.tiles_w;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    mbar_init(w_bar, 1);
+    for (int s = 0; s < D_NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(holder, 256);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *holder_ptr;
+  const uint32_t sw = base + DLayout::W_OFF;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: Wd rows (z*64 + ci), K = t*128 + co; tile ((zi*4 + t)*2 + cc) = [64 ci][64 co of chunk cc]
+      mbar_arrive_expect_tx(w_bar, DLayout::W_BYTES);
+      for (int zi = 0; zi < 2; ++zi)
+        for (int t = 0; t < 4; ++t)
+          for (int cc = 0; cc < 2; ++cc)
+            tma_load_2d(&map_w, sw + ((zi * 4 + t) * 2 + cc) * 8192, w_bar, t * 128 + cc * 64, (rh * 2 + zi) * 64);
+      uint32_t kit = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        const int tx = tile % a.tiles_w, ty = (tile / a.tiles_w) % a.tiles_h, img = tile / (a.tiles_w * a.tiles_h);
+        for (int cc = 0; cc < 2; ++cc, ++kit) {
+          const int s = kit % D_NSTAGE;
+          const uint32_t ph = (kit / D_NSTAGE) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), D_BOX_BYTES);
+          // halo tile of chunk cc: base positions (ty*7 - 1 .. +7, tx*16 - 1 .. +16); outside dPre2 = zero fill
+          tma_load_4d(&map_a, base + DLayout::A_OFF + s * D_STAGE, full_bar(s), cc * 64, tx * D_TW - 1, ty * D_TH - 1, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+      mbar_wait(w_bar, 0);
+      uint32_t kit = 0, tit = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tit) {
+        const int acc = tit & 1;
+        mbar_wait(tempty_bar(acc), ((tit >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int cc = 0; cc < 2; ++cc, ++kit) {
+          const int s = kit % D_NSTAGE;
+          mbar_wait(full_bar(s), (kit / D_NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + DLayout::A_OFF + s * D_STAGE;
+#pragma unroll
+          for (int zi = 0; zi < 2; ++zi) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int thh = t >> 1, tww = t & 1;
+              // rh = 0: kh in {1,3} -> dh = 0, -1;  rh = 1: kh in {0,2} -> dh = +1, 0   (same for the columns with rw = zi)
+              const int dh = rh == 0 ? (thh == 0 ? 0 : -1) : (thh == 0 ? 1 : 0);
+              const int dw = zi == 0 ? (tww == 0 ? 0 : -1) : (tww == 0 ? 1 : 0);
+              const uint32_t ab = sa + ((dh + 1) * D_PITCH + (dw + 1)) * 128;
+              const uint32_t wb = sw + ((zi * 4 + t) * 2 + cc) * 8192;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tmem + acc * 128 + zi * 64, make_smem_desc(ab + k * 32, 16, 1024),
+                           make_smem_desc(wb + k * 32, 16, 1024), idesc, (cc > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          mma_commit(empty_bar(s));
+        }
+        mma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int ew = warp - 2, q = warp & 3;   // TMEM lane quarter this warp may read
+    const int zi = ew >> 2;                  // warps 2..5: class rw = 0, warps 6..9: class rw = 1
+    float* stg = reinterpret_cast<float*>(gen + DLayout::STG_OFF) + ew * (32 * D_EPI_PITCH);
+    long long* row_tab = reinterpret_cast<long long*>(gen + DLayout::ROW_OFF) + ew * 32;
+    const int rr = lane >> 2, cq = lane & 3;
+    uint32_t tit = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tit) {
+      const int acc = tit & 1;
+      const int tx = tile % a.tiles_w, ty = (tile / a.tiles_w) % a.tiles_h, img = tile / (a.tiles_w * a.tiles_h);
+      {
+        const int m = q * 32 + lane;
+        const int dy = m / D_PITCH, dx = m - dy * D_PITCH;
+        const int ih = 2 * (ty * D_TH + dy) + rh, iw = 2 * (tx * D_TW + dx) + zi;
+        const bool ok = dy < D_TH && dx < D_TW && ih < a.Hin && iw < a.Win;
+        __syncwarp();
+        row_tab[lane] = ok ? (((long long)img * a.Hin + ih) * a.Win + iw) * 64 : -1;
+      }
+      mbar_wait(tfull_bar(acc), (tit >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ta = tmem + acc * 128 + zi * 64 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < 64; c += D_CHUNK) {
+        float v[D_CHUNK];
+        __syncwarp();  // the previous pass has finished reading the staging rows
+        tmem_ld16(ta + c, v);
+        float4* srow = reinterpret_cast<float4*>(stg + lane * D_EPI_PITCH);
+#pragma unroll
+        for (int i = 0; i < D_CHUNK / 4; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        __syncwarp();
+        const int n = c + cq * 4;  // this lane's four channels
+        uint2 mk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // masks first: four independent loads in flight
+          const long long off = row_tab[j * 8 + rr];
+          mk[j] = off >= 0 ? __ldg(reinterpret_cast<const uint2*>(a.mask_src + off + n)) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rl = j * 8 + rr;
+          const long long off = row_tab[rl];
+          if (off < 0) continue;
+          const float4 x = *reinterpret_cast<const float4*>(stg + rl * D_EPI_PITCH + cq * 4);
+          float o[4] = {x.x, x.y, x.z, x.w};
+          const uint32_t mw[2] = {mk[j].x, mk[j].y};
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {   // bf16 > 0  <=>  sign bit clear and not zero
+            const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+            o[2 * i] *= (lo != 0u && lo < 0x8000u) ? 1.f : a.mask_slope;
+            o[2 * i + 1] *= (hi != 0u && hi < 0x8000u) ? 1.f : a.mask_slope;
+          }
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+          *reinterpret_cast<uint2*>(a.out + off + n) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem, 256);
+  }
+}
+
+// dpre: dPre2 [N][H2][W2][128]; wd: conv2's dgrad pack [4*64][512]; mask_src: A1 [N][Hin][Win][64]; out: dPre1
+int conv2_dgrad(const __nv_bfloat16* dpre, const __nv_bfloat16* wd, const __nv_bfloat16* mask_src, __nv_bfloat16* out,
+                int N, int Hin, int Win, int H2, int W2, float mask_slope, double flops, double bytes, cudaStream_t st) {
+  CUtensorMap map_a, map_w;
+  int rc;
+  uint64_t dims[4] = {128, (uint64_t)W2, (uint64_t)H2, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)128 * 2, (uint64_t)W2 * 128 * 2, (uint64_t)H2 * W2 * 128 * 2};
+  if ((rc = encode_4d(&map_a, dpre, dims, str, D_PITCH, D_BOX_H))) return rc;
+  if ((rc = encode_2d(&map_w, wd, 512, 4 * 64, 512 * 2, 64))) return rc;
+  DArgs a;
+  a.N = N; a.Hin = Hin; a.Win = Win;
+  a.tiles_h = cdiv(cdiv(Hin, 2), D_TH);
+  a.tiles_w = cdiv(cdiv(Win, 2), D_TW);
+  a.mask_src = mask_src; a.mask_slope = mask_slope; a.out = out;
+  static bool configured = false;
+  if (!configured) {
+    ASN_CUDA(cudaFuncSetAttribute(conv2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DLayout::TOTAL));
+    configured = true;
+  }
+  const long long tiles = (long long)N * a.tiles_h * a.tiles_w;
+  long long ctas = 2 * tiles < sm_count() ? 2 * tiles : sm_count();
+  ctas &= ~1LL;  // pairs of CTAs: row parity 0 / 1
+  if (ctas < 2) ctas = 2;
+  prof::Scope ps("fcd_conv2_dgrad", flops, bytes, st);
+  conv2_dgrad_kernel<<<(unsigned)ctas, D_THREADS, DLayout::TOTAL, st>>>(map_a, map_w, a);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
 }  // namespace halo
 }  // namespace asn
