@@ -752,10 +752,9 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   const int bn = block_n_for(rows, 4LL * p.N * cdiv(eh, th) * cdiv(ew, tw));
   const int tile_rows = rows_per_cta(MODE_CONV, (long long)p.N * cdiv(eh, th) * cdiv(ew, tw), 4LL * cdiv(rows, bn));
   if (tile_rows == 256) pick_tile(eh, ew, 256, &th, &tw);
-  // conv2 (128 -> 64 channels): halo-tile kernel (halo.cu), opt-in with ASN_HALO2=1.  Measured at the very end of round 1:
-  // tests/test_gpu_fcd.py green with it (11 tests: odd sizes, batch 2, backward on saved activations) and
-  // 0.234 -> 0.187 ms per step; it stays opt-in until the whole GPU suite has run with it.
-  static const bool use_halo2 = getenv("ASN_HALO2") != nullptr && getenv("ASN_HALO2")[0] == '1';
+  // conv2 (128 -> 64 channels): halo-tile kernel (halo.cu); ASN_HALO2=0 falls back to the ring kernel.  Default since
+  // round 2: the whole GPU suite (124 tests) ran green with it, 0.234 -> 0.187 ms per step.
+  static const bool use_halo2 = !(getenv("ASN_HALO2") != nullptr && getenv("ASN_HALO2")[0] == '0');
   if (use_halo2 && l == 2 && rows == 64 && Cout == 128)
     return halo::conv2_dgrad(dpre, wd, act_in, din, p.N, Hin, Win, Hout, Wout, FCD_SLOPE, layer_flops(p, l),
                              layer_bytes(p, l, 0) + layer_bytes(p, l, 1) + 2.0 * 4 * rows * 4 * Cout, st);

@@ -9,6 +9,10 @@ namespace asn {
 
 constexpr int UP_THREADS = 256;
 
+// one linear interpolation exactly as ATen's CPU kernel evaluates it: w0 * a + w1 * b with the second product rounded
+// and the first fused into the addition (pinned bit for bit against the reference: tests/golden/eval2.npz)
+__device__ __forceinline__ float lerp3(float w0, float w1, float a, float b) { return __fmaf_rn(w0, a, __fmul_rn(w1, b)); }
+
 // one thread = VEC consecutive output columns; it keeps their x-interpolation (indices + weights) in
 // registers and walks down the rows (nc, Y) assigned to its CTA row-slice, so the per-pixel work is
 // 4 gathers (L1-resident low-res rows) + 6 FMAs and the kernel stays HBM-write-bound.
@@ -234,10 +238,10 @@ upsample_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred, 
       const float* r1 = x + (((int64_t)n * C + c) * h + ly.i1) * w;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        // explicit IEEE mul/add (no FMA contraction): bit-identical to the numpy oracle
-        float top = __fadd_rn(__fmul_rn(lx[k].l0, __ldg(r0 + lx[k].i0)), __fmul_rn(lx[k].l1, __ldg(r0 + lx[k].i1)));
-        float bot = __fadd_rn(__fmul_rn(lx[k].l0, __ldg(r1 + lx[k].i0)), __fmul_rn(lx[k].l1, __ldg(r1 + lx[k].i1)));
-        float v = __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
+        // ATen's CPU kernel (UpSampleKernel.cpp `interpolate`, what the reference's evaluate script runs) computes
+        // each lerp as fma(w0, a, w1 * b): spelled out, so the values -- and the ties -- are the reference's bit for bit
+        const float v = lerp3(ly.l0, ly.l1, lerp3(lx[k].l0, lx[k].l1, __ldg(r0 + lx[k].i0), __ldg(r0 + lx[k].i1)),
+                              lerp3(lx[k].l0, lx[k].l1, __ldg(r1 + lx[k].i0), __ldg(r1 + lx[k].i1)));
         // strict '>' keeps the first maximum (np.argmax); NaN handling: numpy treats the
         // first NaN as the maximum
         if (v > best[k] || (v != v && best[k] == best[k])) {
@@ -255,6 +259,75 @@ upsample_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred, 
       for (int k = 0; k < 4; ++k)
         if (xv * 4 + k < W) dst[k] = (uint8_t)arg[k];
     }
+  }
+}
+
+// K9, two stages: the fork upsamples the heads' logits to the INPUT size inside ResNetMulti.forward
+// (model/deeplab_multi.py:188-189) and evaluate_cityscapes.py:153,163 resizes that again to the label size before the
+// argmax (:168-169).  Two align_corners bilinear resizes compose into one only when (out-1) % (in-1) == 0, which the
+// Cityscapes shapes (64x128 -> 512x1024 -> 1024x2048) do not satisfy, so both stages are computed -- but the 39.8 MB
+// intermediate never leaves the SM: a CTA owns a TH2 x TW2 output tile, interpolates the (few) intermediate pixels the
+// tile touches for all C channels into shared memory (stage 1, from the L1/L2-resident low-res logits), then every
+// thread interpolates its four outputs from shared memory and keeps the first maximum (stage 2).  Per frame 0.6 MB are
+// read and 2 MB written.  Both stages use ATen's op order (lerp3), so the result equals the reference's bit for bit.
+constexpr int TH2 = 8, TW2 = 128;   // output tile: 256 threads x 4 pixels
+__global__ void __launch_bounds__(256)
+upsample2_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred, int N, int C, int h, int w, int Hm,
+                        int Wm, int H, int W, float s1h, float s1w, float s2h, float s2w, int MR, int MC) {
+  extern __shared__ float mid[];  // [C][MR][MC]
+  const int tiles_w = (W + TW2 - 1) / TW2, tiles_h = (H + TH2 - 1) / TH2;
+  const int tx = blockIdx.x % tiles_w, ty = (blockIdx.x / tiles_w) % tiles_h, n = blockIdx.x / (tiles_w * tiles_h);
+  const int Y0 = ty * TH2, X0 = tx * TW2;
+  const int my0 = lerp_at(Y0, s2h, Hm).i0, mx0 = lerp_at(X0, s2w, Wm).i0;   // first intermediate row / column of the tile
+  // ---- stage 1: intermediate pixels (my0 + r, mx0 + c) for all channels ----
+  const float* xn = x + (int64_t)n * C * h * w;
+  for (int i = threadIdx.x; i < MR * MC; i += blockDim.x) {
+    const int r = i / MC, c = i - r * MC;
+    const int my = min(my0 + r, Hm - 1), mx = min(mx0 + c, Wm - 1);
+    const Lerp ly = lerp_at(my, s1h, h), lx = lerp_at(mx, s1w, w);
+    const float* p00 = xn + (int64_t)ly.i0 * w + lx.i0;
+    const int dx = lx.i1 - lx.i0, dy = (ly.i1 - ly.i0) * w;
+    for (int ch = 0; ch < C; ++ch) {
+      const float* p = p00 + (int64_t)ch * h * w;
+      mid[(ch * MR + r) * MC + c] = lerp3(ly.l0, ly.l1, lerp3(lx.l0, lx.l1, __ldg(p), __ldg(p + dx)),
+                                          lerp3(lx.l0, lx.l1, __ldg(p + dy), __ldg(p + dy + dx)));
+    }
+  }
+  __syncthreads();
+  // ---- stage 2: thread = 4 consecutive output pixels of one row ----
+  const int Y = Y0 + (threadIdx.x >> 5), Xb = X0 + (threadIdx.x & 31) * 4;
+  if (Y >= H || Xb >= W) return;
+  const Lerp ly = lerp_at(Y, s2h, Hm);
+  const int r0 = (ly.i0 - my0) * MC, r1 = (ly.i1 - my0) * MC;
+  int c0[4], c1[4];
+  float l0[4], l1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const Lerp lx = lerp_at(min(Xb + k, W - 1), s2w, Wm);
+    c0[k] = lx.i0 - mx0; c1[k] = lx.i1 - mx0; l0[k] = lx.l0; l1[k] = lx.l1;
+  }
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int arg[4] = {0, 0, 0, 0};
+  for (int ch = 0; ch < C; ++ch) {
+    const float* m0 = mid + ch * MR * MC + r0;
+    const float* m1 = mid + ch * MR * MC + r1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = lerp3(ly.l0, ly.l1, lerp3(l0[k], l1[k], m0[c0[k]], m0[c1[k]]), lerp3(l0[k], l1[k], m1[c0[k]], m1[c1[k]]));
+      if (v > best[k] || (v != v && best[k] == best[k])) {   // first maximum; the first NaN wins (numpy)
+        best[k] = v;
+        arg[k] = ch;
+      }
+    }
+  }
+  uint8_t* dst = pred + ((int64_t)n * H + Y) * W + Xb;
+  if ((W & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(dst) =
+        (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (Xb + k < W) dst[k] = (uint8_t)arg[k];
   }
 }
 
@@ -343,6 +416,42 @@ extern "C" int asn_upsample_argmax_u8(const float* x, int N, int C, int h, int w
   int64_t items = (int64_t)N * H * ((W + 3) / 4);
   prof::Scope ps("upsample_argmax", 0, 4.0 * N * C * h * w + (double)N * H * W, st);
   upsample_argmax_kernel<<<full_grid(items, 128), 128, 0, st>>>(x, pred, N, C, h, w, H, W, sh, sw);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
+// rows / columns of the intermediate grid a TH2 x TW2 output tile can touch (host side of upsample2_argmax_kernel)
+static int mid_extent(int tile, int n_mid, int n_out) {
+  const float s = lerp_scale(n_mid, n_out);
+  int e = (int)ceilf(s * (float)(tile - 1)) + 3;
+  return e < n_mid + 1 ? e : n_mid + 1;
+}
+
+extern "C" int asn_upsample2_argmax_u8(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H,
+                                       int W, void* stream) {
+  ASN_CHECK_ARG(x && pred, "asn_upsample2_argmax_u8: null pointer");
+  ASN_CHECK_ARG(N > 0 && C > 0 && C <= 256 && h > 0 && w > 0 && Hm > 0 && Wm > 0 && H > 0 && W > 0,
+                "asn_upsample2_argmax_u8: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int MR = mid_extent(TH2, Hm, H), MC = mid_extent(TW2, Wm, W);
+  const size_t smem = (size_t)C * MR * MC * sizeof(float);
+  if (smem > 160 * 1024) {
+    set_error("asn_upsample2_argmax_u8: a %dx%d output tile needs %zu bytes of intermediate pixels (strong minification "
+              "in the second stage); resize in two calls instead", TH2, TW2, smem);
+    return ASN_EUNSUPPORTED;
+  }
+  static int smem_set[64] = {0};
+  int dev = 0;
+  ASN_CUDA(cudaGetDevice(&dev));
+  if (smem > 48 * 1024 && dev < 64 && smem_set[dev] < (int)smem) {
+    ASN_CUDA(cudaFuncSetAttribute(upsample2_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[dev] = (int)smem;
+  }
+  const long long tiles = (long long)N * cdiv(H, TH2) * cdiv(W, TW2);
+  prof::Scope ps("upsample2_argmax", 0, 4.0 * N * C * h * w + (double)N * H * W, st);
+  upsample2_argmax_kernel<<<(unsigned)tiles, 256, smem, st>>>(x, pred, N, C, h, w, Hm, Wm, H, W, lerp_scale(h, Hm),
+                                                              lerp_scale(w, Wm), lerp_scale(Hm, H), lerp_scale(Wm, W), MR,
+                                                              MC);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }

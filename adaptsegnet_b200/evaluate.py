@@ -10,9 +10,11 @@ from . import ops
 @torch.no_grad()
 def predict_labels(model, image: torch.Tensor, size=(1024, 2048)) -> torch.Tensor:
     """uint8 (N, size[0], size[1]) class ids == np.argmax(interp(model(image)[1]), channel) of the reference
-    (evaluate_cityscapes.py:162-169), computed by the fused upsample+argmax kernel."""
+    (evaluate_cityscapes.py:162-169).  ``model(image)[1]`` is already upsampled to the image size inside the fork's
+    forward (model/deeplab_multi.py:188-189), so the chain has TWO bilinear stages -- low-res logits -> image size ->
+    ``size`` -- and both are evaluated (fused, with ATen's float op order) by asn_upsample2_argmax_u8."""
     _, x2 = model.low_res_logits(image)
-    return ops.upsample_argmax(x2, size)
+    return ops.upsample2_argmax(x2, tuple(image.shape[-2:]), size)
 
 
 class ConfusionMatrix:

@@ -156,6 +156,21 @@ def upsample_argmax(x: torch.Tensor, size) -> torch.Tensor:
     return pred
 
 
+def upsample2_argmax(x: torch.Tensor, mid_size, size) -> torch.Tensor:
+    """argmax_c interp_size(interp_mid(x)) as uint8 [N,H,W]: the fork's evaluation chain with BOTH of its bilinear stages
+    (model/deeplab_multi.py:188-189 to the input size ``mid_size``, then evaluate_cityscapes.py:153,163 to ``size``),
+    :168-169 fused; the intermediate tensor only ever exists in shared memory."""
+    x = _req(x, torch.float32, "x")
+    N, Cc, h, w = x.shape
+    Hm, Wm = int(mid_size[0]), int(mid_size[1])
+    H, W = int(size[0]), int(size[1])
+    pred = torch.empty((N, H, W), dtype=torch.uint8, device=x.device)
+    check(_lib.load().asn_upsample2_argmax_u8(x.data_ptr(), N, Cc, h, w, Hm, Wm, pred.data_ptr(), H, W, _stream()),
+          "asn_upsample2_argmax_u8")
+    _count()
+    return pred
+
+
 # --------------------------------------------------------------------------------------
 # K3 softmax cross entropy
 # --------------------------------------------------------------------------------------

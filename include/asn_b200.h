@@ -99,6 +99,14 @@ ASN_API int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, int 
                               void* workspace, size_t workspace_bytes, void* stream);
 ASN_API int asn_upsample_argmax_u8(const float* x, int N, int C, int h, int w, uint8_t* pred, int H, int W,
                            void* stream);
+/* the fork's evaluation chain as it really runs: x (h x w low-res logits) -> bilinear to (Hm x Wm), the upsample to the
+ * input size inside ResNetMulti.forward (model/deeplab_multi.py:188-189) -> bilinear to (H x W), the script's `interp`
+ * (evaluate_cityscapes.py:153,163) -> argmax -> uint8 (:168-169).  The two stages do not compose into one unless
+ * (out-1) % (in-1) == 0; both are evaluated with ATen's float op order (bit-identical intermediate), the
+ * intermediate lives in shared memory only.  ASN_EUNSUPPORTED when the second stage minifies so strongly that a
+ * tile's intermediate pixels do not fit in shared memory. */
+ASN_API int asn_upsample2_argmax_u8(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H,
+                            int W, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K3  softmax + cross entropy with ignore label over (N,C,H,W) logits.

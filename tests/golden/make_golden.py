@@ -244,6 +244,57 @@ def gold_argmax():
     save("argmax", x=x.numpy(), pred=output)
 
 
+def gold_eval2():
+    """Evaluation chain at shapes where the two bilinear stages do NOT compose into one ((out-1) % (in-1) != 0):
+    ResNetMulti.forward's own upsample to the input size (model/deeplab_multi.py:188-189) followed by the script's
+    interp to the label size and the CPU argmax (evaluate_cityscapes.py:153,163,168-169)."""
+    import hashlib
+    from model.deeplab_multi import DeeplabMulti
+
+    out = {}
+    # (a) the reference's own model end to end on a 72x136 image: features 9x17 -> 72x136 (ratio 71/8) -> 144x272
+    torch.manual_seed(SEED)
+    model = DeeplabMulti(19).eval()
+    keep = {}
+    model.layer6.register_forward_hook(lambda m, i, o: keep.__setitem__("low", o.detach().clone()))
+    gen = torch.Generator().manual_seed(SEED + 11)
+    image = torch.randn((1, 3, 72, 136), generator=gen) * 50
+    interp = nn.Upsample(size=(144, 272), mode="bilinear", align_corners=True)      # evaluate_cityscapes.py:153
+    with torch.no_grad():
+        _, output2 = model(image, (136, 72))                                         # :162 (input_size = (W, H), Q1)
+        output = interp(output2).cpu().data[0].numpy()                               # :163
+    pred = np.asarray(np.argmax(output.transpose(1, 2, 0), axis=2), dtype=np.uint8)   # :168-169
+    out["model_low"] = keep["low"].numpy()
+    out["model_mid_hw"] = np.array(output2.shape[-2:])
+    out["model_mid_sha"] = hashlib.sha256(output2.numpy().tobytes()).hexdigest()
+    out["model_pred"] = pred
+    # (b) fixed logits with exact ties, 33x65 -> 259x515 -> 518x1030
+    x = torch.randn((1, 19, 33, 65), generator=gen) * 3
+    x[0, 3] = x[0, 7]
+    mid = nn.Upsample(size=(259, 515), mode="bilinear", align_corners=True)(x)
+    up = nn.Upsample(size=(518, 1030), mode="bilinear", align_corners=True)(mid)
+    out["mid_x"] = x.numpy()
+    out["mid_sha"] = hashlib.sha256(mid.numpy().tobytes()).hexdigest()
+    out["mid_pred"] = np.asarray(np.argmax(up[0].numpy().transpose(1, 2, 0), axis=2), dtype=np.uint8)
+    # (c) BASELINE config 5 shapes: 64x128 -> 512x1024 -> 1024x2048; the input is re-created from the seed (CPU
+    #     generator, platform independent), the outputs are pinned by digest and class histogram
+    g5 = torch.Generator().manual_seed(SEED + 5)
+    x5 = torch.randn((1, 19, 64, 128), generator=g5) * 3
+    mid5 = nn.Upsample(size=(512, 1024), mode="bilinear", align_corners=True)(x5)
+    up5 = nn.Upsample(size=(1024, 2048), mode="bilinear", align_corners=True)(mid5)
+    pred5 = np.asarray(np.argmax(up5[0].numpy().transpose(1, 2, 0), axis=2), dtype=np.uint8)
+    one = nn.Upsample(size=(1024, 2048), mode="bilinear", align_corners=True)(x5)
+    pred5_one = np.asarray(np.argmax(one[0].numpy().transpose(1, 2, 0), axis=2), dtype=np.uint8)
+    out["cfg5_seed"] = np.array(SEED + 5)
+    out["cfg5_x_sha"] = hashlib.sha256(x5.numpy().tobytes()).hexdigest()
+    out["cfg5_mid_sha"] = hashlib.sha256(mid5.numpy().tobytes()).hexdigest()
+    out["cfg5_pred_sha"] = hashlib.sha256(pred5.tobytes()).hexdigest()
+    out["cfg5_pred_bincount"] = np.bincount(pred5.ravel(), minlength=19)
+    out["cfg5_one_stage_differs"] = np.array(int((pred5 != pred5_one).sum()))   # what a single-stage resize gets wrong
+    print("cfg5: one-stage vs two-stage argmax differs on", int((pred5 != pred5_one).sum()), "pixels")
+    save("eval2", **out)
+
+
 def gold_step():
     """whole multi-level / single-level iteration (train_gta2cityscapes_multi.py:560-683, :373-464) driven
     through oracle/torch_ref.RefTrainer's restated loop with the REFERENCE's own modules injected."""
@@ -278,6 +329,6 @@ def gold_step():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["aspp", "upsample", "ce", "softmax", "fcd", "ganloss", "hist", "argmax", "step"]
+    which = sys.argv[1:] or ["aspp", "upsample", "ce", "softmax", "fcd", "ganloss", "hist", "argmax", "eval2", "step"]
     for name in which:
         globals()["gold_" + name]()

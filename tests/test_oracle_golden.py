@@ -112,3 +112,25 @@ def test_upsample_argmax_bit_exact(golden):
     pred = O.upsample_argmax(g["x"], 64, 128)
     assert pred.dtype == np.uint8
     assert np.array_equal(pred, g["pred"])
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_two_stage_eval_chain_bit_exact(golden):
+    """model/deeplab_multi.py:188-189 then evaluate_cityscapes.py:153,163,168-169 at shapes where the two bilinear
+    stages do not compose ((out-1) % (in-1) != 0): the float32 restatement reproduces the reference's intermediate
+    tensor bit for bit (sha256) and its uint8 prediction exactly."""
+    g = golden("eval2")
+    # the reference's own model: layer6 logits 9x17 -> 72x136 -> 144x272
+    mh, mw = (int(v) for v in g["model_mid_hw"])
+    assert _sha(O.upsample_bilinear_f32(g["model_low"], mh, mw)) == str(g["model_mid_sha"])
+    assert np.array_equal(O.upsample_argmax(g["model_low"], 144, 272, mid=(mh, mw)), g["model_pred"])
+    # fixed logits with exact ties: 33x65 -> 259x515 -> 518x1030
+    assert _sha(O.upsample_bilinear_f32(g["mid_x"], 259, 515)) == str(g["mid_sha"])
+    pred = O.upsample_argmax(g["mid_x"], 518, 1030, mid=(259, 515))
+    assert np.array_equal(pred, g["mid_pred"])
+    # a single-stage resize is NOT the reference's arithmetic at these shapes
+    assert (O.upsample_argmax(g["mid_x"], 518, 1030) != g["mid_pred"]).any()
