@@ -31,6 +31,9 @@ SIGNATURES = {
     "asn_upsample_argmax_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "asn_upsample2_argmax_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                         c_void_p]),
+    "asn_upsample2_argmax_hist": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                          c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "asn_per_class_iu": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "asn_softmax_ce_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p]),
     "asn_softmax_ce_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -170,7 +170,51 @@ static int launch_hist(const void* label, const uint8_t* pred, int64_t n_px, int
   return ASN_OK;
 }
 
+// compute_iou.py:20-21,61-64 on the device: iu[c] = hist[c][c] / (row_c + col_c - hist[c][c]) in float64 (0/0 -> nan,
+// like numpy), miou = nanmean(iu) (nan when every class is nan).  The int64 counts are exact in float64 below 2^53, which
+// is how the reference holds them (np.zeros((n, n)) accumulates float64).  One warp: lane strides the classes.
+__global__ void per_class_iu_kernel(const long long* __restrict__ hist, int n, double* __restrict__ iu,
+                                    double* __restrict__ miou) {
+  const int lane = threadIdx.x;
+  double sum = 0.0;
+  long long cnt = 0;
+  for (int c = lane; c < n; c += 32) {
+    double row = 0.0, col = 0.0;
+    for (int j = 0; j < n; ++j) {   // numpy sums the float64 matrix entry by entry in this order
+      row += (double)hist[(long long)c * n + j];
+      col += (double)hist[(long long)j * n + c];
+    }
+    const double d = (double)hist[(long long)c * n + c];
+    const double v = d / (row + col - d);
+    iu[c] = v;
+    if (v == v) { sum += v; ++cnt; }
+  }
+  // per-lane partial sums are combined in lane order so the result does not depend on the shuffle tree
+  __shared__ double s_sum[32];
+  __shared__ long long s_cnt[32];
+  s_sum[lane] = sum;
+  s_cnt[lane] = cnt;
+  __syncwarp();
+  if (lane == 0) {
+    double t = 0.0;
+    long long k = 0;
+    for (int i = 0; i < 32; ++i) { t += s_sum[i]; k += s_cnt[i]; }
+    *miou = k ? t / (double)k : nan("");
+  }
+}
+
 }  // namespace asn
+
+extern "C" int asn_per_class_iu(const int64_t* hist, int n_cls, double* iu, double* miou, void* stream) {
+  using namespace asn;
+  ASN_CHECK_ARG(hist && iu && miou, "asn_per_class_iu: null pointer");
+  ASN_CHECK_ARG(n_cls >= 1 && n_cls <= 4096, "asn_per_class_iu: bad n_cls");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  prof::Scope ps("per_class_iu", 0, 8.0 * n_cls * n_cls, st);
+  per_class_iu_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const long long*>(hist), n_cls, iu, miou);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
 
 static int fast_hist_impl(const void* label, int label_dtype, const uint8_t* lut, const uint8_t* pred, int64_t n_px,
                           int n_cls, int64_t* hist, int64_t* overflow, void* stream) {

@@ -271,10 +271,34 @@ upsample_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred, 
 // thread interpolates its four outputs from shared memory and keeps the first maximum (stage 2).  Per frame 0.6 MB are
 // read and 2 MB written.  Both stages use ATen's op order (lerp3), so the result equals the reference's bit for bit.
 constexpr int TH2 = 8, TW2 = 128;   // output tile: 256 threads x 4 pixels
+struct HistArgs {           // optional fused confusion matrix (compute_iou.py:15-17,55-57); label == nullptr: off
+  const void* label;        // [N][H][W], ASN_LABEL_U8 / I32 / I64
+  int label_dtype;
+  const uint8_t* lut;       // nullable 256-entry label_mapping table (compute_iou.py:24-28)
+  int n_cls;
+  unsigned long long* hist;      // [n_cls][n_cls], accumulated
+  unsigned long long* overflow;  // flat index >= n_cls^2 under a valid label (np.bincount would grow)
+};
+
+__device__ __forceinline__ int hist_label(const HistArgs& ha, int64_t i) {
+  // -1 = not counted: the reference's mask (a >= 0) & (a < n) after the optional mapping of ids in [0, 256)
+  unsigned long long v;
+  if (ha.label_dtype == ASN_LABEL_U8) v = static_cast<const uint8_t*>(ha.label)[i];
+  else if (ha.label_dtype == ASN_LABEL_I32) v = (unsigned long long)(long long)static_cast<const int32_t*>(ha.label)[i];
+  else v = (unsigned long long)static_cast<const int64_t*>(ha.label)[i];
+  if (ha.lut && v < 256ull) v = ha.lut[v];
+  return v < (unsigned long long)ha.n_cls ? (int)v : -1;
+}
+
 __global__ void __launch_bounds__(256)
 upsample2_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred, int N, int C, int h, int w, int Hm,
-                        int Wm, int H, int W, float s1h, float s1w, float s2h, float s2w, int MR, int MC) {
-  extern __shared__ float mid[];  // [C][MR][MC]
+                        int Wm, int H, int W, float s1h, float s1w, float s2h, float s2w, int MR, int MC,
+                        const HistArgs ha) {
+  extern __shared__ float mid[];  // [C][MR][MC] (+ n_cls^2 uint32 bins when the confusion matrix is fused)
+  uint32_t* bins = reinterpret_cast<uint32_t*>(mid + C * MR * MC);
+  const int nbins = ha.n_cls * ha.n_cls;
+  if (ha.label)
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) bins[i] = 0;
   const int tiles_w = (W + TW2 - 1) / TW2, tiles_h = (H + TH2 - 1) / TH2;
   const int tx = blockIdx.x % tiles_w, ty = (blockIdx.x / tiles_w) % tiles_h, n = blockIdx.x / (tiles_w * tiles_h);
   const int Y0 = ty * TH2, X0 = tx * TW2;
@@ -296,8 +320,9 @@ upsample2_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred,
   __syncthreads();
   // ---- stage 2: thread = 4 consecutive output pixels of one row ----
   const int Y = Y0 + (threadIdx.x >> 5), Xb = X0 + (threadIdx.x & 31) * 4;
-  if (Y >= H || Xb >= W) return;
-  const Lerp ly = lerp_at(Y, s2h, Hm);
+  const bool active = Y < H && Xb < W;
+  if (active) {
+  const Lerp ly = lerp_at(min(Y, H - 1), s2h, Hm);
   const int r0 = (ly.i0 - my0) * MC, r1 = (ly.i1 - my0) * MC;
   int c0[4], c1[4];
   float l0[4], l1[4];
@@ -320,14 +345,38 @@ upsample2_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ pred,
       }
     }
   }
-  uint8_t* dst = pred + ((int64_t)n * H + Y) * W + Xb;
-  if ((W & 3) == 0) {
-    *reinterpret_cast<uint32_t*>(dst) =
-        (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
-  } else {
+  const int64_t px = ((int64_t)n * H + Y) * W + Xb;
+  if (pred) {
+    uint8_t* dst = pred + px;
+    if ((W & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(dst) =
+          (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (Xb + k < W) dst[k] = (uint8_t)arg[k];
+      for (int k = 0; k < 4; ++k)
+        if (Xb + k < W) dst[k] = (uint8_t)arg[k];
+    }
+  }
+  if (ha.label) {   // hist[a][b] += 1 for valid labels; equal neighbours are merged before the shared-memory atomic
+    int cur = -1;
+    uint32_t cnt = 0, ovf = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (Xb + k >= W) break;
+      const int a = hist_label(ha, px + k);
+      const int idx = a >= 0 ? a * ha.n_cls + arg[k] : -1;
+      if (idx == cur) { ++cnt; continue; }
+      if (cur >= 0) { if (cur < nbins) atomicAdd(&bins[cur], cnt); else ovf += cnt; }
+      cur = idx; cnt = 1;
+    }
+    if (cur >= 0) { if (cur < nbins) atomicAdd(&bins[cur], cnt); else ovf += cnt; }
+    if (ovf) atomicAdd(ha.overflow, (unsigned long long)ovf);
+  }
+  }  // active
+  if (ha.label) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+      if (bins[i]) atomicAdd(&ha.hist[i], (unsigned long long)bins[i]);
   }
 }
 
@@ -427,31 +476,53 @@ static int mid_extent(int tile, int n_mid, int n_out) {
   return e < n_mid + 1 ? e : n_mid + 1;
 }
 
-extern "C" int asn_upsample2_argmax_u8(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H,
-                                       int W, void* stream) {
-  ASN_CHECK_ARG(x && pred, "asn_upsample2_argmax_u8: null pointer");
-  ASN_CHECK_ARG(N > 0 && C > 0 && C <= 256 && h > 0 && w > 0 && Hm > 0 && Wm > 0 && H > 0 && W > 0,
-                "asn_upsample2_argmax_u8: bad shape");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int upsample2_impl(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H, int W,
+                          const HistArgs& ha, cudaStream_t st) {
   const int MR = mid_extent(TH2, Hm, H), MC = mid_extent(TW2, Wm, W);
-  const size_t smem = (size_t)C * MR * MC * sizeof(float);
+  const size_t smem = (size_t)C * MR * MC * sizeof(float) + (ha.label ? (size_t)ha.n_cls * ha.n_cls * 4 : 0);
   if (smem > 160 * 1024) {
-    set_error("asn_upsample2_argmax_u8: a %dx%d output tile needs %zu bytes of intermediate pixels (strong minification "
-              "in the second stage); resize in two calls instead", TH2, TW2, smem);
+    set_error("asn_upsample2_argmax: a %dx%d output tile needs %zu bytes of shared memory (strong minification in the "
+              "second stage, or too many classes for the fused confusion matrix); use the unfused entry points", TH2, TW2,
+              smem);
     return ASN_EUNSUPPORTED;
   }
   static int smem_set[64] = {0};
   int dev = 0;
   ASN_CUDA(cudaGetDevice(&dev));
-  if (smem > 48 * 1024 && dev < 64 && smem_set[dev] < (int)smem) {
+  if (smem > 48 * 1024 && dev >= 0 && dev < 64 && smem_set[dev] < (int)smem) {
     ASN_CUDA(cudaFuncSetAttribute(upsample2_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set[dev] = (int)smem;
   }
   const long long tiles = (long long)N * cdiv(H, TH2) * cdiv(W, TW2);
-  prof::Scope ps("upsample2_argmax", 0, 4.0 * N * C * h * w + (double)N * H * W, st);
+  const double label_bytes = !ha.label ? 0.0 : (ha.label_dtype == ASN_LABEL_U8 ? 1.0 : ha.label_dtype == ASN_LABEL_I32 ? 4.0 : 8.0);
+  prof::Scope ps(ha.label ? "upsample2_argmax_hist" : "upsample2_argmax", 0,
+                 4.0 * N * C * h * w + (double)N * H * W * ((pred ? 1.0 : 0.0) + label_bytes), st);
   upsample2_argmax_kernel<<<(unsigned)tiles, 256, smem, st>>>(x, pred, N, C, h, w, Hm, Wm, H, W, lerp_scale(h, Hm),
                                                               lerp_scale(w, Wm), lerp_scale(Hm, H), lerp_scale(Wm, W), MR,
-                                                              MC);
+                                                              MC, ha);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
+}
+
+extern "C" int asn_upsample2_argmax_u8(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H,
+                                       int W, void* stream) {
+  ASN_CHECK_ARG(x && pred, "asn_upsample2_argmax_u8: null pointer");
+  ASN_CHECK_ARG(N > 0 && C > 0 && C <= 256 && h > 0 && w > 0 && Hm > 0 && Wm > 0 && H > 0 && W > 0,
+                "asn_upsample2_argmax_u8: bad shape");
+  HistArgs ha{};
+  return upsample2_impl(x, N, C, h, w, Hm, Wm, pred, H, W, ha, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int asn_upsample2_argmax_hist(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H,
+                                         int W, const void* label, int label_dtype, const uint8_t* lut256, int n_cls,
+                                         int64_t* hist, int64_t* overflow, void* stream) {
+  ASN_CHECK_ARG(x && label && hist && overflow, "asn_upsample2_argmax_hist: null pointer");
+  ASN_CHECK_ARG(N > 0 && C > 0 && C <= 256 && h > 0 && w > 0 && Hm > 0 && Wm > 0 && H > 0 && W > 0,
+                "asn_upsample2_argmax_hist: bad shape");
+  ASN_CHECK_ARG(n_cls >= 1 && n_cls <= 64, "asn_upsample2_argmax_hist: n_cls=%d outside [1,64]", n_cls);
+  ASN_CHECK_ARG(label_dtype == ASN_LABEL_U8 || label_dtype == ASN_LABEL_I32 || label_dtype == ASN_LABEL_I64,
+                "asn_upsample2_argmax_hist: unknown label_dtype %d", label_dtype);
+  HistArgs ha{label, label_dtype, lut256, n_cls, reinterpret_cast<unsigned long long*>(hist),
+              reinterpret_cast<unsigned long long*>(overflow)};
+  return upsample2_impl(x, N, C, h, w, Hm, Wm, pred, H, W, ha, static_cast<cudaStream_t>(stream));
 }

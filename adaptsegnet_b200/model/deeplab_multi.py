@@ -120,6 +120,8 @@ class ResNetMulti(nn.Module):
     # Execution mode of the (unchanged) trunk modules, SURVEY.md 8f row 1: run them under torch.autocast(bfloat16).
     # Off by default -- the reference computes the trunk in fp32 (TF32 on the GPU); the heads always receive fp32 features.
     trunk_autocast = False
+    # True: forward() returns lazy upsampled-logits handles (adaptsegnet_b200/lazy.py) instead of full-resolution tensors
+    lazy_outputs = False
 
     def trunk(self, x):
         """ResNet-101 features: (layer3 output, layer4 output), both H/8 x W/8."""
@@ -147,6 +149,11 @@ class ResNetMulti(nn.Module):
         f3, f4 = self.trunk(x)
         x1 = self.layer5(f3)
         x2 = self.layer6(f4)
+        if self.lazy_outputs:
+            # Tier-B behind the unchanged scripts: handles that route the script's own CrossEntropyLoss / F.softmax /
+            # .detach() / nn.Upsample calls to the fused kernels and materialise on anything else (lazy.py)
+            from ..lazy import UpsampledLogits
+            return UpsampledLogits.make(x1, size), UpsampledLogits.make(x2, size)
         return ops.upsample_bilinear(x1, size), ops.upsample_bilinear(x2, size)
 
     def low_res_logits(self, x):

@@ -171,6 +171,40 @@ def upsample2_argmax(x: torch.Tensor, mid_size, size) -> torch.Tensor:
     return pred
 
 
+def upsample2_argmax_hist(x, mid_size, size, label, n_cls, hist, overflow, lut=None, want_pred=False):
+    """upsample2_argmax with compute_iou.py:55-57 fused in: ``hist`` (int64 [n,n]) += fast_hist(label, pred, n) for the
+    frame(s), in the same kernel that forms the prediction.  Returns the uint8 prediction if ``want_pred`` else None."""
+    x = _req(x, torch.float32, "x")
+    label = _req(label, None, "label")
+    if label.dtype not in _LABEL_CODE:
+        raise TypeError(f"label dtype {label.dtype} not supported (uint8, int32, int64)")
+    N, Cc, h, w = x.shape
+    Hm, Wm = int(mid_size[0]), int(mid_size[1])
+    H, W = int(size[0]), int(size[1])
+    if label.numel() != N * H * W:
+        raise ValueError("label and prediction must have the same number of pixels")
+    if lut is not None:
+        lut = _req(lut, torch.uint8, "lut")
+    pred = torch.empty((N, H, W), dtype=torch.uint8, device=x.device) if want_pred else None
+    check(_lib.load().asn_upsample2_argmax_hist(x.data_ptr(), N, Cc, h, w, Hm, Wm, pred.data_ptr() if want_pred else None,
+                                                H, W, label.data_ptr(), _LABEL_CODE[label.dtype],
+                                                lut.data_ptr() if lut is not None else None, int(n_cls), hist.data_ptr(),
+                                                overflow.data_ptr(), _stream()), "asn_upsample2_argmax_hist")
+    _count()
+    return pred
+
+
+def per_class_iu_device(hist: torch.Tensor):
+    """(iu float64 [n], miou float64 []) on the device -- compute_iou.py:20-21,61-64."""
+    hist = _req(hist, torch.int64, "hist")
+    n = hist.shape[0]
+    iu = torch.empty(n, dtype=torch.float64, device=hist.device)
+    miou = torch.empty((), dtype=torch.float64, device=hist.device)
+    check(_lib.load().asn_per_class_iu(hist.data_ptr(), n, iu.data_ptr(), miou.data_ptr(), _stream()), "asn_per_class_iu")
+    _count()
+    return iu, miou
+
+
 # --------------------------------------------------------------------------------------
 # K3 softmax cross entropy
 # --------------------------------------------------------------------------------------

@@ -30,7 +30,6 @@ METRIC = "train iters/s (720x1280 src+512x1024 tgt)"
 UNIT = "iters/s"
 SRC_HW = (720, 1280)
 TGT_HW = (512, 1024)
-SAMPLE_HW = (256, 512)  # bounded CPU sample: BASELINE.json configs[0] shape, src = tgt
 SEED = 1338
 
 
@@ -48,7 +47,13 @@ def parse():
     ap.add_argument("--channels-last", type=int, default=1, help="run the (unchanged) trunk in channels_last")
     ap.add_argument("--no-kernel-events", action="store_true", help="skip the per-kernel event pass (ncu runs)")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=2, help="timed full-size CPU iterations of the cpu_baseline leg")
+    ap.add_argument("--mode", default="train", choices=["train", "eval"],
+                    help="train: BASELINE configs[1] (the headline); eval: configs[4], evaluate_cityscapes + fast_hist "
+                         "over --frames synthetic 1024x2048 frames")
+    ap.add_argument("--frames", type=int, default=500)
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the reference-on-B200 (PyTorch eager) comparator block")
     ap.add_argument("--trunk-dtype", default="tf32", choices=["tf32", "bf16"],
                     help="tf32: the trunk as the reference's GPU path computes it; bf16: the trunk modules under "
                          "torch.autocast(bfloat16) (execution mode of the untouched trunk, SURVEY.md 8f row 1)")
@@ -125,11 +130,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the restated reference loop on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(steps, warmup, level, gan):
-    """iters/s of the full-size workload, extrapolated from a bounded sample on the host CPU.
-
-    Sample: the same iteration at 256x512 source = target (configs[0]); the trunk, heads, upsample, CE and
-    discriminators are all linear in the pixel count, so full-size rate = sample rate * sample_px / full_px."""
+def cpu_reference_rate(steps, warmup, level, gan, budget_s=240.0):
+    """iters/s of the restated reference loop (oracle/torch_ref.RefTrainer, torch CPU fp32, all host threads) MEASURED at
+    the full workload -- 720x1280 source + 512x1024 target, the same synthetic batch the GPU arm uses.  `steps` timed
+    iterations after `warmup` untimed ones; if the first iterations show that the request would run past `budget_s` of
+    wall clock, fewer are run and the counts actually used are returned (never extrapolated)."""
     import torch
     from oracle import torch_ref as TR
 
@@ -137,37 +142,351 @@ def cpu_reference_rate(steps, warmup, level, gan):
     torch.set_num_threads(cores)
     torch.manual_seed(SEED)
     tr = TR.RefTrainer(level=level, gan=gan, device="cpu")
-    src, lab, tgt = TR.synthetic_batch(SEED, SAMPLE_HW, SAMPLE_HW)
-    for i in range(warmup):
-        tr.step(src, lab, tgt, i_iter=i)
+    src, lab, tgt = TR.synthetic_batch(SEED, SRC_HW, TGT_HW)
+    t_start = time.perf_counter()
     t0 = time.perf_counter()
-    for i in range(steps):
-        tr.step(src, lab, tgt, i_iter=warmup + i)
-    dt = (time.perf_counter() - t0) / steps
-    full_px = SRC_HW[0] * SRC_HW[1] + TGT_HW[0] * TGT_HW[1]
-    sample_px = 2 * SAMPLE_HW[0] * SAMPLE_HW[1]
-    scale = sample_px / full_px
-    return {"value": (1.0 / dt) * scale, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"{steps} timed iterations (after {warmup} warm-up) of the restated reference loop "
-                       f"(oracle/torch_ref.RefTrainer, torch {torch.__version__} CPU fp32, {cores} threads) at "
-                       f"{SAMPLE_HW[0]}x{SAMPLE_HW[1]} src=tgt: {dt:.3f} s/iter; scaled by pixel count x{scale:.4f} "
-                       f"to the 720x1280+512x1024 workload"),
-            "sample_s_per_iter": dt}
+    tr.step(src, lab, tgt, i_iter=0)                      # first (cold) iteration: always untimed
+    first = time.perf_counter() - t0
+    warm_done = 1
+    while warm_done < warmup and (time.perf_counter() - t_start) + (steps + 1) * first < budget_s:
+        tr.step(src, lab, tgt, i_iter=warm_done)
+        warm_done += 1
+    left = budget_s - (time.perf_counter() - t_start)
+    steps_run = max(1, min(steps, int(left / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(steps_run):
+        tr.step(src, lab, tgt, i_iter=warm_done + i)
+    dt = (time.perf_counter() - t0) / steps_run
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": (f"{steps_run} timed full-size iterations (720x1280 source + 512x1024 target, after {warm_done} "
+                       f"untimed) of the restated reference loop (oracle/torch_ref.RefTrainer, torch {torch.__version__} "
+                       f"CPU fp32, {cores} threads): {dt:.3f} s/iter, measured, not extrapolated"),
+            "s_per_iter": dt, "steps_timed": steps_run, "warmup_run": warm_done, "extrapolated": False}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    steps = max(1, min(args.steps, 20))
-    warmup = max(1, min(args.warmup, 3))
-    base = cpu_reference_rate(steps, warmup, args.level, args.gan)
+    if args.mode == "eval":
+        return run_reference_eval(args)
+    base = cpu_reference_rate(max(1, args.steps), max(1, args.warmup), args.level, args.gan)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
+            "steps": base["steps_timed"], "warmup": base["warmup_run"], "steps_requested": args.steps,
+            "warmup_requested": args.warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_reference(dev, args, steps=5, warmup=3):
+    """the reference's own modules and loop (restated, oracle/torch_ref.RefTrainer) on the SAME
+    B200 in PyTorch eager -- NCHW fp32 tensors, cuDNN benchmark mode as train_gta2cityscapes_multi.py:228 sets it, .item()
+    per loss, CPU-built GAN targets -- with TF32 on (torch's cuDNN default, what the reference gets on this GPU) and off
+    (true fp32).  Whole step in ms, plus the hot-path groups through ATen next to libasn_b200's (bench_groups.py)."""
+    import torch
+    from oracle import torch_ref as TR
+    import bench_groups
+
+    out = {}
+    src, lab, tgt = TR.synthetic_batch(SEED, SRC_HW, TGT_HW)
+    src, lab, tgt = src.to(dev), lab.to(dev), tgt.to(dev)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.manual_seed(SEED)
+            tr = TR.RefTrainer(level=args.level, gan=args.gan, device=dev)
+            for i in range(warmup):
+                tr.step(src, lab, tgt, i_iter=i)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                tr.step(src, lab, tgt, i_iter=warmup + i)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            out[f"step_ms_{tag}"] = e0.elapsed_time(e1) / steps
+            del tr
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["steps"], out["warmup"] = steps, warmup
+    out["what"] = ("restated reference loop (train_gta2cityscapes_multi.py:560-683) over the restated reference modules, "
+                   "PyTorch eager on this GPU, NCHW fp32, cudnn.benchmark=True; CUDA events")
+    if args.level == "multi-level":
+        out["hot_path_groups"] = bench_groups.compare(dev, tier=args.tier)
+        out["hot_path_groups_what"] = ("one iteration's hot path at config-2 shapes on synthetic features / logits, per group, "
+                                       "median of 5 after 2 warm-ups, L2 flushed between repetitions: heads = 2 ASPP heads x "
+                                       "(source, target) fwd+bwd; seg_loss = upsample+CE fwd+bwd (source, 2 heads); adversarial = "
+                                       "all discriminator passes of both levels incl. target upsample+softmax and the GAN "
+                                       "losses; optimizers = SGD + 2 x Adam")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# --mode eval: BASELINE configs[4] -- evaluate_cityscapes inference at 1024x2048 + fast_hist 19-class IoU
+# ------------------------------------------------------------------------------------------------------
+EVAL_METRIC = "eval frames/s (512x1024 image -> 1024x2048 argmax + fast_hist 19-class IoU)"
+EVAL_IMG_HW, EVAL_LABEL_HW = (512, 1024), (1024, 2048)
+# Cityscapes id -> train id (the absent dataset/cityscapes_list/info.json `label2train`, compute_iou.py:40): the public
+# Cityscapes label definition; every id without a train id maps to 255
+CITYSCAPES_LABEL2TRAIN = [[i, 255] for i in range(34)] + [[-1, 255]]
+for _i, _t in zip((7, 8, 11, 12, 13, 17, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 31, 32, 33), range(19)):
+    CITYSCAPES_LABEL2TRAIN[_i] = [_i, _t]
+
+
+def eval_frame(seed):
+    """one synthetic validation frame: mean-subtracted BGR-like image (1,3,512,1024) fp32 and a blocky raw-id label map
+    (1024,2048) uint8 with Cityscapes ids 0..33 (per-frame seed)"""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    mean = torch.tensor([104.00698793, 116.66876762, 122.67891434]).view(1, 3, 1, 1)
+    img = torch.randint(0, 256, (1, 3) + EVAL_IMG_HW, generator=g).float() - mean
+    coarse = torch.randint(0, 34, (1, 1, 32, 64), generator=g).float()
+    lab = F.interpolate(coarse, size=EVAL_LABEL_HW, mode="nearest")[0].to(torch.uint8)
+    return img, lab
+
+
+def eval_workload_config(args, world, impl):
+    cfg = {"workload": f"evaluate_cityscapes + compute_iou over {args.frames} synthetic frames: DeeplabMulti(ResNet-101, 19 cls) "
+                       "forward on 1x3x512x1024, output2 -> 512x1024 -> 1024x2048 bilinear, argmax, label_mapping, "
+                       "19x19 fast_hist, mIoU; random init; 8 distinct seeded frames cycled",
+           "frames": args.frames, "per_gpu_batch": "1 frame"}
+    if impl == "reference":
+        cfg.update({"parallelism": "none (rank 0 only, host CPU)",
+                    "hot_path": "the reference's torch CPU + numpy ops (evaluate_cityscapes.py:155-169, compute_iou.py:50-64 restated)"})
+    else:
+        cfg.update({"parallelism": f"dp{world}: frames sharded round-robin, one int64 all-reduce of the 19x19 matrix at the end",
+                    "hot_path": "libasn_b200: tcgen05 layer6 head + ONE fused kernel for both bilinear stages, argmax, "
+                                "label_mapping LUT and the confusion matrix; device mIoU",
+                    "execution": "one CUDA graph per frame; trunk = unchanged PyTorch modules (cuDNN TF32, channels_last), eval mode",
+                    "dead_work": "layer5 (output1) is not computed: the reference computes it and never uses it "
+                                 "(evaluate_cityscapes.py:162-163)",
+                    "l2": "8 distinct frames x (6.3 MB image + 2.1 MB label) cycled, trunk activations >> 126 MB L2"})
+    return cfg
+
+
+def cpu_reference_eval(frames, preds_by_seed=None, budget_s=60.0):
+    """frames/s of the reference's CPU path per frame (evaluate_cityscapes.py:155-169 + compute_iou.py:53-57 restated with
+    the reference's own torch / numpy calls), measured on a bounded number of frames.  If ``preds_by_seed`` (GPU
+    predictions of the same frames) is given, also returns numpy's confusion matrix over THOSE predictions -- the checker
+    for the GPU matrix (bit-exact by contract)."""
+    import numpy as np
+    import torch
+    from oracle import np_oracle as O
+    from oracle import torch_ref as TR
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(SEED)
+    model = TR.RefDeeplabMulti(19).eval()
+    mapping = np.array(CITYSCAPES_LABEL2TRAIN, dtype=np.int64)
+    parts = {"forward": 0.0, "interp_d2h": 0.0, "argmax": 0.0, "label_mapping": 0.0, "fast_hist": 0.0}
+    hist = np.zeros((19, 19))
+    t_start = time.perf_counter()
+    done = 0
+    for f in range(frames + 1):                      # frame 0 is the untimed warm-up
+        img, lab = eval_frame(SEED + (f % 8))
+        t = [time.perf_counter()]
+        with torch.no_grad():
+            _, out2 = model(img, (img.shape[3], img.shape[2]))                                    # evaluate...:162
+            t.append(time.perf_counter())
+            interp = torch.nn.Upsample(size=EVAL_LABEL_HW, mode="bilinear", align_corners=True)    # :153
+            output = interp(out2).cpu().data[0].numpy()                                            # :163
+        t.append(time.perf_counter())
+        pred = np.asarray(np.argmax(output.transpose(1, 2, 0), axis=2), dtype=np.uint8)            # :168-169
+        t.append(time.perf_counter())
+        label = O.label_mapping(lab.numpy(), mapping)                                              # compute_iou.py:55
+        t.append(time.perf_counter())
+        h = O.fast_hist(label.flatten(), pred.flatten(), 19)                                       # :57
+        t.append(time.perf_counter())
+        if f > 0:
+            hist += h
+            for k, a, b in zip(parts, t[:-1], t[1:]):
+                parts[k] += b - a
+            done += 1
+        if f > 0 and time.perf_counter() - t_start > budget_s:
+            break
+    total = sum(parts.values())
+    res = {"value": done / total, "unit": "frames/s", "cores": cores, "kind": "port", "frames_timed": done,
+           "sample": (f"{done} frames (after 1 untimed) of the restated evaluate_cityscapes + compute_iou loop, torch "
+                      f"{torch.__version__} CPU fp32 + numpy, {cores} threads: {total / done:.3f} s/frame, measured"),
+           "s_per_frame_parts": {k: round(v / done, 4) for k, v in parts.items()}}
+    if preds_by_seed is not None:
+        chk = np.zeros((19, 19), dtype=np.int64)
+        for seed, pred in preds_by_seed.items():
+            _, lab = eval_frame(seed)
+            chk += O.fast_hist(O.label_mapping(lab.numpy(), mapping).flatten(), pred.flatten(), 19)
+        res["_check_hist"] = chk
+    return res
+
+
+def run_reference_eval(args):
+    base = cpu_reference_eval(max(1, args.steps), budget_s=240.0)
+    base.pop("_check_hist", None)
+    line = {"impl": "reference", "metric": EVAL_METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": base["frames_timed"], "warmup": 1, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": eval_workload_config(args, 1, "reference"), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_eval(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from adaptsegnet_b200 import ops, prof
+    from adaptsegnet_b200.evaluate import Evaluator
+    from adaptsegnet_b200.model.deeplab_multi import DeeplabMulti
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    torch.manual_seed(SEED)
+    model = DeeplabMulti(19).to(dev).eval()
+    pool_h = [eval_frame(SEED + i) for i in range(8)]
+    pool_h = [(i.pin_memory(), l.pin_memory()) for i, l in pool_h]
+    pool_d = [(i.to(dev), l.to(dev)) for i, l in pool_h]
+    my_frames = [f for f in range(args.frames) if f % world == rank]   # round-robin shard (SURVEY.md section 8e)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    ev = Evaluator(model, 19, EVAL_LABEL_HW, mapping=CITYSCAPES_LABEL2TRAIN, use_cuda_graph=bool(args.cuda_graph),
+                   channels_last=bool(args.channels_last))
+    for f in range(max(args.warmup, 3)):
+        ev.step(*pool_d[f % 8])
+    ev.hist.zero_()
+
+    def run_resident():
+        for f in my_frames:
+            ev.step(*pool_d[f % 8])
+        ev.all_reduce()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = prof.launch_count()
+    ms_total = timed(run_resident)
+    launches = prof.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    hist_all = ev.hist.clone()
+    iu, miou = ev.result()
+    # ---- e2e: image + label from pinned host memory every frame, the uint8 prediction back to the host ----
+    ev2 = Evaluator(model, 19, EVAL_LABEL_HW, mapping=CITYSCAPES_LABEL2TRAIN, use_cuda_graph=bool(args.cuda_graph),
+                    channels_last=bool(args.channels_last), keep_pred=True)
+    img_d, lab_d = pool_d[0][0].clone(), pool_d[0][1].clone()
+    pred_h = torch.empty((1,) + EVAL_LABEL_HW, dtype=torch.uint8).pin_memory()
+    for f in range(3):
+        ev2.step(img_d, lab_d)
+    ev2.hist.zero_()
+
+    def run_e2e():
+        for f in my_frames:
+            img_d.copy_(pool_h[f % 8][0], non_blocking=True)
+            lab_d.copy_(pool_h[f % 8][1], non_blocking=True)
+            pred = ev2.step(img_d, lab_d)
+            pred_h.copy_(pred, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the caller consumes (saves) every prediction
+        ev2.all_reduce()
+
+    ms_e2e = None if args.no_e2e else timed(run_e2e)
+    # ---- per-kernel events over a few eager frames (events cannot be recorded inside a captured graph) ----
+    kernels = {}
+    if not args.no_kernel_events:
+        ev3 = Evaluator(model, 19, EVAL_LABEL_HW, mapping=CITYSCAPES_LABEL2TRAIN, use_cuda_graph=False,
+                        channels_last=bool(args.channels_last))
+        for f in range(3):
+            ev3.step(*pool_d[f % 8])
+        prof.enable(True)
+        n_ev = 16
+        for f in range(n_ev):
+            ev3.step(*pool_d[f % 8])
+        torch.cuda.synchronize()
+        kernels = prof.report()
+        prof.enable(False)
+    if rank == 0:
+        peaks = load_peaks()
+        n = args.frames
+        line = {"metric": EVAL_METRIC, "value": n * 1000.0 / ms_total, "unit": "frames/s", "n_gpus": world, "steps": n,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / len(my_frames), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": eval_workload_config(args, world, "b200"), "clocks": clocks,
+                "e2e": {"value": (n * 1000.0 / ms_e2e) if ms_e2e else None, "unit": "frames/s",
+                        "h2d_bytes_per_step": int(pool_h[0][0].numel() * 4 + pool_h[0][1].numel()),
+                        "d2h_bytes_per_step": int(pred_h.numel())},
+                "gpu_launches": int(launches) * world, "miou": float(miou.item()),
+                "e2e_hist_equals_resident": bool(torch.equal(ev2.hist, hist_all)) if ms_e2e else None}
+        if kernels:
+            def frac_of(rec):
+                sec = rec["ms"] * 1e-3
+                t_tensor = rec["flops"] / (peaks["tflops_sustained"] * 1e12)
+                t_hbm = rec["bytes"] / (peaks["hbm_gbs"] * 1e9)
+                if t_tensor >= t_hbm:
+                    a = rec["flops"] / sec / 1e12
+                    return {"bound": "tensor", "achieved": a, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": a / peaks["tflops_sustained"]}
+                a = rec["bytes"] / sec / 1e9
+                return {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"]}
+            name, rec = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+            line["roofline"] = {"kernel": name, **frac_of(rec), "traffic": None, "avg_launch_ms": rec["ms"] / rec["launches"],
+                                "algorithmic_bytes_per_launch": rec["bytes"] / rec["launches"],
+                                "algorithmic_flops_per_launch": rec["flops"] / rec["launches"],
+                                "peak_source": peaks["source"]}
+            line["hot_path_kernels"] = {k: {"ms_per_frame": round(v["ms"] / 16, 4), "launches_per_frame": v["launches"] / 16,
+                                            **{kk: (round(vv, 3) if isinstance(vv, float) else vv) for kk, vv in frac_of(v).items()
+                                               if kk in ("bound", "achieved", "unit", "frac")}}
+                                        for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])}
+            line["hot_path_ms_per_frame"] = sum(v["ms"] for v in kernels.values()) / 16
+        if world == 1 and not args.no_cpu_baseline:
+            # GPU predictions of the 8 pool frames -> numpy fast_hist over them on the host = the checker
+            ev4 = Evaluator(model, 19, EVAL_LABEL_HW, mapping=CITYSCAPES_LABEL2TRAIN, use_cuda_graph=False,
+                            channels_last=bool(args.channels_last), keep_pred=True)
+            preds = {}
+            for i in range(8):
+                preds[SEED + i] = ev4.step(*pool_d[i]).cpu().numpy()[0].copy()
+            base = cpu_reference_eval(args.cpu_steps, preds_by_seed=preds, budget_s=45.0)
+            chk = base.pop("_check_hist")
+            line["cpu_baseline"] = base
+            line["hist_bit_exact_vs_numpy"] = bool(np.array_equal(ev4.hist.cpu().numpy(), chk))
+            # the 500-frame matrix is the pool's matrix taken frames/8 times (8 distinct frames cycled)
+            reps = np.array([len([f for f in range(n) if f % 8 == i]) for i in range(8)])
+            per_frame = []
+            for i in range(8):
+                from adaptsegnet_b200.compute_iou import fast_hist as gpu_hist
+                per_frame.append(gpu_hist(torch.from_numpy(eval_frame(SEED + i)[1].numpy().reshape(-1)).to(dev),
+                                          torch.from_numpy(preds[SEED + i].reshape(-1)).to(dev), 19,
+                                          mapping=CITYSCAPES_LABEL2TRAIN).cpu().numpy())
+            want_all = sum(int(r) * h for r, h in zip(reps, per_frame))
+            line["hist_500_frames_consistent"] = bool(np.array_equal(hist_all.cpu().numpy(), want_all))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def workload_config(args, world):
@@ -372,17 +691,28 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": int(src_h.numel() * 4 + lab_h.numel() * 8 + tgt_h.numel() * 4),
                         "d2h_bytes_per_step": 4 * n_losses},
-                "gpu_launches": int(launches), "roofline": roof,
+                "gpu_launches": int(launches) * world, "gpu_launches_per_rank": int(launches), "roofline": roof,
                 "cuda_graph": bool(graph_mode), "cuda_graph_note": graph_note,
                 "eager_ms_per_step_with_kernel_events": ms_eager / args.steps,
                 "hot_path_ms_per_step": hot_ms, "hot_path_kernels": breakdown}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan)
+            line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan, budget_s=60.0)
+    # ---- the kernel-for-kernel bar: the reference's own modules on this GPU in PyTorch eager (rank 0, N = 1) ----
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        try:
+            del trainer
+            trainer = None
+            torch.cuda.empty_cache()
+            line["reference_gpu_eager"] = gpu_eager_reference(dev, args)
+            ref_ms = line["reference_gpu_eager"]["step_ms_tf32"]
+            line["reference_gpu_eager"]["speedup_step_vs_tf32"] = ref_ms / ms_per_step
+        except Exception as exc:  # noqa: BLE001
+            line["reference_gpu_eager"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
     # ---- extra (never the headline): the same step with the untouched trunk under bf16 autocast ----
     extra = None
     if args.also_trunk_bf16 and args.trunk_dtype != "bf16":
         try:
-            del trainer
+            trainer = None
             torch.cuda.empty_cache()
             torch.manual_seed(SEED)
             trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"),
@@ -409,6 +739,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "eval":
+        run_eval(args)
     else:
         run_b200(args)
 

@@ -84,6 +84,10 @@ ASN_API int asn_fast_hist(const void* label, int label_dtype, const uint8_t* pre
 ASN_API int asn_fast_hist_lut(const void* label, int label_dtype, const uint8_t* lut256, const uint8_t* pred,
                       int64_t n_px, int n_cls, int64_t* hist, int64_t* overflow, void* stream);
 
+/* per_class_iu + nanmean on the device (compute_iou.py:20-21,61-64): iu[c] = hist[c][c] / (row + col - diag) in float64
+ * (0/0 -> nan), *miou = nanmean(iu).  One tiny launch; the matrix never visits the host. */
+ASN_API int asn_per_class_iu(const int64_t* hist, int n_cls, double* iu, double* miou, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K2 / K2b / K9  bilinear resize, align_corners=True.
  *   replaces: model/deeplab_multi.py:188-189, evaluate_cityscapes.py:153 (nn.Upsample)
@@ -107,6 +111,13 @@ ASN_API int asn_upsample_argmax_u8(const float* x, int N, int C, int h, int w, u
  * tile's intermediate pixels do not fit in shared memory. */
 ASN_API int asn_upsample2_argmax_u8(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H,
                             int W, void* stream);
+/* the same with the confusion matrix of compute_iou.py:55-57 accumulated in the SAME kernel (SURVEY.md section 8f row 3:
+ * no PNG round trip, no second pass over the prediction): hist[a][b] += 1 for every pixel whose (optionally lut256-
+ * mapped, compute_iou.py:24-28) label a is in [0, n_cls); `pred` may be NULL when only the matrix is wanted.
+ * label: [N][H][W] of label_dtype (ASN_LABEL_*); n_cls <= 64; hist / overflow as asn_fast_hist (accumulated). */
+ASN_API int asn_upsample2_argmax_hist(const float* x, int N, int C, int h, int w, int Hm, int Wm, uint8_t* pred, int H,
+                              int W, const void* label, int label_dtype, const uint8_t* lut256, int n_cls,
+                              int64_t* hist, int64_t* overflow, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K3  softmax + cross entropy with ignore label over (N,C,H,W) logits.

@@ -111,3 +111,61 @@ def test_numpy_fast_hist_api_like_reference():
     assert np.allclose(per_class_iu(h), O.per_class_iu(h), equal_nan=True)
     with pytest.raises(ValueError):
         fast_hist(np.array([18]), np.array([19], dtype=np.uint8), 19)
+
+
+@pytest.mark.parametrize("ldtype", [np.uint8, np.int32, np.int64])
+def test_fused_eval_tail_hist_bit_exact(ldtype):
+    """two-stage upsample + argmax + label_mapping + confusion matrix in ONE kernel == the unfused chain
+    (oracle argmax -> compute_iou.label_mapping -> fast_hist), bit exact, accumulated over frames; device mIoU == numpy"""
+    from adaptsegnet_b200 import ops
+    rng = np.random.default_rng(11)
+    mapping = [[7, 0], [8, 1], [11, 2], [12, 3], [13, 4], [17, 5], [19, 6], [20, 7], [21, 8], [22, 9], [23, 10],
+               [24, 11], [25, 12], [26, 13], [27, 14], [28, 15], [31, 16], [32, 17], [33, 18]]
+    lut = ops.mapping_lut(mapping, "cuda")
+    hist = torch.zeros((19, 19), dtype=torch.int64, device="cuda")
+    ovf = torch.zeros(1, dtype=torch.int64, device="cuda")
+    want = np.zeros((19, 19), dtype=np.int64)
+    for f, (low, mid, size) in enumerate([((1, 19, 9, 17), (72, 136), (144, 272)), ((2, 19, 5, 11), (33, 70), (61, 131))]):
+        x = (rng.standard_normal(low) * 3).astype(np.float32)
+        raw = rng.integers(0, 34, (low[0],) + size).astype(ldtype)       # raw dataset ids; unmapped ids stay >= 19 or map
+        if ldtype != np.uint8:
+            raw[:, :3] = -1
+        pred = ops.upsample2_argmax_hist(torch.from_numpy(x).cuda(), mid, size, torch.from_numpy(raw).cuda(), 19, hist,
+                                         ovf, lut=lut, want_pred=True).cpu().numpy()
+        for n in range(low[0]):
+            p_ref = O.upsample_argmax(x[n:n + 1], size[0], size[1], mid=mid)
+            assert np.array_equal(pred[n], p_ref)
+            want += O.fast_hist(O.label_mapping(raw[n], np.array(mapping)).ravel(), p_ref.ravel(), 19)
+    assert int(ovf.item()) == 0 and np.array_equal(hist.cpu().numpy(), want)
+    iu, miou = ops.per_class_iu_device(hist)
+    iu_ref = O.per_class_iu(want)
+    assert np.array_equal(np.isnan(iu.cpu().numpy()), np.isnan(iu_ref))
+    assert np.array_equal(iu.cpu().numpy()[~np.isnan(iu_ref)], iu_ref[~np.isnan(iu_ref)])
+    assert abs(miou.item() - np.nanmean(iu_ref)) <= 4e-16 * abs(np.nanmean(iu_ref))   # summation order: 1-2 ulp
+    # pred=None flavour accumulates the same counts
+    h2 = torch.zeros_like(hist)
+    ops.upsample2_argmax_hist(torch.from_numpy(x).cuda(), mid, size, torch.from_numpy(raw).cuda(), 19, h2, ovf, lut=lut)
+    h3 = torch.zeros_like(hist)
+    ops.fast_hist(torch.from_numpy(raw).cuda().reshape(-1), torch.from_numpy(pred).cuda().reshape(-1), 19, hist=h3, lut=lut)
+    assert torch.equal(h2, h3)
+
+
+def test_evaluator_graph_matches_eager_and_unfused():
+    """Evaluator (CUDA graph, channels_last, fused tail) over 3 frames == predict_labels + ConfusionMatrix frame by frame"""
+    from adaptsegnet_b200.evaluate import ConfusionMatrix, Evaluator, predict_labels
+    from adaptsegnet_b200.model.deeplab_multi import DeeplabMulti
+    torch.manual_seed(3)
+    model = DeeplabMulti(19).cuda().eval()
+    ev = Evaluator(model, 19, size=(144, 272), use_cuda_graph=True, keep_pred=True)
+    cm = ConfusionMatrix(19)
+    for f in range(3):
+        img, _, _ = TR.synthetic_batch(20 + f, (72, 136), (72, 136))
+        lab = torch.randint(0, 20, (1, 144, 272), generator=torch.Generator().manual_seed(f)).to(torch.uint8)
+        lab[lab == 19] = 255
+        pred = ev.step(img.cuda(), lab.cuda()).clone()
+        ref_pred = predict_labels(model, img.cuda().contiguous(memory_format=torch.channels_last), size=(144, 272))
+        assert torch.equal(pred, ref_pred)
+        cm.update(lab.cuda(), ref_pred)
+    assert torch.equal(ev.hist, cm.hist) and ev.frames == 3
+    iu, miou = ev.result()
+    assert np.allclose(iu.cpu().numpy(), cm.per_class_iu(), equal_nan=True, rtol=0, atol=0)
