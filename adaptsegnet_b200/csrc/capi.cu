@@ -19,6 +19,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < ASN_MAX_DEVICES ? dev : ASN_MAX_DEVICES - 1;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

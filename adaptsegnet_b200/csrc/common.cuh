@@ -12,6 +12,17 @@ namespace asn {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+int device_index();  // current CUDA device clamped to [0, ASN_MAX_DEVICES)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy answers are PER DEVICE: one-time kernel configuration
+// is remembered per device (a process may drive several GPUs, e.g. nn.DataParallel), with atomics because several
+// host threads may launch concurrently.  The configuration calls are idempotent, so a lost race only repeats them.
+constexpr int ASN_MAX_DEVICES = 64;
+struct PerDevice {
+  int v[ASN_MAX_DEVICES];  // zero-initialised (static storage)
+  int get() const { return __atomic_load_n(&v[device_index()], __ATOMIC_ACQUIRE); }
+  void set(int x) { __atomic_store_n(&v[device_index()], x, __ATOMIC_RELEASE); }
+};
 
 // Optional per-kernel timing with CUDA events on the launching stream (asn_prof_enable /
 // asn_prof_report): bench.py uses it to time the dominant kernel live inside the timed steps.

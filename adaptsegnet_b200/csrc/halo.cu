@@ -216,10 +216,10 @@ int conv1_fwd(const __nv_bfloat16* in, const __nv_bfloat16* wf, const float* bia
   a.N = N; a.OH = OH; a.OW = OW;
   a.tiles_h = cdiv(OH, TH); a.tiles_w = cdiv(OW, TW);
   a.bias = bias; a.slope = slope; a.out = out;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice configured;
+  if (!configured.get()) {
     ASN_CUDA(cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout::TOTAL));
-    configured = true;
+    configured.set(1);
   }
   const long long tiles = (long long)N * a.tiles_h * a.tiles_w;
   const int ctas = (int)(tiles < sm_count() ? tiles : sm_count());
@@ -446,10 +446,10 @@ int conv2_dgrad(const __nv_bfloat16* dpre, const __nv_bfloat16* wd, const __nv_b
   a.tiles_h = cdiv(cdiv(Hin, 2), D_TH);
   a.tiles_w = cdiv(cdiv(Win, 2), D_TW);
   a.mask_src = mask_src; a.mask_slope = mask_slope; a.out = out;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice configured;
+  if (!configured.get()) {
     ASN_CUDA(cudaFuncSetAttribute(conv2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DLayout::TOTAL));
-    configured = true;
+    configured.set(1);
   }
   const long long tiles = (long long)N * a.tiles_h * a.tiles_w;
   long long ctas = 2 * tiles < sm_count() ? 2 * tiles : sm_count();

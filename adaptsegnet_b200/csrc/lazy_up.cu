@@ -303,7 +303,8 @@ lazy_strip_kernel(const Args a) {
 // resident CTAs of a strip kernel (queried once per kernel)
 template <int C, int FUNC>
 static int strip_slots() {
-  static int slots = 0;
+  static PerDevice cache;   // per device: occupancy depends on the device the kernel will run on
+  int slots = cache.get();
   if (!slots) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lazy_strip_kernel<C, FUNC>, LZ_COLS, 0) != cudaSuccess ||
@@ -312,6 +313,7 @@ static int strip_slots() {
       per_sm = 2;
     }
     slots = per_sm * sm_count();
+    cache.set(slots);
   }
   return slots;
 }

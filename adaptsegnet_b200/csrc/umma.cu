@@ -119,9 +119,9 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
   constexpr int STAGES = Sh::stages, EW = Sh::EW, NUM_THREADS = EpiCfg<EW>::threads;
   using L = KernelSmem<MODE, BLOCK_N, STAGES, CL, MT, EW>;
   auto kern = umma_kernel<MODE, BLOCK_N, STAGES, CL, MT, EW>;
-  static bool configured = false;
-  static int max_clusters = 0;  // CL = 2: CTA pairs the device can keep resident at once (one per TPC)
-  if (!configured) {
+  static PerDevice configured, clusters;  // clusters: CL = 2, CTA pairs the device can keep resident at once (one per TPC)
+  int max_clusters = clusters.get();
+  if (!configured.get()) {
     ASN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     if (CL > 1) {
       cudaLaunchConfig_t q = {};
@@ -139,8 +139,9 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
         cudaGetLastError();
         max_clusters = sm_count() / CL;
       }
+      clusters.set(max_clusters);
     }
-    configured = true;
+    configured.set(1);
   }
   Params Pp = P;
   Pp.grid_x = (int)grid.x;

@@ -486,12 +486,10 @@ static int upsample2_impl(const float* x, int N, int C, int h, int w, int Hm, in
               smem);
     return ASN_EUNSUPPORTED;
   }
-  static int smem_set[64] = {0};
-  int dev = 0;
-  ASN_CUDA(cudaGetDevice(&dev));
-  if (smem > 48 * 1024 && dev >= 0 && dev < 64 && smem_set[dev] < (int)smem) {
+  static PerDevice smem_set;
+  if (smem > 48 * 1024 && smem_set.get() < (int)smem) {
     ASN_CUDA(cudaFuncSetAttribute(upsample2_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[dev] = (int)smem;
+    smem_set.set((int)smem);
   }
   const long long tiles = (long long)N * cdiv(H, TH2) * cdiv(W, TW2);
   const double label_bytes = !ha.label ? 0.0 : (ha.label_dtype == ASN_LABEL_U8 ? 1.0 : ha.label_dtype == ASN_LABEL_I32 ? 4.0 : 8.0);

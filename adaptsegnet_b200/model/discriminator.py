@@ -57,7 +57,7 @@ class FCDiscriminator(nn.Module):
         last = self._last_lazy
         if (last is not None and last[0] == key and ops.precision_mode() == "bf16" and torch.is_grad_enabled()
                 and not low.requires_grad and all(p.requires_grad for p in params)
-                and self._pack.key == last[1].key == tuple((p.data_ptr(), p._version) for p in params)):
+                and self._pack.key_on(low.device) == last[1].key == tuple((p.data_ptr(), p._version) for p in params)):
             self._last_lazy = None
             return ops.fcd_replay(last[1], params, self._pack)
         # (a forward on another input in between -- the D step on the source prediction, :645-646 -- leaves the entry alone)

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -468,34 +469,45 @@ def gemm_bf16_nt_mn(a: torch.Tensor, b: torch.Tensor, split_k: int = 1) -> torch
 # --------------------------------------------------------------------------------------
 class AsppWeightPack:
     """bf16 GEMM-layout shadow of the four fp32 OIHW branch weights (asn_aspp_pack_weights).
-    Re-packed when the parameters' version counters change (i.e. after optimizer.step())."""
+    Re-packed when the parameters' version counters change (i.e. after optimizer.step()).  One entry per device and a
+    lock: nn.DataParallel replicas share the module's pack object across devices and threads."""
 
     def __init__(self):
-        self.key = None
-        self.wp = self.wpt = self.bias_sum = None
+        self._by_dev = {}
+        self._lock = threading.Lock()
+
+    def key_on(self, device):
+        """key of the pack currently held for `device` (None if there is none)"""
+        e = self._by_dev.get(torch.device(device).index)
+        return e[0] if e else None
 
     def invalidate(self):
         """force a re-pack on the next use (CUDA-graph capture: the pack kernels must be part of the graph)"""
-        self.key = None
+        with self._lock:
+            self._by_dev.clear()
 
     def get(self, weights, biases, n_active):
         key = tuple((w.data_ptr(), w._version) for w in list(weights) + list(biases)) + (n_active,)
-        if key != self.key:
-            lib = _lib.load()
-            w0 = weights[0]
-            n_cls, cin = w0.shape[0], w0.shape[1]
-            NP = lib.asn_aspp_np(n_cls, n_active)
-            self.wp = torch.empty((NP, cin), dtype=torch.bfloat16, device=w0.device)
-            self.wpt = torch.empty((cin, NP), dtype=torch.bfloat16, device=w0.device)
-            ws = [_req(w.detach(), torch.float32, "weight") for w in weights[:n_active]]
-            check(lib.asn_aspp_pack_weights(_lib.ptr_array([w.data_ptr() for w in ws]), n_active, n_cls, cin,
-                                            self.wp.data_ptr(), self.wpt.data_ptr(), _stream()),
-                  "asn_aspp_pack_weights")
-            _count()
-            with torch.no_grad():
-                self.bias_sum = torch.stack([b.detach() for b in biases[:n_active]]).sum(0).contiguous()
-            self.key = key
-        return self.wp, self.wpt, self.bias_sum
+        dev = weights[0].device.index
+        with self._lock:
+            entry = self._by_dev.get(dev)
+            if entry is None or entry[0] != key:
+                lib = _lib.load()
+                w0 = weights[0]
+                n_cls, cin = w0.shape[0], w0.shape[1]
+                NP = lib.asn_aspp_np(n_cls, n_active)
+                wp = torch.empty((NP, cin), dtype=torch.bfloat16, device=w0.device)
+                wpt = torch.empty((cin, NP), dtype=torch.bfloat16, device=w0.device)
+                ws = [_req(w.detach(), torch.float32, "weight") for w in weights[:n_active]]
+                check(lib.asn_aspp_pack_weights(_lib.ptr_array([w.data_ptr() for w in ws]), n_active, n_cls, cin,
+                                                wp.data_ptr(), wpt.data_ptr(), _stream()),
+                      "asn_aspp_pack_weights")
+                _count()
+                with torch.no_grad():
+                    bias_sum = torch.stack([b.detach() for b in biases[:n_active]]).sum(0).contiguous()
+                entry = (key, wp, wpt, bias_sum)
+                self._by_dev[dev] = entry
+        return entry[1], entry[2], entry[3]
 
 
 class _AsppHeadTC(torch.autograd.Function):
@@ -602,30 +614,40 @@ LRELU_SLOPE = 0.2  # model/discriminator.py:16
 
 class FcdWeightPack:
     """bf16 implicit-GEMM shadows of the discriminator's fp32 OIHW parameters
-    (asn_fcd_pack_weights); rebuilt when a parameter's version counter changes."""
+    (asn_fcd_pack_weights); rebuilt when a parameter's version counter changes.  Per device, locked (see AsppWeightPack)."""
 
     def __init__(self):
-        self.key = None
-        self.buf = None
+        self._by_dev = {}
+        self._lock = threading.Lock()
+
+    def key_on(self, device):
+        """key of the pack currently held for `device` (None if there is none)"""
+        e = self._by_dev.get(torch.device(device).index)
+        return e[0] if e else None
 
     def invalidate(self):
-        self.key = None
+        with self._lock:
+            self._by_dev.clear()
 
     def get(self, params, n_cls, ndf):
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if key != self.key:
-            lib = _lib.load()
-            nbytes = lib.asn_fcd_wpack_bytes(n_cls, ndf)
-            if nbytes == 0:
-                raise _lib.AsnError(f"FCDiscriminator(num_classes={n_cls}, ndf={ndf}) is outside the tensor-core "
-                                    "path (needs num_classes <= 32, ndf a multiple of 64); use ASN_PRECISION=fp32")
-            self.buf = _ws(nbytes, params[0].device)
-            ps = [_req(p.detach(), torch.float32, "parameter") for p in params]
-            check(lib.asn_fcd_pack_weights(_lib.ptr_array([p.data_ptr() for p in ps]), n_cls, ndf,
-                                           self.buf.data_ptr(), _stream()), "asn_fcd_pack_weights")
-            _count(1)
-            self.key = key
-        return self.buf
+        dev = params[0].device.index
+        with self._lock:
+            entry = self._by_dev.get(dev)
+            if entry is None or entry[0] != key:
+                lib = _lib.load()
+                nbytes = lib.asn_fcd_wpack_bytes(n_cls, ndf)
+                if nbytes == 0:
+                    raise _lib.AsnError(f"FCDiscriminator(num_classes={n_cls}, ndf={ndf}) is outside the tensor-core "
+                                        "path (needs num_classes <= 32, ndf a multiple of 64); use ASN_PRECISION=fp32")
+                buf = _ws(nbytes, params[0].device)
+                ps = [_req(p.detach(), torch.float32, "parameter") for p in params]
+                check(lib.asn_fcd_pack_weights(_lib.ptr_array([p.data_ptr() for p in ps]), n_cls, ndf,
+                                               buf.data_ptr(), _stream()), "asn_fcd_pack_weights")
+                _count(1)
+                entry = (key, buf)
+                self._by_dev[dev] = entry
+        return entry[1]
 
 
 class _FcdTC(torch.autograd.Function):
@@ -724,7 +746,8 @@ class _FcdReplay(torch.autograd.Function):
 def fcd_replay(saved: FcdSaved, params, pack: "FcdWeightPack"):
     """D(x) for the x and weights of an earlier fcd_forward(..., return_saved=True), without recomputing it."""
     params = tuple(params)
-    if pack.key != saved.key or pack.key != tuple((p.data_ptr(), p._version) for p in params):
+    key = pack.key_on(params[0].device)
+    if key != saved.key or key != tuple((p.data_ptr(), p._version) for p in params):
         raise _lib.AsnError("fcd_replay: the discriminator's weights changed since the saved forward")
     return _FcdReplay.apply(saved, *params)
 
@@ -815,4 +838,4 @@ def fcd_forward(x, params, pack: FcdWeightPack | None = None, x_is_logits: bool 
     if fn is None:  # nothing requires grad: no autograd node holds the activations
         return out, None
     xs, wpack, acts = fn.saved_tensors
-    return out, FcdSaved(xs if fn.cfg[5] else None, wpack, acts, fn.cfg, out, pack.key)
+    return out, FcdSaved(xs if fn.cfg[5] else None, wpack, acts, fn.cfg, out, pack.key_on(params[0].device))

@@ -106,6 +106,10 @@ class AdaptSegTrainer:
         all discriminator passes, ~2 300 kernel launches) into one CUDA graph and replay it; the gradient
         all-reduce and the three optimizer steps stay eager.  Same kernels, same order, no per-launch CPU cost."""
         self.cfg = cfg = cfg or TrainConfig()
+        if cfg.iter_size != 1:
+            # the reference accumulates iter_size sub-batches per optimizer step (train...:578-679); step() takes exactly
+            # one (source, target) pair, so anything else would silently train on 1/iter_size of the gradient
+            raise NotImplementedError("AdaptSegTrainer.step() runs one sub-iteration per optimizer step: iter_size must be 1")
         self.device = torch.device(device)
         # fused optimizer steps on flat parameter buffers (optim.py) wherever the CUDA library runs; torch.optim on CPU
         self.fused_optimizers = (self.device.type == "cuda") if fused_optimizers is None else bool(fused_optimizers)
@@ -115,29 +119,36 @@ class AdaptSegTrainer:
         self._capture_stream = None   # the stream warm-up and capture ran on (autograd remembers it per parameter)
         self.multi = cfg.level == "multi-level"
         self.model = (model or DeeplabMulti(cfg.num_classes)).to(self.device).train()
+        # single-output trunk + head (DeeplabVGG, BASELINE config 4): forward() returns low-res logits, one level only
+        self.single_head = not hasattr(self.model, "layer5")
+        if self.single_head and self.multi:
+            raise ValueError("a single-head model (DeeplabVGG) trains with level='single-level'")
         if trunk_bf16:   # execution mode of the untouched trunk; the hot path is unaffected
             self.model.trunk_autocast = True
         if self.channels_last:
             # execution detail of the unchanged trunk: cuDNN's sm_100 kernels are NHWC, so an NCHW trunk spends a
             # quarter of its time in layout conversions; the head kernels take the channels_last features as they are
-            for name in ("conv1", "bn1", "layer1", "layer2", "layer3", "layer4"):
+            for name in (("features",) if self.single_head else ("conv1", "bn1", "layer1", "layer2", "layer3", "layer4")):
                 getattr(self.model, name).to(memory_format=torch.channels_last)
         self.model_D2 = (model_D2 or FCDiscriminator(cfg.num_classes)).to(self.device).train()
         self.model_D1 = (model_D1 or FCDiscriminator(cfg.num_classes)).to(self.device).train() if self.multi else None
         self.bce_loss = GANLoss(cfg.gan)
         self.seg_loss = SegCrossEntropy(ignore_index=255)
         # optimizers exactly as train...:532-540 (the duplicated trunk parameters included, Q11)
+        groups = self.model.optim_parameters(cfg)
+        if not (isinstance(groups, list) and groups and isinstance(groups[0], dict)):
+            groups = [{"params": list(groups), "lr": cfg.learning_rate}]     # DeeplabVGG: one group (deeplab_vgg.py:53-54)
         if self.fused_optimizers:
             from .optim import FlatParams, FusedAdam, FusedSGD
             self.flat_G = FlatParams(self.model.parameters())
             self.flat_D2 = FlatParams(self.model_D2.parameters())
             self.flat_D1 = FlatParams(self.model_D1.parameters()) if self.multi else None
-            self.optimizer = FusedSGD(self.flat_G, self.model.optim_parameters(cfg), lr=cfg.learning_rate,
+            self.optimizer = FusedSGD(self.flat_G, groups, lr=cfg.learning_rate,
                                       momentum=cfg.momentum, weight_decay=cfg.weight_decay)
             self.optimizer_D2 = FusedAdam(self.flat_D2, lr=cfg.learning_rate_D, betas=(0.9, 0.99))
             self.optimizer_D1 = FusedAdam(self.flat_D1, lr=cfg.learning_rate_D, betas=(0.9, 0.99)) if self.multi else None
         else:
-            self.optimizer = torch.optim.SGD(self.model.optim_parameters(cfg), lr=cfg.learning_rate,
+            self.optimizer = torch.optim.SGD(groups, lr=cfg.learning_rate,
                                              momentum=cfg.momentum, weight_decay=cfg.weight_decay)
             self.optimizer_D2 = torch.optim.Adam(self.model_D2.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
             self.optimizer_D1 = (torch.optim.Adam(self.model_D1.parameters(), lr=cfg.learning_rate_D, betas=(0.9, 0.99))
@@ -145,13 +156,37 @@ class AdaptSegTrainer:
             self.flat_G = FlatGrads(self.model.parameters())
             self.flat_D2 = FlatGrads(self.model_D2.parameters())
             self.flat_D1 = FlatGrads(self.model_D1.parameters()) if self.multi else None
+        self.sync_replicas()
+
+    def sync_replicas(self, group=None):
+        """Data-parallel replicas must start from identical weights and optimizer state: broadcast rank 0's (flat
+        parameter buffers, momentum / Adam moments, BatchNorm statistics) once when a process group is active.  Seeding
+        every rank alike already gives that; this makes it hold for a checkpoint loaded on rank 0 only."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        bufs = []
+        for fp in (self.flat_G, self.flat_D2, self.flat_D1):
+            if fp is not None and hasattr(fp, "values"):
+                bufs.append(fp.values)
+        if not bufs:   # torch.optim path: parameters are ordinary tensors
+            bufs = [p.data for m in (self.model, self.model_D2, self.model_D1) if m is not None for p in m.parameters()]
+        for opt in (self.optimizer, self.optimizer_D2, self.optimizer_D1):
+            for name in ("momentum_buffer", "exp_avg", "exp_avg_sq"):
+                if opt is not None and isinstance(getattr(opt, name, None), torch.Tensor):
+                    bufs.append(getattr(opt, name))
+        bufs += [b for b in self.model.buffers() if b.is_floating_point()]
+        for b in bufs:
+            dist.broadcast(b, src=0, group=group)
 
     # ---- pieces of the loop ------------------------------------------------------------------
     def _adjust_lr(self, i_iter):
         cfg = self.cfg
         lr = lr_poly(cfg.learning_rate, i_iter, cfg.num_steps, cfg.power)
         self.optimizer.param_groups[0]["lr"] = lr
-        self.optimizer.param_groups[1]["lr"] = lr * 10
+        if len(self.optimizer.param_groups) > 1:                 # train...:166-170
+            self.optimizer.param_groups[1]["lr"] = lr * 10
         lr_d = lr_poly(cfg.learning_rate_D, i_iter, cfg.num_steps, cfg.power)
         for opt in (self.optimizer_D1, self.optimizer_D2):
             if opt is not None:
@@ -169,7 +204,8 @@ class AdaptSegTrainer:
                 p.requires_grad = flag
 
     def _packs(self):
-        packs = [self.model.layer5._pack, self.model.layer6._pack, self.model_D2._pack]
+        heads = [self.model.classifier] if self.single_head else [self.model.layer5, self.model.layer6]
+        packs = [h._pack for h in heads] + [self.model_D2._pack]
         if self.multi:
             packs.append(self.model_D1._pack)
         return packs
@@ -199,14 +235,18 @@ class AdaptSegTrainer:
         lazy = cfg.lazy_upsample and cfg.fuse_softmax
         up_s = tuple(src_images.shape[-2:]) if lazy else None   # where the consumers upsample to (Tier-B)
         up_t = tuple(tgt_images.shape[-2:]) if lazy else None
-        if lazy:
-            pred1, pred2 = self.model.low_res_logits(src_images)
+        def preds(images):
+            if lazy:
+                return self.model.low_res_logits(images)
+            if self.single_head:   # DeeplabVGG.forward returns low-res logits; the caller interpolates (evaluate...:164-166)
+                return None, ops.upsample_bilinear(self.model(images), tuple(images.shape[-2:]))
+            return self.model(images)
 
+        pred1, pred2 = preds(src_images)
+        if lazy:
             def seg(z):
                 return ops.upsample_softmax_cross_entropy(z, up_s, src_labels, ignore_label=255)
         else:
-            pred1, pred2 = self.model(src_images)
-
             def seg(z):
                 return self.seg_loss(z, src_labels)
         loss_seg2 = seg(pred2)
@@ -219,7 +259,7 @@ class AdaptSegTrainer:
         (loss / it).backward()
         out["loss_seg2"] = loss_seg2.detach() / it
 
-        pred_target1, pred_target2 = self.model.low_res_logits(tgt_images) if lazy else self.model(tgt_images)
+        pred_target1, pred_target2 = preds(tgt_images)
         reuse = cfg.reuse_target_forward and cfg.fuse_softmax and ops.precision_mode() == "bf16"
         saved = {}
 
@@ -237,7 +277,8 @@ class AdaptSegTrainer:
             out["loss_adv_target1"] = loss_adv1.detach() / it
         (loss / it).backward()
         out["loss_adv_target2"] = loss_adv2.detach() / it
-        return out, (pred1.detach(), pred2.detach(), pred_target1.detach(), pred_target2.detach(), saved, up_s, up_t)
+        det = lambda t: None if t is None else t.detach()  # noqa: E731
+        return out, (det(pred1), det(pred2), det(pred_target1), det(pred_target2), saved, up_s, up_t)
 
     def _d_part(self, carry):
         """train...:635-679: both discriminators on the (detached) source and target predictions."""

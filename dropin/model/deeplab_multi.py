@@ -1,5 +1,17 @@
-"""Drop-in for the reference's model/deeplab_multi.py: same names, B200 kernels underneath."""
-from adaptsegnet_b200.model.deeplab_multi import (Bottleneck, Classifier_Module, DeeplabMulti,  # noqa: F401
-                                                   ResNetMulti)
+"""Drop-in for the reference's model/deeplab_multi.py: same names, B200 kernels underneath.
+
+Behind the unchanged scripts the model hands out lazy upsampled-logits handles (adaptsegnet_b200/lazy.py) so that the
+scripts' own CrossEntropyLoss / F.softmax / .detach() / nn.Upsample calls reach the fused kernels; ASN_LAZY_LOGITS=0
+returns ordinary full-resolution tensors instead (same values, more HBM traffic)."""
+import os
+
+from adaptsegnet_b200.model import deeplab_multi as _impl
+from adaptsegnet_b200.model.deeplab_multi import Bottleneck, Classifier_Module, ResNetMulti  # noqa: F401
 
 affine_par = True
+
+
+def DeeplabMulti(num_classes=21):
+    model = _impl.DeeplabMulti(num_classes)
+    model.lazy_outputs = os.environ.get("ASN_LAZY_LOGITS", "1") != "0"
+    return model
