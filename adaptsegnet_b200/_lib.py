@@ -71,15 +71,16 @@ SIGNATURES = {
     "asn_fcd_bwd_lowres": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, PP, c_int, c_int,
                                    c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "asn_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
-                             C.POINTER(c_float), c_int, c_float, c_float, c_int, c_void_p]),
+                             C.POINTER(c_float), c_int, c_float, c_float, c_int, c_float, c_void_p]),
     "asn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
-                              c_int64, c_void_p]),
+                              c_int64, c_float, c_void_p]),
     "asn_gemm_bf16_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "asn_gemm_bf16_nt_mn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
 }
 
+ABI_VERSION = 2   # include/asn_b200.h: ASN_ABI_VERSION
 _lib = None
 
 
@@ -101,8 +102,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.asn_abi_version() != 1:
-        raise AsnError(f"ABI version mismatch: library reports {lib.asn_abi_version()}, binding expects 1")
+    if lib.asn_abi_version() != ABI_VERSION:
+        raise AsnError(f"ABI version mismatch: library reports {lib.asn_abi_version()}, binding expects {ABI_VERSION}")
     _lib = lib
     return lib
 

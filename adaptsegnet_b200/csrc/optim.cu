@@ -27,6 +27,7 @@ struct SgdArgs {
   int n_seg;
   float lr[OPT_MAX_GROUPS];
   float momentum, weight_decay;
+  float grad_scale;             // gradients are multiplied by this first (1 / world size under data parallelism)
   int first_step;
 };
 
@@ -53,7 +54,11 @@ __global__ void __launch_bounds__(OPT_THREADS) sgd_step_kernel(const SgdArgs a) 
   const float lr = a.lr[__ldg(a.seg_group + lo)];
   const int repeat = __ldg(a.seg_repeat + lo);
   float4 p = reinterpret_cast<float4*>(a.p)[i];
-  const float4 g = ld_stream(reinterpret_cast<const float4*>(a.g) + i);
+  float4 g = ld_stream(reinterpret_cast<const float4*>(a.g) + i);
+  if (a.grad_scale != 1.f) {  // a separate rounded multiply: bit-identical to `grad.mul_(scale)` followed by the step
+    g.x = __fmul_rn(g.x, a.grad_scale); g.y = __fmul_rn(g.y, a.grad_scale);
+    g.z = __fmul_rn(g.z, a.grad_scale); g.w = __fmul_rn(g.w, a.grad_scale);
+  }
   float4 b = a.first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(a.buf)[i];
   const bool first = a.first_step != 0;
   sgd_one(p.x, g.x, b.x, lr, a.momentum, a.weight_decay, repeat, first);
@@ -66,11 +71,16 @@ __global__ void __launch_bounds__(OPT_THREADS) sgd_step_kernel(const SgdArgs a) 
 
 __global__ void __launch_bounds__(OPT_THREADS)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 long long n4, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2) {
+                 long long n4, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2,
+                 float grad_scale) {
   const long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x;
   if (i >= n4) return;
   float4 P = reinterpret_cast<float4*>(p)[i];
-  const float4 G = ld_stream(reinterpret_cast<const float4*>(g) + i);
+  float4 G = ld_stream(reinterpret_cast<const float4*>(g) + i);
+  if (grad_scale != 1.f) {
+    G.x = __fmul_rn(G.x, grad_scale); G.y = __fmul_rn(G.y, grad_scale);
+    G.z = __fmul_rn(G.z, grad_scale); G.w = __fmul_rn(G.w, grad_scale);
+  }
   float4 M = reinterpret_cast<float4*>(m)[i];
   float4 V = reinterpret_cast<float4*>(v)[i];
   auto one = [&](float& pp, float gg, float& mm, float& vv) {
@@ -95,7 +105,7 @@ using namespace asn;
 extern "C" int asn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n,
                             const int64_t* seg_begin, const int* seg_group, const int* seg_repeat, int n_seg,
                             const float* group_lr_host, int n_groups, float momentum, float weight_decay,
-                            int first_step, void* stream) {
+                            int first_step, float grad_scale, void* stream) {
   ASN_CHECK_ARG(params && grads && momentum_buf && seg_begin && seg_group && seg_repeat && group_lr_host,
                 "asn_sgd_step: null pointer");
   ASN_CHECK_ARG(n > 0 && n % 4 == 0 && n_seg > 0, "asn_sgd_step: n must be a positive multiple of 4 (got %lld)", (long long)n);
@@ -111,6 +121,7 @@ extern "C" int asn_sgd_step(float* params, const float* grads, float* momentum_b
   a.seg_group = seg_group; a.seg_repeat = seg_repeat; a.n_seg = n_seg;
   for (int i = 0; i < n_groups; ++i) a.lr[i] = group_lr_host[i];
   a.momentum = momentum; a.weight_decay = weight_decay; a.first_step = first_step;
+  a.grad_scale = grad_scale;
   prof::Scope ps("sgd_step", 0, 5.0 * 4.0 * (double)n, st);
   sgd_step_kernel<<<(unsigned)cdiv(a.n4, (long long)OPT_THREADS), OPT_THREADS, 0, st>>>(a);
   ASN_LAUNCH_CHECK();
@@ -118,7 +129,7 @@ extern "C" int asn_sgd_step(float* params, const float* grads, float* momentum_b
 }
 
 extern "C" int asn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                             float beta1, float beta2, float eps, int64_t step, void* stream) {
+                             float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream) {
   ASN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "asn_adam_step: null pointer");
   ASN_CHECK_ARG(n > 0 && n % 4 == 0 && step >= 1, "asn_adam_step: n must be a positive multiple of 4, step >= 1");
   ASN_CHECK_ARG(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
@@ -132,7 +143,7 @@ extern "C" int asn_adam_step(float* params, const float* grads, float* exp_avg, 
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   prof::Scope ps("adam_step", 0, 7.0 * 4.0 * (double)n, st);
   adam_step_kernel<<<(unsigned)cdiv(n / 4, (int64_t)OPT_THREADS), OPT_THREADS, 0, st>>>(
-      params, grads, exp_avg, exp_avg_sq, n / 4, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+      params, grads, exp_avg, exp_avg_sq, n / 4, beta1, beta2, eps, step_size, inv_sqrt_bc2, grad_scale);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }

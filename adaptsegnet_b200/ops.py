@@ -797,7 +797,13 @@ def fcd_saved_activations(out: torch.Tensor):
     if type(fn).__name__.startswith("_FcdF32"):
         return [t.detach().clone() for t in saved[1:5]]
     _x, _wpack, acts = saved
-    N, n_cls, ndf, H, W = fn.cfg[:5]
+    return fcd_decode_activations(acts, fn.cfg)
+
+
+def fcd_decode_activations(acts: torch.Tensor, cfg):
+    """conv1..conv4 post-LeakyReLU activations as fp32 NCHW tensors out of the packed bf16 NHWC buffer of a tensor-core
+    forward (`cfg` = the (N, n_cls, ndf, H, W, ...) tuple of that forward, e.g. FcdSaved.cfg)."""
+    N, n_cls, ndf, H, W = cfg[:5]
     lay = (C.c_int64 * 20)()
     check(_lib.load().asn_fcd_act_layout(N, n_cls, ndf, H, W, lay), "asn_fcd_act_layout")
     res = []

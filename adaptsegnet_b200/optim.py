@@ -74,10 +74,18 @@ class FlatParams:
     def mark_updated(self):
         """The kernels write through raw pointers: bump the parameters' autograd version counters by hand, so that
         anything keyed on them (ops.AsppWeightPack / FcdWeightPack re-pack when a version changes) sees the step."""
-        torch._C._increment_version(self.params)
+        try:
+            torch._C._increment_version(self.params)
+        except TypeError:   # older torch: one tensor per call
+            for p in self.params:
+                torch._C._increment_version(p)
 
     def all_reduce_mean(self, group=None):
+        """synchronous SUM all-reduce and division by the world size, in place"""
         self.all_reduce_finish(self.all_reduce_start(group), group)
+        if self.grad_scale != 1.0:
+            self.flat.mul_(self.grad_scale)
+            self.grad_scale = 1.0
 
     def all_reduce_start(self, group=None):
         """asynchronous SUM all-reduce of the flat gradient buffer (None when there is nothing to reduce)"""
@@ -88,11 +96,15 @@ class FlatParams:
         return None
 
     def all_reduce_finish(self, work, group=None):
+        """waits for the SUM all-reduce; the division by the world size happens inside the fused optimizer kernel
+        (`grad_scale`), not in a separate pass over the buffer"""
         import torch.distributed as dist
 
         if work is not None:
             work.wait()
-            self.flat.mul_(1.0 / dist.get_world_size(group))
+            self.grad_scale = 1.0 / dist.get_world_size(group)
+
+    grad_scale = 1.0   # what the next fused step multiplies the gradient by (reset by the step)
 
 
 class FusedSGD:
@@ -135,8 +147,9 @@ class FusedSGD:
         check(_lib.load().asn_sgd_step(f.values.data_ptr(), f.flat.data_ptr(), self.momentum_buffer.data_ptr(), f.numel,
                                        self.seg_begin.data_ptr(), self.seg_group.data_ptr(), self.seg_repeat.data_ptr(),
                                        len(f.params), lrs, len(self.param_groups), self.momentum, self.weight_decay,
-                                       int(self.steps == 0), _stream()), "asn_sgd_step")
+                                       int(self.steps == 0), float(f.grad_scale), _stream()), "asn_sgd_step")
         self.steps += 1
+        f.grad_scale = 1.0
         f.mark_updated()
 
     def zero_grad(self, set_to_none=False):
@@ -159,7 +172,9 @@ class FusedAdam:
         self.steps += 1
         check(_lib.load().asn_adam_step(f.values.data_ptr(), f.flat.data_ptr(), self.exp_avg.data_ptr(),
                                         self.exp_avg_sq.data_ptr(), f.numel, self.param_groups[0]["lr"], self.betas[0],
-                                        self.betas[1], self.eps, self.steps, _stream()), "asn_adam_step")
+                                        self.betas[1], self.eps, self.steps, float(f.grad_scale), _stream()),
+              "asn_adam_step")
+        f.grad_scale = 1.0
         f.mark_updated()
 
     def zero_grad(self, set_to_none=False):

@@ -97,6 +97,24 @@ class FlatGrads:
             self.flat.mul_(1.0 / dist.get_world_size(group))
 
 
+class _FlatView:
+    """the slice of a shared FlatParams that belongs to one module (gradient views for tests and tools)"""
+
+    def __init__(self, parent, begin, end):
+        self.parent, self.begin, self.end = parent, begin, end
+
+    @property
+    def flat(self):
+        return self.parent.flat[self.begin:self.end]
+
+    @property
+    def values(self):
+        return self.parent.values[self.begin:self.end]
+
+    def zero(self):
+        self.flat.zero_()
+
+
 class AdaptSegTrainer:
     """Holds G (DeeplabMulti), D1/D2 (FCDiscriminator), their optimizers and runs iterations."""
 
@@ -141,12 +159,19 @@ class AdaptSegTrainer:
         if self.fused_optimizers:
             from .optim import FlatParams, FusedAdam, FusedSGD
             self.flat_G = FlatParams(self.model.parameters())
-            self.flat_D2 = FlatParams(self.model_D2.parameters())
-            self.flat_D1 = FlatParams(self.model_D1.parameters()) if self.multi else None
+            # both discriminators in ONE flat buffer: the reference's two Adam optimizers (train...:538-540) have the same
+            # hyper-parameters, learning-rate schedule and step count, and Adam is element-wise -- one kernel and, under
+            # data parallelism, one all-reduce give bit-identical results to two
+            d_params = (list(self.model_D1.parameters()) if self.multi else []) + list(self.model_D2.parameters())
+            self.flat_D = FlatParams(d_params)
+            n1 = sum((p.numel() + 3) // 4 * 4 for p in self.model_D1.parameters()) if self.multi else 0
+            self.flat_D1 = _FlatView(self.flat_D, 0, n1) if self.multi else None
+            self.flat_D2 = _FlatView(self.flat_D, n1, self.flat_D.numel)
             self.optimizer = FusedSGD(self.flat_G, groups, lr=cfg.learning_rate,
                                       momentum=cfg.momentum, weight_decay=cfg.weight_decay)
-            self.optimizer_D2 = FusedAdam(self.flat_D2, lr=cfg.learning_rate_D, betas=(0.9, 0.99))
-            self.optimizer_D1 = FusedAdam(self.flat_D1, lr=cfg.learning_rate_D, betas=(0.9, 0.99)) if self.multi else None
+            self.optimizer_D = FusedAdam(self.flat_D, lr=cfg.learning_rate_D, betas=(0.9, 0.99))
+            self.optimizer_D2 = self.optimizer_D
+            self.optimizer_D1 = self.optimizer_D if self.multi else None
         else:
             self.optimizer = torch.optim.SGD(groups, lr=cfg.learning_rate,
                                              momentum=cfg.momentum, weight_decay=cfg.weight_decay)
@@ -156,6 +181,7 @@ class AdaptSegTrainer:
             self.flat_G = FlatGrads(self.model.parameters())
             self.flat_D2 = FlatGrads(self.model_D2.parameters())
             self.flat_D1 = FlatGrads(self.model_D1.parameters()) if self.multi else None
+            self.flat_D = self.optimizer_D = None
         self.sync_replicas()
 
     def sync_replicas(self, group=None):
@@ -167,12 +193,12 @@ class AdaptSegTrainer:
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return
         bufs = []
-        for fp in (self.flat_G, self.flat_D2, self.flat_D1):
+        for fp in (self.flat_G, self.flat_D):
             if fp is not None and hasattr(fp, "values"):
                 bufs.append(fp.values)
         if not bufs:   # torch.optim path: parameters are ordinary tensors
             bufs = [p.data for m in (self.model, self.model_D2, self.model_D1) if m is not None for p in m.parameters()]
-        for opt in (self.optimizer, self.optimizer_D2, self.optimizer_D1):
+        for opt in (self.optimizer, self.optimizer_D2, None if self.optimizer_D1 is self.optimizer_D2 else self.optimizer_D1):
             for name in ("momentum_buffer", "exp_avg", "exp_avg_sq"):
                 if opt is not None and isinstance(getattr(opt, name, None), torch.Tensor):
                     bufs.append(getattr(opt, name))
@@ -222,9 +248,12 @@ class AdaptSegTrainer:
         cfg = self.cfg
         it = cfg.iter_size
         self.flat_G.zero()
-        self.flat_D2.zero()
-        if self.multi:
-            self.flat_D1.zero()
+        if self.flat_D is not None:
+            self.flat_D.zero()
+        else:
+            self.flat_D2.zero()
+            if self.multi:
+                self.flat_D1.zero()
         out = {}
         # ---------------- train G: discriminators frozen (train...:583-587) ----------------
         self._set_requires_grad(self.model_D1, False)
@@ -346,7 +375,23 @@ class AdaptSegTrainer:
             out, carry = self._g_part(src_images, src_labels, tgt_images)
             pending = self.flat_G.all_reduce_start(group)
             out.update(self._d_part(carry))
-        # ---------------- data-parallel averaging, then the three optimizer steps ----------------
+        # ---------------- data-parallel averaging, then the optimizer steps (train...:681-683) ----------------
+        if self.flat_D is not None:
+            # one all-reduce for both discriminators, started right behind the discriminator part; the generator's (started
+            # before it) is waited for first, its fused SGD step then runs while the discriminators' reduce is in flight
+            pending_d = self.flat_D.all_reduce_start(group)
+            self.flat_G.all_reduce_finish(pending, group)
+            if do_optimizer_step:
+                self.optimizer.step()
+            self.flat_D.all_reduce_finish(pending_d, group)
+            if do_optimizer_step:
+                self.optimizer_D.step()
+            else:   # parity tests read averaged gradients
+                for fp in (self.flat_G, self.flat_D):
+                    if fp.grad_scale != 1.0:
+                        fp.flat.mul_(fp.grad_scale)
+                        fp.grad_scale = 1.0
+            return out
         self.flat_G.all_reduce_finish(pending, group)
         self.flat_D2.all_reduce_mean(group)
         if self.multi:

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ASN_ABI_VERSION 1
+#define ASN_ABI_VERSION 2
 
 enum {
   ASN_OK = 0,
@@ -280,13 +280,15 @@ ASN_API int asn_fcd_bwd_lowres(const float* dout, const float* z_low, int x_h, i
  *   its first step()); afterwards buf = momentum * buf + d_p per mention.
  *   asn_adam_step: torch.optim.Adam(lr, betas, eps) train...:351-355,538-540, stepped at :682-683;
  *   `step` is the 1-based step count (bias corrections).
+ *   grad_scale (both): the gradient is multiplied by it first (one rounded multiply, exactly `grad.mul_(scale)`):
+ *   1 / world size after a SUM all-reduce of the flat gradient buffer, 1 otherwise.
  * ---------------------------------------------------------------------------------- */
 ASN_API int asn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n,
                  const int64_t* seg_begin, const int* seg_group, const int* seg_repeat, int n_seg,
                  const float* group_lr_host, int n_groups, float momentum, float weight_decay,
-                 int first_step, void* stream);
+                 int first_step, float grad_scale, void* stream);
 ASN_API int asn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                  float beta1, float beta2, float eps, int64_t step, void* stream);
+                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * raw tcgen05 GEMM (exposed for tests / benchmarking of the tensor-core core):

@@ -34,7 +34,7 @@ def test_header_symbols_exported_and_bound(lib):
         assert hasattr(raw, n), f"{n} declared in include/asn_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.asn_abi_version() == 1
+    assert lib.asn_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_size_queries_without_gpu(lib):

@@ -51,7 +51,13 @@ def _worker(rank, world, port, out_dir):
     pending = fp.all_reduce_start()
     assert pending is not None
     fp.all_reduce_finish(pending)
-    torch.save({"local": local2, "avg": fp.flat.clone()}, os.path.join(out_dir, f"f{rank}.pt"))
+    # the division by the world size is deferred to the fused optimizer kernel (asn_sgd_step / asn_adam_step grad_scale)
+    assert fp.grad_scale == 1.0 / world
+    torch.save({"local": local2, "avg": fp.flat.clone() * fp.grad_scale}, os.path.join(out_dir, f"f{rank}.pt"))
+    fp.grad_scale = 1.0
+    fp.flat.copy_(local2)
+    fp.all_reduce_mean()          # the synchronous flavour scales in place
+    assert fp.grad_scale == 1.0 and torch.allclose(fp.flat, torch.load(os.path.join(out_dir, f"f{rank}.pt"))["avg"])
     # eval: per-rank confusion matrices summed exactly
     rng = np.random.RandomState(rank)
     hist = torch.from_numpy(rng.randint(0, 1000, (19, 19)).astype(np.int64))

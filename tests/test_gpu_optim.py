@@ -96,3 +96,39 @@ def test_flat_params_keep_module_semantics():
     assert flat.flat.abs().sum().item() > 0           # autograd accumulated into the flat gradient buffer
     net.load_state_dict({k: v * 2 for k, v in sd.items()})
     assert abs(flat.values.abs().sum().item() - 2 * sum(v.abs().sum().item() for v in sd.values())) < 1e-3
+
+
+def test_grad_scale_equals_scaling_the_gradient_first():
+    """data parallelism: `grad_scale = 1 / world` inside the fused step == `grad.mul_(1 / world)` before it, bit for bit"""
+    from adaptsegnet_b200.optim import FlatParams, FusedAdam, FusedSGD
+    res = []
+    for deferred in (True, False):
+        net, _ = _nets()
+        flat = FlatParams(net.parameters())
+        sgd = FusedSGD(flat, _groups(net), lr=0.01, momentum=0.9, weight_decay=5e-4)
+        rng = np.random.default_rng(4)
+        for step in range(3):
+            flat.flat.copy_(torch.from_numpy(rng.standard_normal(flat.numel).astype(np.float32)))
+            if deferred:
+                flat.grad_scale = 1.0 / 3.0
+            else:
+                flat.flat.mul_(1.0 / 3.0)
+            sgd.step()
+            assert flat.grad_scale == 1.0
+        res.append(flat.values.clone())
+    assert torch.equal(res[0], res[1])
+    res = []
+    for deferred in (True, False):
+        net, _ = _nets()
+        flat = FlatParams(net.parameters())
+        adam = FusedAdam(flat, lr=1e-3, betas=(0.9, 0.99))
+        rng = np.random.default_rng(5)
+        for step in range(3):
+            flat.flat.copy_(torch.from_numpy(rng.standard_normal(flat.numel).astype(np.float32)))
+            if deferred:
+                flat.grad_scale = 0.125
+            else:
+                flat.flat.mul_(0.125)
+            adam.step()
+        res.append(flat.values.clone())
+    assert torch.equal(res[0], res[1])

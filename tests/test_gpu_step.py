@@ -131,9 +131,9 @@ def test_cuda_graph_replay_equals_eager():
         assert rel_err(graph.flat_D1.flat.cpu().numpy(), eager.flat_D1.flat.cpu().numpy()) < 1e-3, it
         ge, gg = eager.model.layer6.conv2d_list[0].weight.grad, graph.model.layer6.conv2d_list[0].weight.grad
         assert rel_err(gg.cpu().numpy(), ge.cpu().numpy()) < 1e-3, it
-        eager.optimizer.step()       # move every weight so that the next replay must re-pack them
-        eager.optimizer_D1.step()
-        eager.optimizer_D2.step()
+        # move every weight so that the next replay must re-pack them (D1 and D2 share one fused Adam: step it once)
+        for opt in {id(o): o for o in (eager.optimizer, eager.optimizer_D1, eager.optimizer_D2)}.values():
+            opt.step()
 
 
 def test_trunk_bf16_autocast_mode():

@@ -21,7 +21,7 @@ def timeit(name, fn, n=10):
     e1.record(); torch.cuda.synchronize()
     res[name] = round(e0.elapsed_time(e1) / n, 4)
 timeit("sgd_G_step_ms", tr.optimizer.step)
-timeit("adam_D1_step_ms", tr.optimizer_D1.step)
+timeit("adam_D_step_ms", tr.optimizer_D.step)
 timeit("adam_D2_step_ms", tr.optimizer_D2.step)
 timeit("zero_flat_ms", lambda: (tr.flat_G.zero(), tr.flat_D1.zero(), tr.flat_D2.zero()))
 n_list = sum(len(g["params"]) for g in tr.optimizer.param_groups)
