@@ -119,7 +119,7 @@ class AdaptSegTrainer:
     """Holds G (DeeplabMulti), D1/D2 (FCDiscriminator), their optimizers and runs iterations."""
 
     def __init__(self, cfg: TrainConfig | None = None, device="cuda", model=None, model_D1=None, model_D2=None,
-                 use_cuda_graph=False, channels_last=False, fused_optimizers=None, trunk_bf16=False):
+                 use_cuda_graph=False, channels_last=False, fused_optimizers=None, trunk_bf16=False, overlap=False):
         """``use_cuda_graph``: capture everything of an iteration up to the gradients (both G forwards/backwards,
         all discriminator passes, ~2 300 kernel launches) into one CUDA graph and replay it; the gradient
         all-reduce and the three optimizer steps stay eager.  Same kernels, same order, no per-launch CPU cost."""
@@ -132,6 +132,11 @@ class AdaptSegTrainer:
         # fused optimizer steps on flat parameter buffers (optim.py) wherever the CUDA library runs; torch.optim on CPU
         self.fused_optimizers = (self.device.type == "cuda") if fused_optimizers is None else bool(fused_optimizers)
         self.use_cuda_graph = bool(use_cuda_graph)
+        # overlap: the source pipeline (forward, seg loss, backward) and the target pipeline (forward, discriminator
+        # forward, adversarial backward) of one iteration run on two CUDA streams, and the discriminator step runs beside
+        # the target backward (_grads_step_overlap).  Same kernels, same accumulation order, more of the GPU busy.
+        self.overlap = bool(overlap)
+        self._stream_t = None
         self.channels_last = bool(channels_last)
         self._graph = None
         self._capture_stream = None   # the stream warm-up and capture ran on (autograd remembers it per parameter)
@@ -238,8 +243,116 @@ class AdaptSegTrainer:
 
     def _grads_step(self, src_images, src_labels, tgt_images):
         """Everything of train...:578-679: forwards, losses, backwards; gradients end up in the flat buffers."""
+        if self.overlap:
+            return self._grads_step_overlap(src_images, src_labels, tgt_images)
         out, carry = self._g_part(src_images, src_labels, tgt_images)
         out.update(self._d_part(carry))
+        return out
+
+    def _grads_step_overlap(self, src_images, src_labels, tgt_images):
+        """The same iteration as _g_part + _d_part, scheduled on two streams.  What depends on what (train...:578-679):
+
+          source pipeline  S: forward(src) -> seg loss -> backward(src)                      needs the weights only
+          target pipeline  T: forward(tgt) -> D(softmax(pred_tgt)) -> adversarial loss -> backward(tgt)
+                              forward(tgt) must follow forward(src) (both update the BatchNorm running statistics, in this
+                              order); its backward accumulates into the generator's gradients AFTER backward(src)'s
+          discriminator    D: D(pred_src.detach()) + backward, replay of T's discriminator forward + backward
+                              needs S's and T's predictions and the (unchanged) discriminator weights
+
+        The current stream runs S, then D; stream `_stream_t` forks after forward(src) and runs T.  autograd executes every
+        backward node on the stream of its forward op and every parameter's gradient accumulation on the stream the
+        parameter was first used on (the current one), inserting the event waits itself -- so backward(tgt)'s convolutions
+        run on `_stream_t` beside backward(src) and the discriminator step, while the `+=` into the flat gradient buffers
+        stays on one stream, in the reference's order (source first, then target).  Host order matters only in so far as
+        every stream executes what it is handed in order: the discriminator step is issued BEFORE backward(tgt), because
+        backward(tgt)'s gradient accumulations land on the current stream and would otherwise sit in front of it."""
+        cfg = self.cfg
+        it = cfg.iter_size
+        main = torch.cuda.current_stream()
+        if self._stream_t is None:
+            self._stream_t = torch.cuda.Stream()
+        st = self._stream_t
+        self.flat_G.zero()
+        if self.flat_D is not None:
+            self.flat_D.zero()
+        else:
+            self.flat_D2.zero()
+            if self.multi:
+                self.flat_D1.zero()
+        out = {}
+        self._set_requires_grad(self.model_D1, False)
+        self._set_requires_grad(self.model_D2, False)
+        if self.channels_last:
+            src_images = src_images.contiguous(memory_format=torch.channels_last)
+            tgt_images = tgt_images.contiguous(memory_format=torch.channels_last)
+        lazy = cfg.lazy_upsample and cfg.fuse_softmax
+        up_s = tuple(src_images.shape[-2:]) if lazy else None
+        up_t = tuple(tgt_images.shape[-2:]) if lazy else None
+        Ds = [(self.model_D2, "D2", cfg.lambda_adv_target2)]
+        if self.multi:
+            Ds.insert(0, (self.model_D1, "D1", cfg.lambda_adv_target1))
+        if ops.precision_mode() == "bf16":
+            for D, _, _ in Ds:      # weight packs are shared by both streams: pack them here, before the fork
+                D._pack.get(D._params(), cfg.num_classes, D.conv1.weight.shape[0])
+
+        def preds(images):
+            if lazy:
+                return self.model.low_res_logits(images)
+            if self.single_head:
+                return None, ops.upsample_bilinear(self.model(images), tuple(images.shape[-2:]))
+            return self.model(images)
+
+        # ---- S: forward(src), seg loss ----
+        pred1, pred2 = preds(src_images)
+        seg = (lambda z: ops.upsample_softmax_cross_entropy(z, up_s, src_labels, ignore_label=255)) if lazy else \
+            (lambda z: self.seg_loss(z, src_labels))
+        loss_seg2 = seg(pred2)
+        loss = loss_seg2
+        if self.multi:
+            loss_seg1 = seg(pred1)
+            loss = loss_seg2 + cfg.lambda_seg * loss_seg1
+            out["loss_seg1"] = loss_seg1.detach() / it
+        out["loss_seg2"] = loss_seg2.detach() / it
+        # ---- T (forked): forward(tgt), discriminator forward, adversarial loss ----
+        st.wait_stream(main)
+        reuse = cfg.reuse_target_forward and cfg.fuse_softmax and ops.precision_mode() == "bf16"
+        saved, adv = {}, {}
+        with torch.cuda.stream(st):
+            pred_t = dict(zip(("D1", "D2"), preds(tgt_images)))
+            loss_t = 0
+            for D, key, lam in Ds:
+                if reuse:
+                    d, saved[key] = D(pred_t[key], from_logits=True, return_saved=True, up_size=up_t)
+                else:
+                    d = self._d_out(D, pred_t[key], up_t)
+                adv[key] = self.bce_loss(d, SOURCE_LABEL)
+                loss_t = lam * adv[key] + loss_t
+            loss_t = loss_t / it
+            fwd_t_done = torch.cuda.Event()
+            fwd_t_done.record(st)
+        # ---- S: backward(src) (beside T's forward) ----
+        (loss / it).backward()
+        # ---- D: the discriminator step on the current stream ----
+        self._set_requires_grad(self.model_D1, True)
+        self._set_requires_grad(self.model_D2, True)
+        pred_s = {"D1": pred1, "D2": pred2}
+        l_src = {}
+        for D, key, _ in Ds:         # source passes first: they need nothing from T
+            l_src[key] = self.bce_loss(self._d_out(D, pred_s[key].detach(), up_s), SOURCE_LABEL) / it / 2
+            l_src[key].backward()
+        main.wait_event(fwd_t_done)  # T's predictions and discriminator activations exist from here on
+        for D, key, _ in Ds:
+            d_tgt = D.replay(saved[key]) if saved.get(key) is not None else self._d_out(D, pred_t[key].detach(), up_t)
+            l_tgt = self.bce_loss(d_tgt, TARGET_LABEL) / it / 2
+            l_tgt.backward()
+            out["loss_" + key] = l_src[key].detach() + l_tgt.detach()
+        # ---- T: backward(tgt); its convolutions run on `_stream_t`, the accumulation into the flat buffers on `main` ----
+        with torch.cuda.stream(st):
+            loss_t.backward()
+        main.wait_stream(st)
+        for key in adv:
+            out["loss_adv_target" + key[1]] = adv[key].detach() / it
+        self._keep = (pred1, pred2, pred_t, saved, adv)   # cross-stream tensors stay alive until the next iteration
         return out
 
     def _g_part(self, src_images, src_labels, tgt_images):
@@ -349,6 +462,12 @@ class AdaptSegTrainer:
         # both captures (and the warm-up above) on ONE stream: autograd ties every parameter's gradient accumulation to
         # the stream it first ran on
         self._graph = torch.cuda.CUDAGraph()
+        if self.overlap:   # one graph: the two pipelines and the discriminator step are interleaved inside it
+            self._graph_d = None
+            with torch.cuda.graph(self._graph, stream=side):
+                self._static_out = self._grads_step_overlap(*self._static_in)
+            self.model.load_state_dict(bn_state, strict=False)
+            return
         with torch.cuda.graph(self._graph, stream=side):
             out_g, self._carry = self._g_part(*self._static_in)   # (kept alive: the D graph reads these buffers)
         self._graph_d = torch.cuda.CUDAGraph()
@@ -369,8 +488,12 @@ class AdaptSegTrainer:
                     dst.copy_(src, non_blocking=True)
             self._graph.replay()
             pending = self.flat_G.all_reduce_start(group)   # 178 MB over NVLink while the discriminators train
-            self._graph_d.replay()
+            if self._graph_d is not None:
+                self._graph_d.replay()
             out = self._static_out
+        elif self.overlap:
+            out = self._grads_step_overlap(src_images, src_labels, tgt_images)
+            pending = self.flat_G.all_reduce_start(group)
         else:
             out, carry = self._g_part(src_images, src_labels, tgt_images)
             pending = self.flat_G.all_reduce_start(group)

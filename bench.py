@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the iteration (up to the gradients) as a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
+    ap.add_argument("--overlap", type=int, default=0,
+                    help="1: source and target pipelines of the iteration on two CUDA streams, discriminator step beside the "
+                         "target backward (AdaptSegTrainer overlap=True)")
     ap.add_argument("--channels-last", type=int, default=1, help="run the (unchanged) trunk in channels_last")
     ap.add_argument("--no-kernel-events", action="store_true", help="skip the per-kernel event pass (ncu runs)")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
@@ -501,8 +504,11 @@ def workload_config(args, world):
         return cfg
     cfg.update({"parallelism": f"dp{world} (NCCL all-reduce of 3 flat gradient buffers per step)",
                 "hot_path": "libasn_b200 sm_100a kernels (tcgen05 heads + discriminators, fused losses)",
-                "execution": ("forward/backward of the iteration replayed as two CUDA graphs (generator part, discriminator "
-                              "part; the generator's gradient all-reduce overlaps the second); fused optimizer steps eager"
+                "execution": (("forward/backward of the iteration replayed as ONE CUDA graph with two streams inside: the source "
+                               "pipeline and the discriminator step on one, the target pipeline on the other; fused optimizer "
+                               "steps eager" if args.overlap else
+                               "forward/backward of the iteration replayed as two CUDA graphs (generator part, discriminator "
+                               "part; the generator's gradient all-reduce overlaps the second); fused optimizer steps eager")
                               if args.cuda_graph else "eager"),
                 "trunk": ("ResNet-101 as PyTorch modules on cuDNN (" + ("bf16 autocast" if args.trunk_dtype == "bf16" else "TF32")
                           + (", channels_last" if args.channels_last else "") + "), timed, not rewritten"),
@@ -538,7 +544,7 @@ def run_b200(args):
     torch.manual_seed(SEED)  # identical replicas
     trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"), device=dev,
                               use_cuda_graph=bool(args.cuda_graph), channels_last=bool(args.channels_last),
-                              trunk_bf16=args.trunk_dtype == "bf16")
+                              trunk_bf16=args.trunk_dtype == "bf16", overlap=bool(args.overlap))
     src_h, lab_h, tgt_h = synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
     src_h, lab_h, tgt_h = src_h.pin_memory(), lab_h.pin_memory(), tgt_h.pin_memory()
     src, lab, tgt = src_h.to(dev), lab_h.to(dev), tgt_h.to(dev)
@@ -717,7 +723,7 @@ def run_b200(args):
             torch.manual_seed(SEED)
             trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"),
                                       device=dev, use_cuda_graph=bool(args.cuda_graph),
-                                      channels_last=bool(args.channels_last), trunk_bf16=True)
+                                      channels_last=bool(args.channels_last), trunk_bf16=True, overlap=bool(args.overlap))
             for _ in range(max(args.warmup, 3) + 1):
                 step_resident(0)
             ms_bf16 = timed(args.steps, step_resident)
