@@ -17,6 +17,7 @@ PP = C.POINTER(c_void_p)
 # name -> (restype, argtypes); mirrors include/asn_b200.h one to one
 SIGNATURES = {
     "asn_abi_version": (c_int, []),
+    "asn_build_id": (C.c_char_p, []),
     "asn_last_error": (C.c_char_p, []),
     "asn_sm_count": (c_int, [C.POINTER(c_int)]),
     "asn_launch_count": (c_int64, []),

@@ -132,6 +132,10 @@ extern "C" int64_t asn_prof_report(char* buf, int64_t cap) {
   return (int64_t)out.size() + 1;
 }
 
+#ifndef ASN_BUILD_ID
+#define ASN_BUILD_ID "unknown"
+#endif
+extern "C" const char* asn_build_id(void) { return ASN_BUILD_ID; }
 extern "C" int asn_abi_version(void) { return ASN_ABI_VERSION; }
 extern "C" const char* asn_last_error(void) { return asn::g_err; }
 extern "C" int asn_sm_count(int* out_host) {

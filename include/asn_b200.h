@@ -54,6 +54,9 @@ enum { ASN_LABEL_U8 = 0, ASN_LABEL_I32 = 1, ASN_LABEL_I64 = 2 };
 enum { ASN_GAN_BCE = 0, ASN_GAN_MSE = 1 };
 
 ASN_API int asn_abi_version(void);
+/* sha256 prefix over the sources (csrc, this header) and compiler flags the library was built from (adaptsegnet_b200/
+ * _build.py::source_id): lets a run prove which tree produced the binary it loaded */
+ASN_API const char* asn_build_id(void);
 ASN_API const char* asn_last_error(void);
 /* number of SMs of the current device (grids are sized from it) */
 ASN_API int asn_sm_count(int* out_host);

@@ -64,10 +64,10 @@ def test_train_script_multi_level_runs_unchanged(tmp_path, lazy):
     if lazy == "1":
         test_train_script_multi_level_runs_unchanged.lazy_lines = lines
     elif hasattr(test_train_script_multi_level_runs_unchanged, "lazy_lines"):
-        # Tier-B handles and materialised tensors print the same losses (3 decimals) for the same seeds
+        # Tier-B handles and materialised tensors print the same losses (to 2e-3: different kernels, same mathematics)
         a = re.findall(r"= ([0-9.]+)", test_train_script_multi_level_runs_unchanged.lazy_lines[0].split(",", 1)[1])
         b = re.findall(r"= ([0-9.]+)", lines[0].split(",", 1)[1])
-        assert np.allclose([float(x) for x in a], [float(x) for x in b], atol=2e-3)
+        assert np.allclose([float(x) for x in a], [float(x) for x in b], rtol=2e-3, atol=2e-3)
 
 
 def test_evaluate_script_runs_unchanged(tmp_path):
