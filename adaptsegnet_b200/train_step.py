@@ -137,6 +137,11 @@ class AdaptSegTrainer:
         # the target backward (_grads_step_overlap).  Same kernels, same accumulation order, more of the GPU busy.
         self.overlap = bool(overlap)
         self._stream_t = None
+        if self.overlap:   # gradients produced on `_stream_t` are accumulated on the current stream on purpose (see below)
+            try:
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except AttributeError:
+                pass
         self.channels_last = bool(channels_last)
         self._graph = None
         self._capture_stream = None   # the stream warm-up and capture ran on (autograd remembers it per parameter)

@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the iteration (up to the gradients) as a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
-    ap.add_argument("--overlap", type=int, default=0,
+    ap.add_argument("--overlap", type=int, default=1,
                     help="1: source and target pipelines of the iteration on two CUDA streams, discriminator step beside the "
                          "target backward (AdaptSegTrainer overlap=True)")
     ap.add_argument("--channels-last", type=int, default=1, help="run the (unchanged) trunk in channels_last")
