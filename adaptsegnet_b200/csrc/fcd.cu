@@ -665,6 +665,8 @@ static int encode_plain(CUtensorMap* m, const __nv_bfloat16* base, int N, int H,
 namespace halo {  // halo.cu: conv1 forward from shared-memory halo tiles (ASN_HALO=0 falls back to the ring kernel)
 int conv2_dgrad(const __nv_bfloat16* dpre, const __nv_bfloat16* wd, const __nv_bfloat16* mask_src, __nv_bfloat16* out,
                 int N, int Hin, int Win, int H2, int W2, float mask_slope, double flops, double bytes, cudaStream_t st);
+int conv1_dgrad(const __nv_bfloat16* dpre, const __nv_bfloat16* wd, __nv_bfloat16* out, int N, int Hin, int Win, int W0p,
+                int H1, int W1, double flops, double bytes, cudaStream_t st);
 int conv1_fwd(const __nv_bfloat16* in, const __nv_bfloat16* wf, const float* bias, __nv_bfloat16* out, int N, int H0,
               int W0p, int OH, int OW, float slope, double flops, double bytes, cudaStream_t st);
 }
@@ -758,6 +760,11 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
   if (use_halo2 && l == 2 && rows == 64 && Cout == 128)
     return halo::conv2_dgrad(dpre, wd, act_in, din, p.N, Hin, Win, Hout, Wout, FCD_SLOPE, layer_flops(p, l),
                              layer_bytes(p, l, 0) + layer_bytes(p, l, 1) + 2.0 * 4 * rows * 4 * Cout, st);
+  // conv1 (64 -> 19 (32) channels, writes the packed-input layout): halo-tile kernel, ASN_HALO1D=0 for the ring kernel
+  static const bool use_halo1d = !(getenv("ASN_HALO1D") != nullptr && getenv("ASN_HALO1D")[0] == '0');
+  if (use_halo1d && l == 1 && rows == 32 && Cout == 64)
+    return halo::conv1_dgrad(dpre, wd, din, p.N, Hin, Win, p.W0p, Hout, Wout, layer_flops(p, l),
+                             layer_bytes(p, l, 0) + 2.0 * 4 * rows * 4 * Cout, st);
   CUtensorMap maps[5];
   int rc;
   if ((rc = encode_plain(&maps[0], dpre, p.N, Hout, Wout, Cout, th, tw))) return rc;

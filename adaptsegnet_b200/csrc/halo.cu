@@ -461,5 +461,204 @@ int conv2_dgrad(const __nv_bfloat16* dpre, const __nv_bfloat16* wd, const __nv_b
   return ASN_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv1 data gradient (dPre1 [H1][W1][64] -> dA0 [H0][W0p][32], the packed-input layout: pixel w at padded column w + 1;
+// no LeakyReLU mask below the first layer).  Same construction as conv2_dgrad, one size smaller: Cout = 64 is ONE
+// 64-channel chunk, so a base tile is a single (7+2) x (16+2) halo box (20 KB); the 16 (class, tap) weight tiles are
+// [32 ci][64 co] = 4 KB each, 64 KB for all four parity classes -- resident, and every CTA computes all four classes of
+// its base tiles (4 x 32 accumulator columns, double buffered in 256 TMEM columns).  Per base tile 20 KB enter the SM
+// instead of 16 boxes x 16 KB + weights.  Epilogue: a thread owns base position (i, j) of one ROW parity rh and reads
+// the 64 accumulator columns of classes (rh, 0) and (rh, 1): 2 x 32 channels = the 128 contiguous bytes of pixels
+// (2i+rh, 2j) and (2i+rh, 2j+1); rows are staged XOR-swizzled in shared memory and leave as 16-byte chunks with
+// consecutive lanes on consecutive chunks.
+constexpr int E_THREADS = 320;
+struct ELayout {
+  static constexpr int A_OFF = 0;
+  static constexpr int W_OFF = D_NSTAGE * D_STAGE;       // 63 KB
+  static constexpr int W_BYTES = 16 * 4096;              // 4 classes x 4 taps x [32 ci][64 co]
+  static constexpr int BAR_OFF = W_OFF + W_BYTES;
+  static constexpr int STG_OFF = BAR_OFF + 128;
+  static constexpr int ROW_OFF = STG_OFF + 8 * 32 * 128;  // per epilogue warp: 32 rows x 128 bytes
+  static constexpr int TOTAL = ROW_OFF + 8 * 32 * 8 + 1024;
+};
+static_assert(ELayout::W_OFF % 1024 == 0 && ELayout::TOTAL <= 227 * 1024, "conv1 dgrad shared-memory layout");
+
+struct EArgs {
+  int N, Hin, Win, W0p, tiles_h, tiles_w;   // Hin x Win: the discriminator's input resolution; W0p: padded row pitch of dA0
+  __nv_bfloat16* out;                       // dA0 [N][Hin][W0p][32]
+};
+
+__global__ void __launch_bounds__(E_THREADS, 1)
+conv1_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar = base + ELayout::BAR_OFF;
+  const uint32_t w_bar = bar;
+  auto full_bar = [&](int s) { return bar + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar + 8u * (4 + s); };
+  auto tfull_bar = [&](int s) { return bar + 8u * (7 + s); };
+  auto tempty_bar = [&](int s) { return bar + 8u * (9 + s); };
+  const uint32_t holder = bar + 8u * 11;
+  volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen + ELayout::BAR_OFF + 88);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = a.N * a.tiles_h * a.tiles_w;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    mbar_init(w_bar, 1);
+    for (int s = 0; s < D_NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(holder, 256);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *holder_ptr;
+  const uint32_t sw = base + ELayout::W_OFF;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: Wd rows z*32 + ci, K = t*64 + co; tile (z*4 + t) = [32 ci][64 co]
+      mbar_arrive_expect_tx(w_bar, ELayout::W_BYTES);
+      for (int z = 0; z < 4; ++z)
+        for (int t = 0; t < 4; ++t) tma_load_2d(&map_w, sw + (z * 4 + t) * 4096, w_bar, t * 64, z * 32);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int tx = tile % a.tiles_w, ty = (tile / a.tiles_w) % a.tiles_h, img = tile / (a.tiles_w * a.tiles_h);
+        const int s = it % D_NSTAGE;
+        mbar_wait(empty_bar(s), ((it / D_NSTAGE) & 1) ^ 1);
+        mbar_arrive_expect_tx(full_bar(s), D_BOX_BYTES);
+        tma_load_4d(&map_a, base + ELayout::A_OFF + s * D_STAGE, full_bar(s), 0, tx * D_TW - 1, ty * D_TH - 1, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 32, 0, 0);
+      mbar_wait(w_bar, 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1, s = it % D_NSTAGE;
+        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        mbar_wait(full_bar(s), (it / D_NSTAGE) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + ELayout::A_OFF + s * D_STAGE;
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+          const int rh = z >> 1, rw = z & 1;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int thh = t >> 1, tww = t & 1;
+            const int dh = rh == 0 ? (thh == 0 ? 0 : -1) : (thh == 0 ? 1 : 0);
+            const int dw = rw == 0 ? (tww == 0 ? 0 : -1) : (tww == 0 ? 1 : 0);
+            const uint32_t ab = sa + ((dh + 1) * D_PITCH + (dw + 1)) * 128;
+            const uint32_t wb = sw + (z * 4 + t) * 4096;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss(tmem + acc * 128 + z * 32, make_smem_desc(ab + k * 32, 16, 1024),
+                         make_smem_desc(wb + k * 32, 16, 1024), idesc, (t > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        mma_commit(empty_bar(s));
+        mma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int ew = warp - 2, q = warp & 3;   // TMEM lane quarter this warp may read
+    const int rh = ew >> 2;                  // warps 2..5: row parity 0, warps 6..9: row parity 1
+    uint8_t* stg = gen + ELayout::STG_OFF + ew * (32 * 128);
+    long long* row_tab = reinterpret_cast<long long*>(gen + ELayout::ROW_OFF) + ew * 32;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int tx = tile % a.tiles_w, ty = (tile / a.tiles_w) % a.tiles_h, img = tile / (a.tiles_w * a.tiles_h);
+      {
+        const int m = q * 32 + lane;
+        const int dy = m / D_PITCH, dx = m - dy * D_PITCH;
+        const int ih = 2 * (ty * D_TH + dy) + rh, iw = 2 * (tx * D_TW + dx);
+        const bool ok = dy < D_TH && dx < D_TW && ih < a.Hin && iw < a.Win;
+        __syncwarp();
+        // element offset of pixel (ih, iw) in the packed layout (padded column iw + 1); low bit: pixel iw + 1 exists too
+        row_tab[lane] = ok ? ((((long long)img * a.Hin + ih) * a.W0p + iw + 1) * 32) * 2 + (iw + 1 < a.Win ? 1 : 0) : -1;
+      }
+      mbar_wait(tfull_bar(acc), (it >> 1) & 1);
+      tc_fence_after();
+      float v[64];
+      const uint32_t ta = tmem + acc * 128 + rh * 64 + ((uint32_t)(q * 32) << 16);
+      tmem_ld32(ta, v);
+      tmem_ld32(ta + 32, v + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((c8 ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int row = jj * 4 + (lane >> 3), ch = lane & 7;   // chunks 0..3: pixel iw, chunks 4..7: pixel iw + 1
+        const long long e = row_tab[row];
+        if (e >= 0 && (ch < 4 || (e & 1))) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(a.out + (e >> 1) + ch * 8) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem, 256);
+  }
+}
+
+// dpre: dPre1 [N][H1][W1][64]; wd: conv1's dgrad pack [4*32][256]; out: dA0 [N][Hin][W0p][32]
+int conv1_dgrad(const __nv_bfloat16* dpre, const __nv_bfloat16* wd, __nv_bfloat16* out, int N, int Hin, int Win, int W0p,
+                int H1, int W1, double flops, double bytes, cudaStream_t st) {
+  CUtensorMap map_a, map_w;
+  int rc;
+  uint64_t dims[4] = {64, (uint64_t)W1, (uint64_t)H1, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)64 * 2, (uint64_t)W1 * 64 * 2, (uint64_t)H1 * W1 * 64 * 2};
+  if ((rc = encode_4d(&map_a, dpre, dims, str, D_PITCH, D_BOX_H))) return rc;
+  if ((rc = encode_2d(&map_w, wd, 256, 4 * 32, 256 * 2, 32))) return rc;
+  EArgs a;
+  a.N = N; a.Hin = Hin; a.Win = Win; a.W0p = W0p;
+  a.tiles_h = cdiv(cdiv(Hin, 2), D_TH);
+  a.tiles_w = cdiv(cdiv(Win, 2), D_TW);
+  a.out = out;
+  static PerDevice configured;
+  if (!configured.get()) {
+    ASN_CUDA(cudaFuncSetAttribute(conv1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ELayout::TOTAL));
+    configured.set(1);
+  }
+  const long long tiles = (long long)N * a.tiles_h * a.tiles_w;
+  const int ctas = (int)(tiles < sm_count() ? tiles : sm_count());
+  prof::Scope ps("fcd_conv1_dgrad", flops, bytes, st);
+  conv1_dgrad_kernel<<<ctas, E_THREADS, ELayout::TOTAL, st>>>(map_a, map_w, a);
+  ASN_LAUNCH_CHECK();
+  return ASN_OK;
+}
+
 }  // namespace halo
 }  // namespace asn

@@ -629,6 +629,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     trainer.use_cuda_graph = False
+    overlap_mode, trainer.overlap = trainer.overlap, False   # per-kernel times: one kernel at a time (sequential schedule)
     # on the stream the graphs were captured on: autograd keeps each parameter's gradient accumulation on the stream of
     # its first backward, and would warn about (and synchronise for) a different one
     ev_stream = getattr(trainer, "_capture_stream", None) or torch.cuda.current_stream()
@@ -643,6 +644,7 @@ def run_b200(args):
         prof.enable(False)
     torch.cuda.current_stream().wait_stream(ev_stream)
     trainer.use_cuda_graph = graph_mode
+    trainer.overlap = overlap_mode
 
     if rank == 0:
         peaks = load_peaks()
@@ -700,6 +702,9 @@ def run_b200(args):
                 "gpu_launches": int(launches) * world, "gpu_launches_per_rank": int(launches), "roofline": roof,
                 "cuda_graph": bool(graph_mode), "cuda_graph_note": graph_note,
                 "eager_ms_per_step_with_kernel_events": ms_eager / args.steps,
+                "kernel_events_note": "per-kernel CUDA events are taken in the sequential single-stream eager schedule (one "
+                                      "kernel at a time); the headline runs the same kernels as a CUDA graph"
+                                      + (" with the two-stream schedule" if overlap_mode else ""),
                 "hot_path_ms_per_step": hot_ms, "hot_path_kernels": breakdown}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan, budget_s=60.0)
