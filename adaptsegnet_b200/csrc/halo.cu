@@ -244,7 +244,6 @@ constexpr int D_BOX_BYTES = D_BOX_H * D_PITCH * 128;     // 162 rows x 128 B = 2
 constexpr int D_STAGE = 21504;                           // 168 rows: the last window (row 38 + 127 = 165) stays inside
 constexpr int D_NSTAGE = 3;
 constexpr int D_THREADS = 320;                           // producer, MMA issuer, 8 epilogue warps
-constexpr int D_CHUNK = 16, D_EPI_PITCH = 20;            // epilogue staging: 16 columns per pass, 20 floats per row
 
 struct DLayout {
   static constexpr int A_OFF = 0;
@@ -252,7 +251,7 @@ struct DLayout {
   static constexpr int W_BYTES = 16 * 8192;              // 2 classes x 4 taps x 2 chunks x [64 rows][64 k]
   static constexpr int BAR_OFF = W_OFF + W_BYTES;
   static constexpr int STG_OFF = BAR_OFF + 128;
-  static constexpr int ROW_OFF = STG_OFF + 8 * 32 * D_EPI_PITCH * 4;
+  static constexpr int ROW_OFF = STG_OFF + 8 * 32 * 128;   // per epilogue warp: 32 rows x 128 bytes (bf16, two pixels x 32 ch)
   static constexpr int TOTAL = ROW_OFF + 8 * 32 * 8 + 1024;
 };
 static_assert(DLayout::W_OFF % 1024 == 0 && D_STAGE % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned bases");
@@ -364,64 +363,70 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else {
+    // Epilogue.  A thread owns base position (i, j) = accumulator row m of BOTH column classes rw = 0, 1 of this CTA's
+    // row parity and one half of the 64 channels (warps 2..5: channels 0..31, warps 6..9: 32..63): pixels (2i+rh, 2j) and
+    // (2i+rh, 2j+1) are neighbours in dPre1, so its 2 x 32 values are two 64-byte runs 128 bytes apart.  The LeakyReLU
+    // masks of those runs (A1 at the same offsets) are fetched BEFORE the wait for the accumulator -- their latency hides
+    // behind the MMAs -- and applied in fp32; the bf16 rows are staged XOR-swizzled in shared memory and leave as
+    // 16-byte chunks with consecutive lanes on consecutive chunks (full 32-byte sectors, no partial writes).
     const int ew = warp - 2, q = warp & 3;   // TMEM lane quarter this warp may read
-    const int zi = ew >> 2;                  // warps 2..5: class rw = 0, warps 6..9: class rw = 1
-    float* stg = reinterpret_cast<float*>(gen + DLayout::STG_OFF) + ew * (32 * D_EPI_PITCH);
+    const int half = ew >> 2;                // channel half
+    uint8_t* stg = gen + DLayout::STG_OFF + ew * (32 * 128);
     long long* row_tab = reinterpret_cast<long long*>(gen + DLayout::ROW_OFF) + ew * 32;
-    const int rr = lane >> 2, cq = lane & 3;
     uint32_t tit = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tit) {
       const int acc = tit & 1;
       const int tx = tile % a.tiles_w, ty = (tile / a.tiles_w) % a.tiles_h, img = tile / (a.tiles_w * a.tiles_h);
-      {
-        const int m = q * 32 + lane;
-        const int dy = m / D_PITCH, dx = m - dy * D_PITCH;
-        const int ih = 2 * (ty * D_TH + dy) + rh, iw = 2 * (tx * D_TW + dx) + zi;
-        const bool ok = dy < D_TH && dx < D_TW && ih < a.Hin && iw < a.Win;
-        __syncwarp();
-        row_tab[lane] = ok ? (((long long)img * a.Hin + ih) * a.Win + iw) * 64 : -1;
-      }
+      const int m = q * 32 + lane;
+      const int dy = m / D_PITCH, dx = m - dy * D_PITCH;
+      const int ih = 2 * (ty * D_TH + dy) + rh, iw = 2 * (tx * D_TW + dx);
+      const bool ok0 = dy < D_TH && dx < D_TW && ih < a.Hin && iw < a.Win, ok1 = ok0 && iw + 1 < a.Win;
+      // element offset of this thread's first run: pixel (ih, iw), channels [32 * half, +32); the second run is + 64
+      const long long off = (((long long)img * a.Hin + ih) * a.Win + iw) * 64 + half * 32;
+      __syncwarp();
+      row_tab[lane] = ok0 ? off * 2 + (ok1 ? 1 : 0) : -1;
+      uint4 mk[2][4];
+#pragma unroll
+      for (int z = 0; z < 2; ++z)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          mk[z][c] = (z == 0 ? ok0 : ok1) ? __ldg(reinterpret_cast<const uint4*>(a.mask_src + off + z * 64) + c)
+                                          : make_uint4(0u, 0u, 0u, 0u);
       mbar_wait(tfull_bar(acc), (tit >> 1) & 1);
       tc_fence_after();
-      const uint32_t ta = tmem + acc * 128 + zi * 64 + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < 64; c += D_CHUNK) {
-        float v[D_CHUNK];
-        __syncwarp();  // the previous pass has finished reading the staging rows
-        tmem_ld16(ta + c, v);
-        float4* srow = reinterpret_cast<float4*>(stg + lane * D_EPI_PITCH);
 #pragma unroll
-        for (int i = 0; i < D_CHUNK / 4; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        __syncwarp();
-        const int n = c + cq * 4;  // this lane's four channels
-        uint2 mk[4];
+      for (int z = 0; z < 2; ++z) {
+        float v[32];
+        tmem_ld32(tmem + acc * 128 + z * 64 + half * 32 + ((uint32_t)(q * 32) << 16), v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {   // masks first: four independent loads in flight
-          const long long off = row_tab[j * 8 + rr];
-          mk[j] = off >= 0 ? __ldg(reinterpret_cast<const uint2*>(a.mask_src + off + n)) : make_uint2(0u, 0u);
-        }
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t mw[4] = {mk[z][c].x, mk[z][c].y, mk[z][c].z, mk[z][c].w};
+          uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int rl = j * 8 + rr;
-          const long long off = row_tab[rl];
-          if (off < 0) continue;
-          const float4 x = *reinterpret_cast<const float4*>(stg + rl * D_EPI_PITCH + cq * 4);
-          float o[4] = {x.x, x.y, x.z, x.w};
-          const uint32_t mw[2] = {mk[j].x, mk[j].y};
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {   // bf16 > 0  <=>  sign bit clear and not zero
+          for (int i = 0; i < 4; ++i) {   // bf16 > 0  <=>  sign bit clear and not zero
             const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
-            o[2 * i] *= (lo != 0u && lo < 0x8000u) ? 1.f : a.mask_slope;
-            o[2 * i + 1] *= (hi != 0u && hi < 0x8000u) ? 1.f : a.mask_slope;
+            const float x0 = v[c * 8 + 2 * i] * ((lo != 0u && lo < 0x8000u) ? 1.f : a.mask_slope);
+            const float x1 = v[c * 8 + 2 * i + 1] * ((hi != 0u && hi < 0x8000u) ? 1.f : a.mask_slope);
+            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
           }
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
-          *reinterpret_cast<uint2*>(a.out + off + n) =
-              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          const int ch = z * 4 + c;
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));   // the accumulator set is free for the tile after next
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int row = jj * 4 + (lane >> 3), ch = lane & 7;   // chunks 0..3: pixel iw, chunks 4..7: pixel iw + 1
+        const long long e = row_tab[row];
+        if (e >= 0 && (ch < 4 || (e & 1))) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(a.out + (e >> 1) + (ch < 4 ? ch * 8 : 64 + (ch - 4) * 8)) = val;
+        }
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
