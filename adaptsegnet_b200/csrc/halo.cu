@@ -342,19 +342,20 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tc_fence_after();
           const uint32_t sa = base + DLayout::A_OFF + s * D_STAGE;
 #pragma unroll
-          for (int zi = 0; zi < 2; ++zi) {
+          for (int t = 0; t < 4; ++t) {
+            const int thh = t >> 1, tww = t & 1;
+            // rh = 0: kh in {1,3} -> dh = 0, -1;  rh = 1: kh in {0,2} -> dh = +1, 0   (same for the columns with rw = zi)
+            const int dh = rh == 0 ? (thh == 0 ? 0 : -1) : (thh == 0 ? 1 : 0);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int thh = t >> 1, tww = t & 1;
-              // rh = 0: kh in {1,3} -> dh = 0, -1;  rh = 1: kh in {0,2} -> dh = +1, 0   (same for the columns with rw = zi)
-              const int dh = rh == 0 ? (thh == 0 ? 0 : -1) : (thh == 0 ? 1 : 0);
-              const int dw = zi == 0 ? (tww == 0 ? 0 : -1) : (tww == 0 ? 1 : 0);
-              const uint32_t ab = sa + ((dh + 1) * D_PITCH + (dw + 1)) * 128;
-              const uint32_t wb = sw + ((zi * 4 + t) * 2 + cc) * 8192;
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int zi = 0; zi < 2; ++zi) {   // alternate the two class accumulators: no back-to-back dependent MMAs
+                const int dw = zi == 0 ? (tww == 0 ? 0 : -1) : (tww == 0 ? 1 : 0);
+                const uint32_t ab = sa + ((dh + 1) * D_PITCH + (dw + 1)) * 128;
+                const uint32_t wb = sw + ((zi * 4 + t) * 2 + cc) * 8192;
                 mma_f16_ss(tmem + acc * 128 + zi * 64, make_smem_desc(ab + k * 32, 16, 1024),
                            make_smem_desc(wb + k * 32, 16, 1024), idesc, (cc > 0 || t > 0 || k > 0) ? 1u : 0u);
+              }
             }
           }
           mma_commit(empty_bar(s));
@@ -550,35 +551,39 @@ conv1_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, 32, 0, 0);
-      mbar_wait(w_bar, 0);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1, s = it % D_NSTAGE;
-        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
-        mbar_wait(full_bar(s), (it / D_NSTAGE) & 1);
-        tc_fence_after();
-        const uint32_t sa = base + ELayout::A_OFF + s * D_STAGE;
+    // the whole warp walks the tile loop (converged); one elected lane issues the MMAs (see elect_one)
+    constexpr uint32_t idesc = make_idesc(128, 32, 0, 0);
+    mbar_wait(w_bar, 0);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1, s = it % D_NSTAGE;
+      mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+      mbar_wait(full_bar(s), (it / D_NSTAGE) & 1);
+      tc_fence_after();
+      const uint32_t sa = base + ELayout::A_OFF + s * D_STAGE;
+      if (elect_one()) {
+        // consecutive MMAs go to different accumulators (class innermost)
 #pragma unroll
-        for (int z = 0; z < 4; ++z) {
-          const int rh = z >> 1, rw = z & 1;
+        for (int t = 0; t < 4; ++t) {
+          const int thh = t >> 1, tww = t & 1;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int thh = t >> 1, tww = t & 1;
-            const int dh = rh == 0 ? (thh == 0 ? 0 : -1) : (thh == 0 ? 1 : 0);
-            const int dw = rw == 0 ? (tww == 0 ? 0 : -1) : (tww == 0 ? 1 : 0);
-            const uint32_t ab = sa + ((dh + 1) * D_PITCH + (dw + 1)) * 128;
-            const uint32_t wb = sw + (z * 4 + t) * 4096;
+          for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int z = 0; z < 4; ++z) {
+              const int rh = z >> 1, rw = z & 1;
+              const int dh = rh == 0 ? (thh == 0 ? 0 : -1) : (thh == 0 ? 1 : 0);
+              const int dw = rw == 0 ? (tww == 0 ? 0 : -1) : (tww == 0 ? 1 : 0);
+              const uint32_t ab = sa + ((dh + 1) * D_PITCH + (dw + 1)) * 128;
+              const uint32_t wb = sw + (z * 4 + t) * 4096;
               mma_f16_ss(tmem + acc * 128 + z * 32, make_smem_desc(ab + k * 32, 16, 1024),
                          make_smem_desc(wb + k * 32, 16, 1024), idesc, (t > 0 || k > 0) ? 1u : 0u);
+            }
           }
         }
         mma_commit(empty_bar(s));
         mma_commit(tfull_bar(acc));
       }
+      __syncwarp();
     }
   } else {
     const int ew = warp - 2, q = warp & 3;   // TMEM lane quarter this warp may read

@@ -113,6 +113,21 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// true in exactly one lane of a CONVERGED warp.  Issuing the single-thread tcgen05 / TMA instructions under this predicate
+// from an otherwise converged warp (instead of inside `if (lane == 0)`) keeps their uniform-register operands out of
+// divergent control flow, where ptxas wraps every such instruction in an ELECT / BRA.U.ANY loop (~14 instructions and
+// ~70 cycles per MMA: more than a 128 x 32 or 128 x 64 MMA takes to execute).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -448,7 +463,9 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // The whole warp walks the loop, converged; ONE elected lane issues the copies (elect_one: single-thread instructions
+    // with uniform-register operands cost ~14 extra instructions each when they sit in divergent control flow).
+    {
       const CUtensorMap* amaps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
       uint32_t it = 0;  // k-steps issued so far: the ring keeps streaming across tiles
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
@@ -460,6 +477,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
+          if (elect_one()) {
           if (CL == 2) {
             // pair: both CTAs load their own A rows and their half of the B rows into their own shared memory; all
             // bytes are counted on the LEADER's barrier, which the leader arms for the two CTAs together (a peer box
@@ -541,12 +559,14 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             bx * P.tw + P.tap_dw[tap], by * P.th + P.tap_dh[tap], im);
             }
           }
+          }  // elect_one
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0 && leader) {  // pair: one thread of the leader CTA drives the tensor cores of both SMs
+    if (leader) {  // pair: one (elected) thread of the leader CTA's warp drives the tensor cores of both SMs
       constexpr bool MN_MAJOR = MODE == MODE_WGRAD || MODE == MODE_GEMM_MN;
       constexpr uint32_t idesc = MN_MAJOR ? make_idesc(CL * BLOCK_M, BLOCK_N, 1, 1) : make_idesc(CL * BLOCK_M, BLOCK_N, 0, 0);
       uint32_t it = 0, tile_iter = 0;
@@ -565,9 +585,11 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
+          const bool issuer = elect_one();   // (always the same lane: tcgen05.commit covers the MMAs of ITS thread)
           if constexpr (MODE == MODE_DGRAD4) {
             const int sh = (t.ks_begin + i) / P.c_chunks;
             const int nb = P.d4_n[sh];
+            if (issuer) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
@@ -577,9 +599,10 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 mma_f16_ss(tmem_d + z * BLOCK_N, da, dbj, idesc, (((started >> z) & 1u) || k > 0) ? 1u : 0u);
               }
             }
-            for (int j = 0; j < nb; ++j) started |= 1u << P.d4_z[sh][j];
             mma_commit(empty_bar(s));
-          } else {
+            }
+            for (int j = 0; j < nb; ++j) started |= 1u << P.d4_z[sh][j];
+          } else if (issuer) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               uint64_t da, db;
@@ -608,11 +631,14 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             }
             // frees the stage (in both CTAs of a pair) once these MMAs have read it
             if (CL == 1) mma_commit(empty_bar(s)); else mma_commit_pair(empty_bar(s), CL_MASK);
-        
           }
+          __syncwarp();
         }
         // accumulator of this tile complete (pair: both halves, each CTA's epilogue waits on its own copy)
-        if (CL == 1) mma_commit(tmem_full_bar(acc)); else mma_commit_pair(tmem_full_bar(acc), CL_MASK);
+        if (elect_one()) {
+          if (CL == 1) mma_commit(tmem_full_bar(acc)); else mma_commit_pair(tmem_full_bar(acc), CL_MASK);
+        }
+        __syncwarp();
       }
     }
   } else {
