@@ -33,6 +33,19 @@ TGT_HW = (512, 1024)
 SEED = 1338
 
 
+def shapes(args):
+    """(source H x W, target H x W): config 2 / 3 shapes, or 512x1024 for both with the VGG variant"""
+    return ((512, 1024), (512, 1024)) if args.model == "VGG" else (SRC_HW, TGT_HW)
+
+
+def metric_name(args):
+    if args.model == "VGG":
+        return "train iters/s (DeeplabVGG single-level, 512x1024 src+512x1024 tgt)"
+    if args.level == "single-level":
+        return f"train iters/s (single-level {args.gan} GAN, 720x1280 src+512x1024 tgt)"
+    return METRIC
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -41,6 +54,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--level", default="multi-level", choices=["multi-level", "single-level"])
     ap.add_argument("--gan", default="Vanilla", choices=["Vanilla", "LS"])
+    ap.add_argument("--model", default="DeepLab", choices=["DeepLab", "VGG"],
+                    help="DeepLab: DeeplabMulti / ResNet-101 (BASELINE configs 2, 3); VGG: DeeplabVGG, single-level only, "
+                         "512x1024 source and target (BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the iteration (up to the gradients) as a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
@@ -133,7 +149,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the restated reference loop on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(steps, warmup, level, gan, budget_s=240.0):
+def cpu_reference_rate(steps, warmup, level, gan, budget_s=240.0, model="DeepLab"):
     """iters/s of the restated reference loop (oracle/torch_ref.RefTrainer, torch CPU fp32, all host threads) MEASURED at
     the full workload -- 720x1280 source + 512x1024 target, the same synthetic batch the GPU arm uses.  `steps` timed
     iterations after `warmup` untimed ones; if the first iterations show that the request would run past `budget_s` of
@@ -144,8 +160,11 @@ def cpu_reference_rate(steps, warmup, level, gan, budget_s=240.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(SEED)
-    tr = TR.RefTrainer(level=level, gan=gan, device="cpu")
-    src, lab, tgt = TR.synthetic_batch(SEED, SRC_HW, TGT_HW)
+    vgg = model == "VGG"
+    tr = TR.RefTrainer(level="single-level" if vgg else level, gan=gan, device="cpu",
+                       model=TR.RefDeeplabVGG(19) if vgg else None)
+    src_hw, tgt_hw = ((512, 1024), (512, 1024)) if vgg else (SRC_HW, TGT_HW)
+    src, lab, tgt = TR.synthetic_batch(SEED, src_hw, tgt_hw)
     t_start = time.perf_counter()
     t0 = time.perf_counter()
     tr.step(src, lab, tgt, i_iter=0)                      # first (cold) iteration: always untimed
@@ -161,7 +180,7 @@ def cpu_reference_rate(steps, warmup, level, gan, budget_s=240.0):
         tr.step(src, lab, tgt, i_iter=warm_done + i)
     dt = (time.perf_counter() - t0) / steps_run
     return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"{steps_run} timed full-size iterations (720x1280 source + 512x1024 target, after {warm_done} "
+            "sample": (f"{steps_run} timed full-size iterations ({src_hw[0]}x{src_hw[1]} source + {tgt_hw[0]}x{tgt_hw[1]} target, after {warm_done} "
                        f"untimed) of the restated reference loop (oracle/torch_ref.RefTrainer, torch {torch.__version__} "
                        f"CPU fp32, {cores} threads): {dt:.3f} s/iter, measured, not extrapolated"),
             "s_per_iter": dt, "steps_timed": steps_run, "warmup_run": warm_done, "extrapolated": False}
@@ -173,8 +192,8 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm
     if args.mode == "eval":
         return run_reference_eval(args)
-    base = cpu_reference_rate(max(1, args.steps), max(1, args.warmup), args.level, args.gan)
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+    base = cpu_reference_rate(max(1, args.steps), max(1, args.warmup), args.level, args.gan, model=args.model)
+    line = {"impl": "reference", "metric": metric_name(args), "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": base["steps_timed"], "warmup": base["warmup_run"], "steps_requested": args.steps,
             "warmup_requested": args.warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -193,15 +212,17 @@ def gpu_eager_reference(dev, args, steps=5, warmup=3):
     import bench_groups
 
     out = {}
-    src, lab, tgt = TR.synthetic_batch(SEED, SRC_HW, TGT_HW)
+    src, lab, tgt = TR.synthetic_batch(SEED, *shapes(args))
     src, lab, tgt = src.to(dev), lab.to(dev), tgt.to(dev)
+    vgg = args.model == "VGG"
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     try:
         for tag, tf32 in (("tf32", True), ("fp32", False)):
             torch.backends.cudnn.allow_tf32 = tf32
             torch.backends.cuda.matmul.allow_tf32 = tf32
             torch.manual_seed(SEED)
-            tr = TR.RefTrainer(level=args.level, gan=args.gan, device=dev)
+            tr = TR.RefTrainer(level="single-level" if vgg else args.level, gan=args.gan, device=dev,
+                               model=TR.RefDeeplabVGG(19) if vgg else None)
             for i in range(warmup):
                 tr.step(src, lab, tgt, i_iter=i)
             torch.cuda.synchronize(dev)
@@ -219,7 +240,7 @@ def gpu_eager_reference(dev, args, steps=5, warmup=3):
     out["steps"], out["warmup"] = steps, warmup
     out["what"] = ("restated reference loop (train_gta2cityscapes_multi.py:560-683) over the restated reference modules, "
                    "PyTorch eager on this GPU, NCHW fp32, cudnn.benchmark=True; CUDA events")
-    if args.level == "multi-level":
+    if args.level == "multi-level" and not vgg:
         out["hot_path_groups"] = bench_groups.compare(dev, tier=args.tier)
         out["hot_path_groups_what"] = ("one iteration's hot path at config-2 shapes on synthetic features / logits, per group, "
                                        "median of 5 after 2 warm-ups, L2 flushed between repetitions: heads = 2 ASPP heads x "
@@ -493,9 +514,12 @@ def run_eval(args):
 
 
 def workload_config(args, world):
-    cfg = {"workload": f"{args.level} AdaptSegNet train step, DeeplabMulti(ResNet-101, 19 cls) + "
-                       f"{'2x' if args.level == 'multi-level' else '1x'} FCDiscriminator, {args.gan} GAN, "
-                       f"src 1x3x{SRC_HW[0]}x{SRC_HW[1]} + tgt 1x3x{TGT_HW[0]}x{TGT_HW[1]} per GPU, random init",
+    (sh, sw), (th, tw) = shapes(args)
+    level = "single-level" if args.model == "VGG" else args.level
+    net = "DeeplabVGG(VGG-16, 19 cls, 2-branch head)" if args.model == "VGG" else "DeeplabMulti(ResNet-101, 19 cls)"
+    cfg = {"workload": f"{level} AdaptSegNet train step, {net} + "
+                       f"{'2x' if level == 'multi-level' else '1x'} FCDiscriminator, {args.gan} GAN, "
+                       f"src 1x3x{sh}x{sw} + tgt 1x3x{th}x{tw} per GPU, random init",
            "per_gpu_batch": "1 source + 1 target image", "global_pairs_per_step": world}
     if args.impl == "reference":
         cfg.update({"parallelism": "none (rank 0 only, host CPU)",
@@ -510,7 +534,8 @@ def workload_config(args, world):
                                "forward/backward of the iteration replayed as two CUDA graphs (generator part, discriminator "
                                "part; the generator's gradient all-reduce overlaps the second); fused optimizer steps eager")
                               if args.cuda_graph else "eager"),
-                "trunk": ("ResNet-101 as PyTorch modules on cuDNN (" + ("bf16 autocast" if args.trunk_dtype == "bf16" else "TF32")
+                "trunk": (("VGG-16 features" if args.model == "VGG" else "ResNet-101") + " as PyTorch modules on cuDNN ("
+                          + ("bf16 autocast" if args.trunk_dtype == "bf16" else "TF32")
                           + (", channels_last" if args.channels_last else "") + "), timed, not rewritten"),
                 "tier": ("B: upsample fused into its consumers (CE loss, discriminator input pack); no full-res logits in HBM"
                          if args.tier == "B" else "A: interp -> loss / softmax -> D tensor by tensor, as the reference"),
@@ -542,10 +567,20 @@ def run_b200(args):
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)  # train_gta2cityscapes_multi.py:228
 
     torch.manual_seed(SEED)  # identical replicas
+    if args.model == "VGG":
+        args.level = "single-level"
+
+    def make_model():
+        if args.model == "VGG":
+            from adaptsegnet_b200.model.deeplab_vgg import DeeplabVGG
+            return DeeplabVGG(19)
+        return None
+
     trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"), device=dev,
-                              use_cuda_graph=bool(args.cuda_graph), channels_last=bool(args.channels_last),
-                              trunk_bf16=args.trunk_dtype == "bf16", overlap=bool(args.overlap))
-    src_h, lab_h, tgt_h = synthetic_batch(SEED + rank, SRC_HW, TGT_HW)  # each rank its own pair
+                              model=make_model(), use_cuda_graph=bool(args.cuda_graph),
+                              channels_last=bool(args.channels_last), trunk_bf16=args.trunk_dtype == "bf16",
+                              overlap=bool(args.overlap))
+    src_h, lab_h, tgt_h = synthetic_batch(SEED + rank, *shapes(args))  # each rank its own pair
     src_h, lab_h, tgt_h = src_h.pin_memory(), lab_h.pin_memory(), tgt_h.pin_memory()
     src, lab, tgt = src_h.to(dev), lab_h.to(dev), tgt_h.to(dev)
 
@@ -692,7 +727,7 @@ def run_b200(args):
             breakdown[k] = {"ms_per_step": round(v["ms"] / args.steps, 4),
                             "launches_per_step": v["launches"] / args.steps, "bound": r["bound"],
                             "achieved": round(r["achieved"], 1), "unit": r["unit"], "frac": round(r["frac"], 3)}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks,
@@ -707,7 +742,7 @@ def run_b200(args):
                                       + (" with the two-stream schedule" if overlap_mode else ""),
                 "hot_path_ms_per_step": hot_ms, "hot_path_kernels": breakdown}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan, budget_s=60.0)
+            line["cpu_baseline"] = cpu_reference_rate(args.cpu_steps, 1, args.level, args.gan, budget_s=60.0, model=args.model)
     # ---- the kernel-for-kernel bar: the reference's own modules on this GPU in PyTorch eager (rank 0, N = 1) ----
     if rank == 0 and world == 1 and not args.no_gpu_reference:
         try:
@@ -727,7 +762,7 @@ def run_b200(args):
             torch.cuda.empty_cache()
             torch.manual_seed(SEED)
             trainer = AdaptSegTrainer(TrainConfig(level=args.level, gan=args.gan, lazy_upsample=args.tier == "B"),
-                                      device=dev, use_cuda_graph=bool(args.cuda_graph),
+                                      device=dev, model=make_model(), use_cuda_graph=bool(args.cuda_graph),
                                       channels_last=bool(args.channels_last), trunk_bf16=True, overlap=bool(args.overlap))
             for _ in range(max(args.warmup, 3) + 1):
                 step_resident(0)

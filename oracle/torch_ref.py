@@ -114,6 +114,46 @@ class RefDeeplabMulti(nn.Module):  # model/deeplab_multi.py:124-235, DeeplabMult
         return [{"params": one_x(), "lr": lr}, {"params": ten_x(), "lr": 10 * lr}]
 
 
+class RefClassifierTwoBranch(RefClassifier):
+    """model/deeplab_vgg.py:6-21 (and model/deeplab.py:101-116): the `return` sits INSIDE the loop, so only branches 0 and 1
+    are summed although all four own weights"""
+
+    def forward(self, x):
+        out = self.conv2d_list[0](x)
+        for i in range(len(self.conv2d_list) - 1):
+            out += self.conv2d_list[i + 1](x)
+            return out
+
+
+class RefDeeplabVGG(nn.Module):
+    """model/deeplab_vgg.py:24-54 with the Python-3 fix of its constructor (`range(23)+range(24,30)`, Q10).  forward()
+    follows the single-level loop's use of a one-output model: logits are interpolated to the input size by the caller
+    (evaluate_cityscapes.py:164-166); here `forward(x, input_size)` returns (None, interp(logits)) so that the restated
+    training loop (RefTrainer) drives it like DeeplabMulti."""
+
+    def __init__(self, num_classes=19):
+        super().__init__()
+        from torchvision import models
+        features = list(models.vgg16().features.children())
+        features = [features[i] for i in list(range(23)) + list(range(24, 30))]
+        for i in (23, 25, 27):
+            features[i].dilation = (2, 2)
+            features[i].padding = (2, 2)
+        fc6 = nn.Conv2d(512, 1024, kernel_size=3, padding=4, dilation=4)
+        fc7 = nn.Conv2d(1024, 1024, kernel_size=3, padding=4, dilation=4)
+        self.features = nn.Sequential(*(features + [fc6, nn.ReLU(inplace=True), fc7, nn.ReLU(inplace=True)]))
+        self.classifier = RefClassifierTwoBranch(1024, (6, 12, 18, 24), num_classes)
+        for m in self.classifier.conv2d_list:
+            m.weight.data.normal_(0, 0.01)
+
+    def forward(self, x, input_size):
+        z = self.classifier(self.features(x))
+        return None, nn.Upsample(size=(input_size[1], input_size[0]), mode="bilinear", align_corners=True)(z)
+
+    def optim_parameters(self, lr):   # deeplab_vgg.py:53-54: one group
+        return [{"params": list(self.parameters()), "lr": lr}]
+
+
 class RefFCDiscriminator(nn.Module):  # model/discriminator.py:5-34
     def __init__(self, num_classes, ndf=64):
         super().__init__()
@@ -189,7 +229,7 @@ class RefTrainer:
         self.model_D2 = (model_D2 or RefFCDiscriminator(num_classes)).to(self.device).train()
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            groups = (self.model.optim_parameters(learning_rate) if isinstance(self.model, RefDeeplabMulti)
+            groups = (self.model.optim_parameters(learning_rate) if isinstance(self.model, (RefDeeplabMulti, RefDeeplabVGG))
                       else self.model.optim_parameters(_Args(learning_rate)))
             self.optimizer = torch.optim.SGD(groups, lr=learning_rate,
                                              momentum=momentum, weight_decay=weight_decay)
@@ -211,7 +251,8 @@ class RefTrainer:
         self.optimizer.zero_grad()
         lr = lr_poly(h["lr"], i_iter, h["num_steps"], h["power"])
         self.optimizer.param_groups[0]["lr"] = lr
-        self.optimizer.param_groups[1]["lr"] = lr * 10
+        if len(self.optimizer.param_groups) > 1:
+            self.optimizer.param_groups[1]["lr"] = lr * 10
         for o in opts_D:
             o.zero_grad()
             o.param_groups[0]["lr"] = lr_poly(h["lr_D"], i_iter, h["num_steps"], h["power"])

@@ -191,3 +191,38 @@ def test_two_stream_overlap_equals_sequential(graph):
         assert abs(float(ovl.flat_G.flat.norm()) / float(seq.flat_G.flat.norm()) - 1) < 1e-3
         for opt in {id(o): o for o in (seq.optimizer, seq.optimizer_D1, seq.optimizer_D2)}.values():
             opt.step()
+
+
+def test_vgg_single_level_step_parity():
+    """BASELINE config 4: DeeplabVGG (restated with the Python-3 constructor fix, Q10; 2-branch head, Q9) + one
+    discriminator, single-level LS-GAN iteration (train...:373-464 driven over the VGG model): losses 1e-2 (bf16 head /
+    discriminator), same state-dict keys as the restated reference model, head gradients 0.1 across the two forwards."""
+    from adaptsegnet_b200.model.deeplab_vgg import DeeplabVGG
+    from adaptsegnet_b200.train_step import AdaptSegTrainer, TrainConfig
+    torch.manual_seed(SEED)
+    G = TR.RefDeeplabVGG(19)
+    D2 = TR.seeded_init_(TR.RefFCDiscriminator(19), SEED + 2)
+    ref = TR.RefTrainer(level="single-level", gan="LS", model=G, model_D2=D2)
+    mine_G = DeeplabVGG(19)
+    assert set(mine_G.state_dict()) == set(G.state_dict())
+    mine_G.load_state_dict(G.state_dict())
+    for lazy in (False, True):
+        mine = AdaptSegTrainer(TrainConfig(level="single-level", gan="LS", lazy_upsample=lazy), device="cuda", model=mine_G,
+                               channels_last=lazy)
+        mine.model_D2.load_state_dict(D2.state_dict())
+        src, lab, tgt = TR.synthetic_batch(SEED, (128, 256), (96, 192))
+        want = ref.step(src, lab, tgt, do_optimizer_step=False)
+        got = mine.step(src.cuda(), lab.cuda(), tgt.cuda(), do_optimizer_step=False)
+        torch.cuda.synchronize()
+        assert set(want) == set(got) == {"loss_seg2", "loss_adv_target2", "loss_D2"}
+        for k, v in want.items():
+            assert abs(float(got[k].item()) - v) <= 1e-2 * max(abs(v), 1e-3), (lazy, k, float(got[k].item()), v)
+        # only branches 0 and 1 of the head receive gradients (the early return of model/deeplab_vgg.py:17-21)
+        gl = [c.weight.grad for c in mine.model.classifier.conv2d_list]
+        rl = [c.weight.grad for c in G.classifier.conv2d_list]
+        for i in (0, 1):
+            assert rel_err(gl[i].cpu().numpy(), rl[i].numpy()) < 0.1, (lazy, i)
+        for i in (2, 3):
+            assert rl[i] is None and float(gl[i].abs().sum()) == 0.0
+        ref.optimizer.zero_grad()
+        ref.optimizer_D2.zero_grad()
