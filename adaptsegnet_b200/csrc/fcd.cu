@@ -738,8 +738,16 @@ static int conv_fwd(const FcdPlan& p, int l, const __nv_bfloat16* in, const __nv
   P.mask_slope = 1.f;
   dim3 grid(p.N * P.tiles_h * P.tiles_w, cdiv(Cout, bn), 1);
   static const char* names[5] = {"", "fcd_conv1_fwd", "fcd_conv2_fwd", "fcd_conv3_fwd", "fcd_conv4_fwd"};
+  // the output tile leaves through TMA stores (ASN_TMA_STORE=0: register -> shared memory -> st.global epilogue)
+  static const bool tma_store = !(getenv("ASN_TMA_STORE") != nullptr && getenv("ASN_TMA_STORE")[0] == '0');
+  CUtensorMap omaps[4];
+  if (tma_store && rows == 128 && Cout % 64 == 0) {
+    if ((rc = encode_plain(&omaps[0], out, p.N, OH, OW, Cout, th, tw))) return rc;
+    omaps[1] = omaps[2] = omaps[3] = omaps[0];
+    P.tma_store = 1;
+  }
   return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l),
-                layer_bytes(p, l, 0) + 2.0 * Cout * K, rows);
+                layer_bytes(p, l, 0) + 2.0 * Cout * K, rows, P.tma_store ? omaps : nullptr);
 }
 
 // dIn (= dPre_{l-1} after the LeakyReLU mask, or dA0 for l == 1) from dPre_l
@@ -838,7 +846,17 @@ static int conv_dgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const 
     dim3 grid4(p.N * P.tiles_h * P.tiles_w, 1, 1);
     return launch(MODE_DGRAD4, bn, maps, P, grid4, st, names[l], layer_flops(p, l), bytes, 4 * 128);
   }
-  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l), bytes, tile_rows);
+  // data gradients: the TMA-store epilogue is parity-tested but measured 3-5 % slower here than the transpose epilogue (the
+  // LeakyReLU-mask loads become per-thread rows) -> opt-in with ASN_TMA_STORE_DGRAD=1; the forward convolutions use it
+  static const bool tma_store = getenv("ASN_TMA_STORE_DGRAD") != nullptr && getenv("ASN_TMA_STORE_DGRAD")[0] == '1';
+  CUtensorMap omaps[4];
+  if (tma_store && tile_rows == 128 && rows % 64 == 0 && l > 1) {
+    for (int z = 0; z < 4; ++z)   // output-parity class z writes the stride-2 view of dIn that starts at (rh, rw)
+      if ((rc = encode_parity(&omaps[z], din, p.N, Hin, Win, rows, z / 2, z % 2, th, tw))) return rc;
+    P.tma_store = 1;
+  }
+  return launch(MODE_CONV, bn, maps, P, grid, st, names[l], layer_flops(p, l), bytes, tile_rows,
+                P.tma_store ? omaps : nullptr);
 }
 
 static int conv_wgrad(const FcdPlan& p, int l, const __nv_bfloat16* dpre, const __nv_bfloat16* act_in, float* part,

@@ -92,7 +92,9 @@ struct Shape {
   static constexpr int b_tile = (((BLOCK_N / CL) * 128 + 1023) / 1024) * 1024;
   // K-major modes: MT row tiles of A per B tile; WGRAD: MT taps' B tiles per A tile
   static constexpr int stage = (MODE == MODE_WGRAD || MODE == MODE_DGRAD4) ? 16384 + MT * b_tile : MT * 16384 + b_tile;
-  static constexpr int fit = ((EW == 4 ? 100 : 184) * 1024) / stage;
+  // ring budget: 184 KB, or 172 KB when the 48 KB of TMA-store staging replace the 36 KB of transpose buffers (same number
+  // of stages for every BLOCK_N in use)
+  static constexpr int fit = ((EW == 4 ? 100 : (has_tma_epi<MODE, BLOCK_N, MT, EW>() ? 172 : 184)) * 1024) / stage;
   static constexpr int stages = fit > 8 ? 8 : (fit < 2 ? 2 : fit);
 };
 
@@ -113,8 +115,8 @@ int cluster_size(int mode, int block_n) {
 }
 
 template <int MODE, int BLOCK_N, int CL, int MT>
-static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st, const char* name,
-                    double flops, double bytes) {
+static int launch_t(const CUtensorMap maps[5], const CUtensorMap* omaps, const Params& P, dim3 grid, cudaStream_t st,
+                    const char* name, double flops, double bytes) {
   using Sh = Shape<MODE, BLOCK_N, MT, CL>;
   constexpr int STAGES = Sh::stages, EW = Sh::EW, NUM_THREADS = EpiCfg<EW>::threads;
   using L = KernelSmem<MODE, BLOCK_N, STAGES, CL, MT, EW>;
@@ -144,6 +146,10 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
     configured.set(1);
   }
   Params Pp = P;
+  // output tensor maps of the TMA-store epilogue (CONV / EPI_BF16 tiles made of 64-channel slabs); anything else keeps the
+  // register -> shared memory -> st.global epilogue and never touches them
+  const CUtensorMap* om = omaps ? omaps : maps;
+  if (!omaps || !has_tma_epi<MODE, BLOCK_N, MT, EW>()) Pp.tma_store = 0;
   Pp.grid_x = (int)grid.x;
   Pp.grid_y = (int)grid.y;
   Pp.grid_z = (int)grid.z;
@@ -152,7 +158,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
   const int ctas = (int)(tiles < slots ? tiles : slots) * CL;
   prof::Scope ps(name, flops, bytes, st);
   if (CL == 1) {
-    kern<<<ctas, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], Pp);
+    kern<<<ctas, NUM_THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], om[0], om[1], om[2], om[3], Pp);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -166,7 +172,7 @@ static int launch_t(const CUtensorMap maps[5], const Params& P, dim3 grid, cudaS
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ASN_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], Pp));
+    ASN_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], om[0], om[1], om[2], om[3], Pp));
   }
   ASN_LAUNCH_CHECK();
   return ASN_OK;
@@ -194,14 +200,14 @@ int rows_per_cta(int mode, long long m_tiles_128, long long other) {
 }
 
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
-           const char* prof_name, double prof_flops, double prof_bytes, int rows) {
+           const char* prof_name, double prof_flops, double prof_bytes, int rows, const CUtensorMap* omaps) {
   int cl = rows == BLOCK_M ? cluster_size(mode, block_n) : 1;
   // MN-major pairs are two x-neighbouring 128-row M tiles of the same N tile: needs an even number of M tiles
   if ((mode == MODE_WGRAD || mode == MODE_GEMM_MN) && (cdiv(P.M, BLOCK_M) % 2 != 0)) cl = 1;
   const int mt = rows / BLOCK_M;
 #define ASN_CASE(MODE, BN, CLS, MTS) \
   if (mode == MODE && block_n == BN && cl == CLS && mt == MTS)  \
-    return launch_t<MODE, BN, CLS, MTS>(maps, P, grid, st, prof_name, prof_flops, prof_bytes);
+    return launch_t<MODE, BN, CLS, MTS>(maps, omaps, P, grid, st, prof_name, prof_flops, prof_bytes);
   ASN_CASE(MODE_GEMM, 128, 1, 1)
   ASN_CASE(MODE_GEMM, 176, 1, 1)
   ASN_CASE(MODE_GEMM, 256, 1, 1)

@@ -87,6 +87,24 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t dst, 
       : "memory");
 }
 
+// TMA store: a SWIZZLE_128B box in shared memory -> global (out-of-range parts of the box are clipped), bulk-group tracked
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {   // at most N of this thread's bulk groups still READ shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// generic-proxy writes to shared memory (st.shared) become visible to the async proxy (TMA) of this CTA
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // cta_group::2 flavours: the box lands in THIS CTA's shared memory, the bytes are counted on an mbarrier that may live
 // in the peer CTA (`bar` is a shared::cluster address, see mapa_rank)
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1) {
@@ -304,6 +322,7 @@ struct Params {
   float slope;                       // LeakyReLU slope applied to the result (1 = none)
   const __nv_bfloat16* mask_src;     // nullable: multiply by (mask_src[off] > 0 ? 1 : mask_slope)
   float mask_slope;
+  int tma_store;                     // CONV / EPI_BF16: the tile leaves through TMA stores over map_o[z] (64-channel slabs)
 };
 
 // A CTA tile is MT x 128 rows: MT accumulators of BLOCK_N fp32 columns that share every B stage (per byte of shared
@@ -334,22 +353,32 @@ struct EpiCfg {
 
 // AT / BT = A / B tiles per stage: K-major modes may stack AT = 2 row tiles on one B tile (MT = 2); the pixel-reduction
 // WGRAD mode may feed BT = 2 or 4 taps' B tiles from one A tile.
-template <int BLOCK_N, int STAGES, int AT = 1, int EW = 8, int CL = 1, int BT = 1>
+constexpr int TMA_SLAB_BYTES = BLOCK_M * 128;   // one 64-channel bf16 slab of a 128-row tile, SWIZZLE_128B
+constexpr int TMA_SLABS = 3;                    // staging buffers in rotation: one barrier per slab (see the epilogue)
+template <int BLOCK_N, int STAGES, int AT = 1, int EW = 8, int CL = 1, int BT = 1, bool TMA_EPI = false>
 struct SmemLayout {
   static constexpr int A_BYTES = AT * BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
   static constexpr int B_BYTES = (BLOCK_N / CL) * BLOCK_K * 2;  // one B tile; a pair keeps half of it in each CTA
   static constexpr int B_TILE = ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + BT * B_TILE;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STG_OFFSET = BAR_OFFSET + 256;                     // barriers take <= 21 x 8 B
-  static constexpr int ROW_OFFSET = STG_OFFSET + EW * 32 * EpiCfg<EW>::pitch * 4;  // per-warp [32][pitch] fp32
-  static constexpr int TOTAL = ROW_OFFSET + EW * 32 * 8 + 1024;                    // + row tables + alignment slack
+  // barriers take <= 21 x 8 B; with the TMA-store epilogue the staging area must start on a 1024-byte boundary and holds
+  // TMA_SLABS slabs, which the per-warp transpose buffers of the other epilogue overlay
+  static constexpr int STG_OFFSET = BAR_OFFSET + (TMA_EPI ? 1024 : 256);
+  static constexpr int STG_PLAIN = EW * 32 * EpiCfg<EW>::pitch * 4;       // per-warp [32][pitch] fp32
+  static constexpr int STG_BYTES = TMA_EPI && TMA_SLABS * TMA_SLAB_BYTES > STG_PLAIN ? TMA_SLABS * TMA_SLAB_BYTES : STG_PLAIN;
+  static constexpr int ROW_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = ROW_OFFSET + EW * 32 * 8 + 1024;           // + row tables + alignment slack
 };
 
 // the stage layout of umma_kernel<MODE, BLOCK_N, STAGES, CL, MT, EW> (shared with the launcher)
+// the TMA-store epilogue exists for single-accumulator convolution tiles made of whole 64-channel slabs
+template <int MODE, int BLOCK_N, int MT, int EW>
+__host__ __device__ constexpr bool has_tma_epi() { return MODE == MODE_CONV && EW == 8 && MT == 1 && BLOCK_N % 64 == 0; }
 template <int MODE, int BLOCK_N, int STAGES, int CL, int MT, int EW>
 using KernelSmem = SmemLayout<BLOCK_N, STAGES, (((MODE == MODE_WGRAD && MT > 1) || MODE == MODE_DGRAD4) ? 1 : MT), EW, CL,
-                              (((MODE == MODE_WGRAD && MT > 1) || MODE == MODE_DGRAD4) ? MT : 1)>;
+                              (((MODE == MODE_WGRAD && MT > 1) || MODE == MODE_DGRAD4) ? MT : 1),
+                              has_tma_epi<MODE, BLOCK_N, MT, EW>()>;
 
 struct TileCoord {
   int z, n0, m0, img, oh0, ow0, wg_tap, ks_begin, nsteps;
@@ -398,7 +427,9 @@ template <int MODE, int BLOCK_N, int STAGES, int CL, int MT, int EW>
 __global__ void __launch_bounds__(EpiCfg<EW>::threads, (EW == 4 ? 2 : 1))
 umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
-            const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params P) {
+            const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o0,
+            const __grid_constant__ CUtensorMap map_o1, const __grid_constant__ CUtensorMap map_o2,
+            const __grid_constant__ CUtensorMap map_o3, const __grid_constant__ Params P) {
   constexpr bool MULTI_TAP = MODE == MODE_WGRAD && MT > 1;
   constexpr bool MULTI_B = MULTI_TAP || MODE == MODE_DGRAD4;  // MT accumulators fed by MT B tiles from one A tile
   using L = KernelSmem<MODE, BLOCK_N, STAGES, CL, MT, EW>;
@@ -658,10 +689,88 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                          ew * 32;  // element offset of each of this warp's 32 rows, -1 = masked row
     const int rr = lane >> 2, cq = lane & 3;  // write-out role: row (of 8) and group of CPL columns
     uint32_t tile_iter = 0;
+    uint32_t slab_iter = 0;                   // TMA-store epilogue: slabs staged so far (buffer = slab_iter % TMA_SLABS)
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++tile_iter) {
       const TileCoord t = decode_tile<MODE, BLOCK_N, CL, MT>(P, tile, rank);
       const uint32_t acc = NACC == 2 ? (tile_iter & 1) : 0;
       const uint32_t acc_ph = NACC == 2 ? ((tile_iter >> 1) & 1) : (tile_iter & 1);
+      if constexpr (has_tma_epi<MODE, BLOCK_N, MT, EW>()) {
+        if (P.tma_store) {
+          // ---- TMA-store epilogue ----
+          // The tile's 128 rows are the th x tw pixel box in row-major order, i.e. exactly the row order of a
+          // {64 ch, tw, th, 1} TMA box over the NHWC output (or its stride-2 parity view for the data gradients): thread
+          // = row writes its 64 channels of a slab as one 128-byte SWIZZLE_128B row (16-byte chunk c of row r at
+          // chunk c ^ (r & 7): conflict-free), the two warps of a lane quarter taking 32 channels each; one barrier,
+          // then ONE elected thread stores the slab with cp.async.bulk.tensor -- full 128-byte lines, rows and columns
+          // beyond the image clipped by the TMA unit (no row tables, no per-lane bounds).  Three staging buffers rotate:
+          // the issuing thread waits until at most one store still reads shared memory right after issuing, so the
+          // buffer reused two slabs later is known to be free by everyone who passes the next barrier.
+          const CUtensorMap* omap = t.z == 0 ? &map_o0 : t.z == 1 ? &map_o1 : t.z == 2 ? &map_o2 : &map_o3;
+          const int r = q * 32 + lane;
+          const int dy = r / P.tw, dx = r - dy * P.tw;
+          const int oh = t.oh0 + dy, ow = t.ow0 + dx;
+          const bool row_ok = t.valid && oh < P.oh_ext[t.z] && ow < P.ow_ext[t.z];
+          const long long row_off = (((long long)t.img * P.out_h + (oh * P.sy + P.oy[t.z])) * P.out_w +
+                                     (ow * P.sx + P.ox[t.z])) * P.ld_out;   // LeakyReLU-mask source of this row
+          uint8_t* stage_base = smem_raw + (smem_base - smem_u32(smem_raw)) + L::STG_OFFSET;
+          mbar_wait(tmem_full_bar(acc), acc_ph);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * (MT * BLOCK_N);
+#pragma unroll 1
+          for (int sl = 0; sl < BLOCK_N / 64; ++sl, ++slab_iter) {
+            const int c0 = sl * 64 + half * 32;       // first of this warp's 32 accumulator columns
+            const int n = t.n0 + c0;
+            uint4 mk[4];
+            if (P.mask_src) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                mk[c] = row_ok ? __ldg(reinterpret_cast<const uint4*>(P.mask_src + row_off + n) + c) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            float v[32];
+            if (t.nsteps > 0) {
+              tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            uint8_t* buf = stage_base + (slab_iter % TMA_SLABS) * TMA_SLAB_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t mw[4] = {mk[c].x, mk[c].y, mk[c].z, mk[c].w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float x0 = v[c * 8 + 2 * i], x1 = v[c * 8 + 2 * i + 1];
+                if (P.bias) { x0 += __ldg(P.bias + n + c * 8 + 2 * i); x1 += __ldg(P.bias + n + c * 8 + 2 * i + 1); }
+                if (P.slope != 1.f) { x0 = x0 > 0.f ? x0 : x0 * P.slope; x1 = x1 > 0.f ? x1 : x1 * P.slope; }
+                if (P.mask_src) {   // bf16 > 0  <=>  sign bit clear and not zero
+                  const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+                  x0 *= (lo != 0u && lo < 0x8000u) ? 1.f : P.mask_slope;
+                  x1 *= (hi != 0u && hi < 0x8000u) ? 1.f : P.mask_slope;
+                }
+                __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              const int ch = half * 4 + c;   // 16-byte chunk of the 128-byte row
+              *reinterpret_cast<uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_async_smem();
+            named_bar_sync(1, EW * 32);      // all 128 rows x 64 channels of the slab are staged
+            if (ew == 0 && elect_one()) {
+              if (t.valid) tma_store_4d(omap, smem_base + L::STG_OFFSET + (slab_iter % TMA_SLABS) * TMA_SLAB_BYTES,
+                                        t.n0 + sl * 64, t.ow0, t.oh0, t.img);
+              bulk_commit();
+              bulk_wait_read<1>();           // the store issued one slab ago has finished reading its buffer
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CL == 1) mbar_arrive(tmem_empty_bar(acc)); else mbar_arrive_cluster(mapa_rank(tmem_empty_bar(acc), 0));
+          }
+          continue;
+        }
+      }
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
 #pragma unroll 1
@@ -811,6 +920,7 @@ umma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   }
 
   // ---- teardown (a CTA may not exit while its peer can still read its shared memory or signal its barriers) ----
+  if (has_tma_epi<MODE, BLOCK_N, MT, EW>() && warp == 2) bulk_wait_read<0>();   // (the issuing lane's groups; no-op elsewhere)
   tc_fence_before();
   if (CL == 1) __syncthreads(); else cluster_sync_all();
   if (warp == 1) {

@@ -17,7 +17,10 @@ int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
 // rows = rows of the CTA tile: 128, or 256 (two accumulators sharing every B stage; the A tensor map / pixel box must
 // then cover 256 rows).  grid.x counts tiles of that height.
 int launch(int mode, int block_n, const CUtensorMap maps[5], const Params& P, dim3 grid, cudaStream_t st,
-           const char* prof_name = "umma", double prof_flops = 0, double prof_bytes = 0, int rows = BLOCK_M);
+           const char* prof_name = "umma", double prof_flops = 0, double prof_bytes = 0, int rows = BLOCK_M,
+           const CUtensorMap* omaps = nullptr);
+// omaps: four {64 ch, tw, th, 1} SWIZZLE_128B maps over the bf16 NHWC output, one per blockIdx.z class (CONV mode with
+// P.tma_store = 1): the tile is written with TMA stores (encode with encode_4d, box = the pixel tile)
 // 128 or 256: the tile height the launcher recommends for this many 128-row tiles x other grid dimensions
 int rows_per_cta(int mode, long long m_tiles_128, long long other);
 
