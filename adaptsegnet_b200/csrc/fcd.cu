@@ -507,47 +507,48 @@ struct LayerReduce {
   int S[4], Cout[4], Cin_real[4], Ncols[4];
 };
 
-// partial[cta][c] = sum of this CTA's row slice (fixed order -> deterministic)
+// partial[cta][c] = sum of this CTA's row slice (fixed order -> deterministic).  Thread = 8 consecutive channels (one 16-byte
+// load per row); the 256 threads split into C/8 channel groups x (2048/C) row phases, each phase striding the rows of the
+// slice with four independent loads in flight; the phases are folded through shared memory in a fixed order.
 __global__ void __launch_bounds__(256) fcd_colsum_partial_kernel(LayerReduce R) {
   const int l = blockIdx.y;
   if ((int)blockIdx.x >= R.ctas[l]) return;
   const __nv_bfloat16* src = R.dpre[l];
-  const int C = R.C[l];
+  const int C = R.C[l];                         // 64 .. 512, a multiple of 64
   const long long r0 = (long long)blockIdx.x * R.rows_per_cta[l];
   const long long r1 = min(R.P[l], r0 + R.rows_per_cta[l]);
-  const int pairs = C / 2;
-  const int tpr = pairs < 256 ? pairs : 256;
-  const int nsub = 256 / tpr;
-  const int sub = threadIdx.x / tpr;
-  __shared__ float sm[512];  // [sub][channel] when several row phases share the CTA (C <= 256: nsub * C = 512)
-  for (int cp = threadIdx.x % tpr; cp < pairs; cp += tpr) {   // (a single pass: tpr = min(pairs, 256) and pairs <= 256)
-    float a0 = 0.f, a1 = 0.f;
-    for (long long r = r0 + sub; r < r1; r += nsub) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * C + cp * 2);
-      a0 += __low2float(v);
-      a1 += __high2float(v);
+  const int groups = C / 8;                     // 8 .. 64 threads cover one row
+  const int nsub = 256 / groups;                // row phases
+  const int g = threadIdx.x % groups, sub = threadIdx.x / groups;
+  __shared__ float sm[256 * 8];                 // [sub][channel]
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  auto add = [&](const uint4& u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      acc[2 * i] += __low2float(v);
+      acc[2 * i + 1] += __high2float(v);
     }
-    float* dst = R.db_partial[l] + (long long)blockIdx.x * C + cp * 2;
-    if (nsub == 1) {
-      dst[0] = a0;
-      dst[1] = a1;
-    } else {
-      // fold the nsub row phases of this CTA in a fixed order: one partial row per CTA
-      float* s0 = sm + (sub * tpr + cp) * 2;
-      s0[0] = a0;
-      s0[1] = a1;
-      __syncthreads();
-      if (sub == 0) {
-        float t0 = 0.f, t1 = 0.f;
-        for (int k = 0; k < nsub; ++k) {
-          const float* sk = sm + (k * tpr + cp) * 2;
-          t0 += sk[0];
-          t1 += sk[1];
-        }
-        dst[0] = t0;
-        dst[1] = t1;
-      }
-    }
+  };
+  long long r = r0 + sub;
+  for (; r + 3LL * nsub < r1; r += 4LL * nsub) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = ld_stream(reinterpret_cast<const uint4*>(src + (r + (long long)k * nsub) * C) + g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) add(u[k]);
+  }
+  for (; r < r1; r += nsub) add(ld_stream(reinterpret_cast<const uint4*>(src + r * C) + g));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[(sub * groups + g) * 8 + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.f;
+    for (int k = 0; k < nsub; ++k) t += sm[k * C + c];     // (sub k, channel c) lives at (k * groups + c / 8) * 8 + c % 8
+    R.db_partial[l][(long long)blockIdx.x * C + c] = t;
   }
 }
 // db[c] = sum_r partial[r][c]: 32 channels per CTA (lane = channel), 8 warps split the partial rows
