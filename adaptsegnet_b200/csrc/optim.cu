@@ -42,60 +42,98 @@ __device__ __forceinline__ void sgd_one(float& p, float g, float& buf, float lr,
   }
 }
 
+// Thread = OPT_VEC float4 elements, OPT_THREADS apart (every load instruction of a warp is 512 contiguous bytes); all
+// 3 x OPT_VEC loads are issued before the first use.  The segment table (where each parameter begins, its learning-rate
+// group and repeat count) is staged in shared memory once per CTA, so the per-element lookup is a handful of shared-memory
+// reads instead of a chain of dependent global loads in front of the streaming loads.
+constexpr int OPT_VEC = 4;
+constexpr int OPT_MAX_SEG_SMEM = 1024;
+
 __global__ void __launch_bounds__(OPT_THREADS) sgd_step_kernel(const SgdArgs a) {
-  const long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x;
-  if (i >= a.n4) return;
-  const long long e = i * 4;
-  int lo = 0, hi = a.n_seg - 1;  // last segment whose begin <= e
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(a.seg_begin + mid) <= e) lo = mid; else hi = mid - 1;
+  __shared__ long long s_begin[OPT_MAX_SEG_SMEM];
+  __shared__ int s_meta[OPT_MAX_SEG_SMEM];   // group | repeat << 8
+  const bool staged = a.n_seg <= OPT_MAX_SEG_SMEM;
+  if (staged) {
+    for (int i = threadIdx.x; i < a.n_seg; i += OPT_THREADS) {
+      s_begin[i] = __ldg(a.seg_begin + i);
+      s_meta[i] = __ldg(a.seg_group + i) | (__ldg(a.seg_repeat + i) << 8);
+    }
+    __syncthreads();
   }
-  const float lr = a.lr[__ldg(a.seg_group + lo)];
-  const int repeat = __ldg(a.seg_repeat + lo);
-  float4 p = reinterpret_cast<float4*>(a.p)[i];
-  float4 g = ld_stream(reinterpret_cast<const float4*>(a.g) + i);
-  if (a.grad_scale != 1.f) {  // a separate rounded multiply: bit-identical to `grad.mul_(scale)` followed by the step
-    g.x = __fmul_rn(g.x, a.grad_scale); g.y = __fmul_rn(g.y, a.grad_scale);
-    g.z = __fmul_rn(g.z, a.grad_scale); g.w = __fmul_rn(g.w, a.grad_scale);
+  const long long base = (long long)blockIdx.x * (OPT_THREADS * OPT_VEC) + threadIdx.x;
+  float4 p[OPT_VEC], g[OPT_VEC], b[OPT_VEC];
+#pragma unroll
+  for (int k = 0; k < OPT_VEC; ++k) {
+    const long long i = base + (long long)k * OPT_THREADS;
+    if (i < a.n4) {
+      p[k] = reinterpret_cast<const float4*>(a.p)[i];
+      g[k] = ld_stream(reinterpret_cast<const float4*>(a.g) + i);
+      b[k] = a.first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.buf)[i];
+    }
   }
-  float4 b = a.first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(a.buf)[i];
   const bool first = a.first_step != 0;
-  sgd_one(p.x, g.x, b.x, lr, a.momentum, a.weight_decay, repeat, first);
-  sgd_one(p.y, g.y, b.y, lr, a.momentum, a.weight_decay, repeat, first);
-  sgd_one(p.z, g.z, b.z, lr, a.momentum, a.weight_decay, repeat, first);
-  sgd_one(p.w, g.w, b.w, lr, a.momentum, a.weight_decay, repeat, first);
-  reinterpret_cast<float4*>(a.p)[i] = p;
-  reinterpret_cast<float4*>(a.buf)[i] = b;
+#pragma unroll
+  for (int k = 0; k < OPT_VEC; ++k) {
+    const long long i = base + (long long)k * OPT_THREADS;
+    if (i >= a.n4) continue;
+    const long long e = i * 4;
+    int lo = 0, hi = a.n_seg - 1;  // last segment whose begin <= e
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const long long bm = staged ? s_begin[mid] : __ldg(a.seg_begin + mid);
+      if (bm <= e) lo = mid; else hi = mid - 1;
+    }
+    const int meta = staged ? s_meta[lo] : (__ldg(a.seg_group + lo) | (__ldg(a.seg_repeat + lo) << 8));
+    const float lr = a.lr[meta & 0xff];
+    const int repeat = meta >> 8;
+    if (a.grad_scale != 1.f) {  // a separate rounded multiply: bit-identical to `grad.mul_(scale)` followed by the step
+      g[k].x = __fmul_rn(g[k].x, a.grad_scale); g[k].y = __fmul_rn(g[k].y, a.grad_scale);
+      g[k].z = __fmul_rn(g[k].z, a.grad_scale); g[k].w = __fmul_rn(g[k].w, a.grad_scale);
+    }
+    sgd_one(p[k].x, g[k].x, b[k].x, lr, a.momentum, a.weight_decay, repeat, first);
+    sgd_one(p[k].y, g[k].y, b[k].y, lr, a.momentum, a.weight_decay, repeat, first);
+    sgd_one(p[k].z, g[k].z, b[k].z, lr, a.momentum, a.weight_decay, repeat, first);
+    sgd_one(p[k].w, g[k].w, b[k].w, lr, a.momentum, a.weight_decay, repeat, first);
+    reinterpret_cast<float4*>(a.p)[i] = p[k];
+    reinterpret_cast<float4*>(a.buf)[i] = b[k];
+  }
 }
 
 __global__ void __launch_bounds__(OPT_THREADS)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  long long n4, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2,
                  float grad_scale) {
-  const long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x;
-  if (i >= n4) return;
-  float4 P = reinterpret_cast<float4*>(p)[i];
-  float4 G = ld_stream(reinterpret_cast<const float4*>(g) + i);
-  if (grad_scale != 1.f) {
-    G.x = __fmul_rn(G.x, grad_scale); G.y = __fmul_rn(G.y, grad_scale);
-    G.z = __fmul_rn(G.z, grad_scale); G.w = __fmul_rn(G.w, grad_scale);
+  const long long base = (long long)blockIdx.x * (OPT_THREADS * OPT_VEC) + threadIdx.x;
+  float4 P[OPT_VEC], G[OPT_VEC], M[OPT_VEC], V[OPT_VEC];
+#pragma unroll
+  for (int k = 0; k < OPT_VEC; ++k) {   // all loads first: 4 x OPT_VEC independent 16-byte loads in flight per thread
+    const long long i = base + (long long)k * OPT_THREADS;
+    if (i < n4) {
+      P[k] = reinterpret_cast<const float4*>(p)[i];
+      G[k] = ld_stream(reinterpret_cast<const float4*>(g) + i);
+      M[k] = reinterpret_cast<const float4*>(m)[i];
+      V[k] = reinterpret_cast<const float4*>(v)[i];
+    }
   }
-  float4 M = reinterpret_cast<float4*>(m)[i];
-  float4 V = reinterpret_cast<float4*>(v)[i];
   auto one = [&](float& pp, float gg, float& mm, float& vv) {
+    if (grad_scale != 1.f) gg = __fmul_rn(gg, grad_scale);
     mm = fmaf(beta1, mm, (1.f - beta1) * gg);          // exp_avg.lerp_(grad, 1 - beta1)
     vv = fmaf(beta2, vv, (1.f - beta2) * gg * gg);     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
     pp = fmaf(-step_size, mm / denom, pp);
   };
-  one(P.x, G.x, M.x, V.x);
-  one(P.y, G.y, M.y, V.y);
-  one(P.z, G.z, M.z, V.z);
-  one(P.w, G.w, M.w, V.w);
-  reinterpret_cast<float4*>(p)[i] = P;
-  reinterpret_cast<float4*>(m)[i] = M;
-  reinterpret_cast<float4*>(v)[i] = V;
+#pragma unroll
+  for (int k = 0; k < OPT_VEC; ++k) {
+    const long long i = base + (long long)k * OPT_THREADS;
+    if (i >= n4) continue;
+    one(P[k].x, G[k].x, M[k].x, V[k].x);
+    one(P[k].y, G[k].y, M[k].y, V[k].y);
+    one(P[k].z, G[k].z, M[k].z, V[k].z);
+    one(P[k].w, G[k].w, M[k].w, V[k].w);
+    reinterpret_cast<float4*>(p)[i] = P[k];
+    reinterpret_cast<float4*>(m)[i] = M[k];
+    reinterpret_cast<float4*>(v)[i] = V[k];
+  }
 }
 
 }  // namespace asn
@@ -123,7 +161,7 @@ extern "C" int asn_sgd_step(float* params, const float* grads, float* momentum_b
   a.momentum = momentum; a.weight_decay = weight_decay; a.first_step = first_step;
   a.grad_scale = grad_scale;
   prof::Scope ps("sgd_step", 0, 5.0 * 4.0 * (double)n, st);
-  sgd_step_kernel<<<(unsigned)cdiv(a.n4, (long long)OPT_THREADS), OPT_THREADS, 0, st>>>(a);
+  sgd_step_kernel<<<(unsigned)cdiv(a.n4, (long long)OPT_THREADS * OPT_VEC), OPT_THREADS, 0, st>>>(a);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -142,7 +180,7 @@ extern "C" int asn_adam_step(float* params, const float* grads, float* exp_avg, 
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   prof::Scope ps("adam_step", 0, 7.0 * 4.0 * (double)n, st);
-  adam_step_kernel<<<(unsigned)cdiv(n / 4, (int64_t)OPT_THREADS), OPT_THREADS, 0, st>>>(
+  adam_step_kernel<<<(unsigned)cdiv(n / 4, (int64_t)OPT_THREADS * OPT_VEC), OPT_THREADS, 0, st>>>(
       params, grads, exp_avg, exp_avg_sq, n / 4, beta1, beta2, eps, step_size, inv_sqrt_bc2, grad_scale);
   ASN_LAUNCH_CHECK();
   return ASN_OK;

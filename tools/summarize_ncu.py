@@ -17,7 +17,7 @@ def short(name):
     return name[:110]
 
 
-OURS = re.compile(r"asn::|umma::|lazy::|^(aspp_|fcd_|lazy_|ce_kernel|ce_finalize|ce_generic|softmax_kernel|softmax_generic|"
+OURS = re.compile(r"asn::|umma::|lazy::|halo::|upsample2_|per_class_iu|^(aspp_|fcd_|lazy_|ce_kernel|ce_finalize|ce_generic|softmax_kernel|softmax_generic|"
                   r"sgd_step|adam_step|upsample_|fast_hist|gan_loss|nchw_|nhwc_)")
 
 
