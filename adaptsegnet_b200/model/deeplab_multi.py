@@ -131,9 +131,17 @@ class ResNetMulti(nn.Module):
             return f3.float(), f4.float()
         return self._trunk(x)
 
+    # optional callable(name, tensor) the trainer sets around ONE forward to learn when the backward has passed layer4 /
+    # layer3 (it hangs gradient hooks on the two activations; used to start bucketed gradient all-reduces early)
+    grad_probe = None
+
     def _trunk(self, x):
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
-        f3 = self.layer3(self.layer2(self.layer1(x)))
+        l2 = self.layer2(self.layer1(x))
+        f3 = self.layer3(l2)
+        if self.grad_probe is not None:
+            self.grad_probe("layer3_in", l2)
+            self.grad_probe("layer4_in", f3)
         return f3, self.layer4(f3)
 
     def forward(self, x, input_size=None, warper=None):

@@ -10,6 +10,7 @@ averaged once per optimizer right before ``step()``.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -137,6 +138,10 @@ class AdaptSegTrainer:
         # the target backward (_grads_step_overlap).  Same kernels, same accumulation order, more of the GPU busy.
         self.overlap = bool(overlap)
         self._stream_t = None
+        # data parallelism + two-stream schedule: the generator's gradient is all-reduced in three buckets (layer4 + heads,
+        # layer3, the rest) that start as soon as the target backward has passed them -- see _bucket_plan / step()
+        self._buckets = None
+        self.bucketed_allreduce = os.environ.get("ASN_BUCKETED_ALLREDUCE", "1") != "0"
         if self.overlap:   # gradients produced on `_stream_t` are accumulated on the current stream on purpose (see below)
             try:
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -322,8 +327,11 @@ class AdaptSegTrainer:
         st.wait_stream(main)
         reuse = cfg.reuse_target_forward and cfg.fuse_softmax and ops.precision_mode() == "bf16"
         saved, adv = {}, {}
+        probe_installed = self._install_bucket_probe(main)
         with torch.cuda.stream(st):
             pred_t = dict(zip(("D1", "D2"), preds(tgt_images)))
+            if probe_installed:
+                self.model.grad_probe = None
             loss_t = 0
             for D, key, lam in Ds:
                 if reuse:
@@ -359,6 +367,54 @@ class AdaptSegTrainer:
             out["loss_adv_target" + key[1]] = adv[key].detach() / it
         self._keep = (pred1, pred2, pred_t, saved, adv)   # cross-stream tensors stay alive until the next iteration
         return out
+
+    def _bucket_plan(self):
+        """[(begin, end, event-or-None)] over flat_G, last layers first: a bucket's gradient is final once the TARGET backward
+        (the second and last one into the generator) has passed its layers; the event is recorded at that point."""
+        if self._buckets is None:
+            fp = self.flat_G
+            b3 = fp.begin[fp.index[id(self.model.layer3[0].conv1.weight)]]
+            b4 = fp.begin[fp.index[id(self.model.layer4[0].conv1.weight)]]
+            ev = {"layer4_in": torch.cuda.Event(external=True), "layer3_in": torch.cuda.Event(external=True)}
+            self._buckets = {"events": ev, "slices": [(b4, fp.numel, "layer4_in"), (b3, b4, "layer3_in"), (0, b3, None)],
+                             "comm": torch.cuda.Stream()}
+        return self._buckets
+
+    def _install_bucket_probe(self, main):
+        """for the next trunk forward (the target's): gradient hooks on layer4's and layer3's inputs that record an event on
+        the accumulation stream `main` -- every parameter gradient of the layers behind them has been accumulated by then
+        (AccumulateGrad nodes run before anything else that is ready)."""
+        import torch.distributed as dist
+
+        if self.single_head or not self.fused_optimizers or not (dist.is_available() and dist.is_initialized()
+                                                                 and dist.get_world_size() > 1):
+            return False
+        plan = self._bucket_plan()
+
+        def probe(name, t):
+            if t.requires_grad:
+                t.register_hook(lambda g, e=plan["events"][name]: e.record(main))
+        self.model.grad_probe = probe
+        return True
+
+    def _all_reduce_generator_bucketed(self, group):
+        """issued right after the (asynchronous) launch of the iteration: three all-reduces over slices of the flat gradient
+        buffer, each behind the event that says its layers' gradients are final, on a side stream -- they overlap the rest of
+        the target backward.  -> list of NCCL work handles (the last bucket waits for the end of the iteration)."""
+        import torch.distributed as dist
+
+        plan, flat, works = self._bucket_plan(), self.flat_G.flat, []
+        cur = torch.cuda.current_stream()
+        comm = plan["comm"]
+        for b, e, name in plan["slices"]:
+            if name is None:
+                works.append(dist.all_reduce(flat[b:e], op=dist.ReduceOp.SUM, group=group, async_op=True))
+            else:
+                with torch.cuda.stream(comm):
+                    comm.wait_event(plan["events"][name])
+                    works.append(dist.all_reduce(flat[b:e], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        del cur
+        return works
 
     def _g_part(self, src_images, src_labels, tgt_images):
         """train...:578-633: the generator's two forward/backward passes.  After it the generator's gradient is final.
@@ -492,7 +548,10 @@ class AdaptSegTrainer:
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
             self._graph.replay()
-            pending = self.flat_G.all_reduce_start(group)   # 178 MB over NVLink while the discriminators train
+            if self.overlap and self.model.grad_probe is None and self._buckets is not None and self.bucketed_allreduce:
+                pending = self._all_reduce_generator_bucketed(group)
+            else:
+                pending = self.flat_G.all_reduce_start(group)   # 178 MB over NVLink while the discriminators train
             if self._graph_d is not None:
                 self._graph_d.replay()
             out = self._static_out
@@ -508,7 +567,13 @@ class AdaptSegTrainer:
             # one all-reduce for both discriminators, started right behind the discriminator part; the generator's (started
             # before it) is waited for first, its fused SGD step then runs while the discriminators' reduce is in flight
             pending_d = self.flat_D.all_reduce_start(group)
-            self.flat_G.all_reduce_finish(pending, group)
+            if isinstance(pending, list):
+                import torch.distributed as dist
+                for w in pending:
+                    w.wait()
+                self.flat_G.grad_scale = 1.0 / dist.get_world_size(group)
+            else:
+                self.flat_G.all_reduce_finish(pending, group)
             if do_optimizer_step:
                 self.optimizer.step()
             self.flat_D.all_reduce_finish(pending_d, group)
