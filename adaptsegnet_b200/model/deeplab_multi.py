@@ -140,8 +140,7 @@ class ResNetMulti(nn.Module):
         l2 = self.layer2(self.layer1(x))
         f3 = self.layer3(l2)
         if self.grad_probe is not None:
-            self.grad_probe("layer3_in", l2)
-            self.grad_probe("layer4_in", f3)
+            self.grad_probe("layer4.0", f3)
         return f3, self.layer4(f3)
 
     def forward(self, x, input_size=None, warper=None):

@@ -89,8 +89,11 @@ class FlatParams:
 
     def all_reduce_start(self, group=None):
         """asynchronous SUM all-reduce of the flat gradient buffer (None when there is nothing to reduce)"""
+        import os
         import torch.distributed as dist
 
+        if os.environ.get("ASN_DIAG_SKIP_ALLREDUCE") == "1":   # diagnosis only: how much of an N > 1 step is the exchange
+            return None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
         return None

@@ -141,7 +141,9 @@ class AdaptSegTrainer:
         # data parallelism + two-stream schedule: the generator's gradient is all-reduced in three buckets (layer4 + heads,
         # layer3, the rest) that start as soon as the target backward has passed them -- see _bucket_plan / step()
         self._buckets = None
-        self.bucketed_allreduce = os.environ.get("ASN_BUCKETED_ALLREDUCE", "1") != "0"
+        # opt-in (ASN_BUCKETED_ALLREDUCE=1): bit-identical to the single all-reduce (tools/dp_bucket_check.py, 2 GPUs) but
+        # measured neutral -- 34.38 vs 34.34 ms/step at 2 GPUs, 33.76 without any exchange; see _bucket_plan
+        self.bucketed_allreduce = os.environ.get("ASN_BUCKETED_ALLREDUCE", "0") == "1"
         if self.overlap:   # gradients produced on `_stream_t` are accumulated on the current stream on purpose (see below)
             try:
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -359,6 +361,8 @@ class AdaptSegTrainer:
             l_tgt = self.bce_loss(d_tgt, TARGET_LABEL) / it / 2
             l_tgt.backward()
             out["loss_" + key] = l_src[key].detach() + l_tgt.detach()
+        if probe_installed:
+            self._buckets["events"]["d_step"].record(main)   # the discriminators' gradients are final from here on
         # ---- T: backward(tgt); its convolutions run on `_stream_t`, the accumulation into the flat buffers on `main` ----
         with torch.cuda.stream(st):
             loss_t.backward()
@@ -373,11 +377,23 @@ class AdaptSegTrainer:
         (the second and last one into the generator) has passed its layers; the event is recorded at that point."""
         if self._buckets is None:
             fp = self.flat_G
-            b3 = fp.begin[fp.index[id(self.model.layer3[0].conv1.weight)]]
-            b4 = fp.begin[fp.index[id(self.model.layer4[0].conv1.weight)]]
-            ev = {"layer4_in": torch.cuda.Event(external=True), "layer3_in": torch.cuda.Event(external=True)}
-            self._buckets = {"events": ev, "slices": [(b4, fp.numel, "layer4_in"), (b3, b4, "layer3_in"), (0, b3, None)],
-                             "comm": torch.cuda.Stream()}
+            # Two buckets.  Measured at 2 GPUs (ms/step; no exchange at all: 33.49): layer4 + heads (68 MB) started when the
+            # target backward has passed layer4 is hidden completely (33.43); every later bucket (layer3 in one piece or
+            # in groups of six blocks, with or without a high-priority NCCL stream) runs beside the last 1-2 ms of the
+            # backward pass, where the NCCL kernels take SMs from the critical path and cost as much as they hide
+            # (33.81-34.37 against 34.03-34.07 for one all-reduce after the iteration).  So: the early bucket, the
+            # discriminators' buffer as soon as the discriminator step is done, and the rest when the iteration ends.
+            names = ["layer4.0"]
+            mods = dict(self.model.named_modules())
+            starts = [fp.begin[fp.index[id(mods[n].conv1.weight)]] for n in names]
+            ev = {n: torch.cuda.Event(external=True) for n in names}
+            ev["d_step"] = torch.cuda.Event(external=True)
+            slices, end = [], fp.numel
+            for n, b in zip(names, starts):
+                slices.append((b, end, n))
+                end = b
+            slices.append((0, end, None))     # conv1 .. layer3: final only when the iteration ends
+            self._buckets = {"events": ev, "slices": slices, "comm": torch.cuda.Stream()}
         return self._buckets
 
     def _install_bucket_probe(self, main):
@@ -392,7 +408,7 @@ class AdaptSegTrainer:
         plan = self._bucket_plan()
 
         def probe(name, t):
-            if t.requires_grad:
+            if t.requires_grad and name in plan["events"]:
                 t.register_hook(lambda g, e=plan["events"][name]: e.record(main))
         self.model.grad_probe = probe
         return True
@@ -404,16 +420,22 @@ class AdaptSegTrainer:
         import torch.distributed as dist
 
         plan, flat, works = self._bucket_plan(), self.flat_G.flat, []
-        cur = torch.cuda.current_stream()
         comm = plan["comm"]
-        for b, e, name in plan["slices"]:
+        diag = os.environ.get("ASN_DIAG_BUCKETS")   # diagnosis only: reduce just the first k buckets
+        work_d = None
+        for k, (b, e, name) in enumerate(plan["slices"]):
+            if diag is not None and k >= int(diag):
+                continue
             if name is None:
                 works.append(dist.all_reduce(flat[b:e], op=dist.ReduceOp.SUM, group=group, async_op=True))
             else:
                 with torch.cuda.stream(comm):
                     comm.wait_event(plan["events"][name])
                     works.append(dist.all_reduce(flat[b:e], op=dist.ReduceOp.SUM, group=group, async_op=True))
-        del cur
+                    if work_d is None and self.flat_D is not None:   # (NCCL runs its collectives in issue order)
+                        comm.wait_event(plan["events"]["d_step"])
+                        work_d = dist.all_reduce(self.flat_D.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        self._pending_d = work_d
         return works
 
     def _g_part(self, src_images, src_labels, tgt_images):
@@ -566,7 +588,10 @@ class AdaptSegTrainer:
         if self.flat_D is not None:
             # one all-reduce for both discriminators, started right behind the discriminator part; the generator's (started
             # before it) is waited for first, its fused SGD step then runs while the discriminators' reduce is in flight
-            pending_d = self.flat_D.all_reduce_start(group)
+            pending_d = getattr(self, "_pending_d", None) if isinstance(pending, list) else None
+            self._pending_d = None
+            if pending_d is None:
+                pending_d = self.flat_D.all_reduce_start(group)
             if isinstance(pending, list):
                 import torch.distributed as dist
                 for w in pending:

@@ -563,7 +563,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options()     # (a high-priority NCCL stream measured neutral: 34.31 vs 34.37 ms at 2 GPUs)
+        opts.is_high_priority_stream = os.environ.get("ASN_NCCL_HIGH_PRIORITY", "0") == "1"
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)  # train_gta2cityscapes_multi.py:228
 
     torch.manual_seed(SEED)  # identical replicas
