@@ -20,6 +20,7 @@ namespace asn {
 int channel_sum_nchw(const float* src, float* out, int N, int O, int P, cudaStream_t st);  // aspp.cu
 
 constexpr float FCD_SLOPE = 0.2f;  // model/discriminator.py:16
+constexpr int CLS_SLICES = 128;    // pixel slices of the classifier's weight gradient (one partial [16][C] each)
 
 struct FcdPlan {
   int N, n_cls, ndf;
@@ -30,7 +31,7 @@ struct FcdPlan {
   // wpack
   size_t wf_off[5], wd_off[5], bias_off[5], wc_off, bc_off, wpack_total;  // index 1..4
   // workspace
-  size_t dpre_off[5], da0_off, part_off[5], dbpart_off, ws_total;
+  size_t dpre_off[5], da0_off, part_off[5], dbpart_off, clspart_off, ws_total;
   int split[5];          // wgrad split-K per layer
   size_t part_bytes;
 };
@@ -122,6 +123,7 @@ static int make_plan(FcdPlan& p, int N, int n_cls, int ndf, int H, int W) {
     p.part_bytes += bytes;
   }
   p.dbpart_off = off; off += align256((size_t)4 * 256 * 2048 * 4);
+  p.clspart_off = off; off += align256((size_t)CLS_SLICES * 16 * p.C[4] * 4);   // classifier weight-gradient partials
   p.ws_total = off;
   return ASN_OK;
 }
@@ -434,8 +436,8 @@ fcd_cls_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w
 // grid (CLS_SLICES, C/64): thread = (channel, 1 of 4 pixel phases).  Every INPUT pixel of the slice is read once
 // (coalesced 128-byte rows along the channels) and feeds the <= 4 taps whose stride-2 footprint contains it -- which
 // taps is a matter of the pixel's row/column parity, uniform over the CTA, so the 16 accumulators stay in registers.
-// Shared-memory reduce over the phases, one fp32 atomic per (channel, tap, slice).
-constexpr int CLS_SLICES = 64;
+// Shared-memory reduce over the phases, then ONE plain store per (slice, tap, channel) into `part`; the slices are summed in
+// a fixed order by the merged end-of-backward reduce (fcd_wgrad_reduce_kernel, blockIdx.y == 4) -- no atomics, bit-reproducible (round 1 used fp32 atomics here).
 
 template <int KH, int KW>
 __device__ __forceinline__ void cls_tap(float (&acc)[16], float v, const float* __restrict__ dout, int n, int ih, int iw,
@@ -449,7 +451,7 @@ __device__ __forceinline__ void cls_tap(float (&acc)[16], float v, const float* 
 }
 
 __global__ void __launch_bounds__(256)
-fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a4, float* __restrict__ dw,
+fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a4, float* __restrict__ part,
                      int N, int H4, int W4, int C, int H5, int W5) {
   __shared__ float red[4][16][64];
   const int cl = threadIdx.x & 63, ph = threadIdx.x >> 6;
@@ -485,11 +487,11 @@ fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __rest
 #pragma unroll
   for (int t = 0; t < 16; ++t) red[ph][t][cl] = acc[t];
   __syncthreads();
-  // 64 channels x 16 taps = 1024 sums over the 4 phases; consecutive threads -> consecutive taps of one channel
+  // 64 channels x 16 taps = 1024 sums over the 4 phases; part[slice][tap][channel]: consecutive threads -> consecutive channels
   for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-    const int ch = e >> 4, t = e & 15;
+    const int t = e >> 6, ch = e & 63;
     if (blockIdx.y * 64 + ch < C)
-      atomicAdd(dw + (int64_t)(blockIdx.y * 64 + ch) * 16 + t, red[0][t][ch] + red[1][t][ch] + red[2][t][ch] + red[3][t][ch]);
+      part[((int64_t)blockIdx.x * 16 + t) * C + blockIdx.y * 64 + ch] = red[0][t][ch] + red[1][t][ch] + red[2][t][ch] + red[3][t][ch];
   }
 }
 
@@ -505,6 +507,10 @@ struct LayerReduce {
   const float* part[4];
   float* dw[4];
   int S[4], Cout[4], Cin_real[4], Ncols[4];
+  // classifier weight gradient: dwc[c][tap] = sum over the CLS_SLICES partials [slice][tap][c] (blockIdx.y == 4)
+  const float* cls_part;
+  float* cls_dw;
+  int cls_C;
 };
 
 // partial[cta][c] = sum of this CTA's row slice (fixed order -> deterministic).  Thread = 8 consecutive channels (one 16-byte
@@ -577,6 +583,16 @@ __global__ void __launch_bounds__(256) fcd_colsum_final_kernel(LayerReduce R) {
 // 256-byte row segments (col fastest), summed over the splits, transposed through shared memory and written as one
 // contiguous run of dW (tap fastest) -- both sides coalesced.
 __global__ void __launch_bounds__(256) fcd_wgrad_reduce_kernel(LayerReduce R) {
+  if (blockIdx.y == 4) {              // classifier: thread = (tap, channel), slices summed in order
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= 16 * R.cls_C) return;
+    const int t = i / R.cls_C, c = i - t * R.cls_C;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int s = 0; s < CLS_SLICES; ++s) acc += __ldg(R.cls_part + (int64_t)s * 16 * R.cls_C + i);
+    R.cls_dw[(int64_t)c * 16 + t] = acc;
+    return;
+  }
   const int l = blockIdx.y;           // 0..3 <-> conv1..conv4
   const int Cout = R.Cout[l], Cin_real = R.Cin_real[l], Ncols = R.Ncols[l], S = R.S[l];
   const int taps = l == 0 ? 8 : 16;
@@ -962,7 +978,8 @@ static int reduce_all(const FcdPlan& p, LayerReduce& R, cudaStream_t st) {
     prof::Scope ps("fcd_wgrad_reduce", 0, dw_bytes, st);
     int blocks = 1;
     for (int i = 0; i < 4; ++i) blocks = max(blocks, R.Cout[i] * cdiv(R.Ncols[i], 64));
-    fcd_wgrad_reduce_kernel<<<dim3((unsigned)blocks, 4), 256, 0, st>>>(R);
+    blocks = max(blocks, cdiv(16 * R.cls_C, 256));
+    fcd_wgrad_reduce_kernel<<<dim3((unsigned)blocks, R.cls_part ? 5 : 4), 256, 0, st>>>(R);
     ASN_LAUNCH_CHECK();
   }
   return ASN_OK;
@@ -1146,10 +1163,13 @@ static int fcd_bwd_impl(const float* dout, const float* x_logits, int x_h, int x
     ASN_CHECK_ARG(dparams_host[8] && dparams_host[9], "asn_fcd_bwd: null classifier gradient");
     {
       prof::Scope ps("fcd_classifier_wgrad", 2.0 * N * p.H[5] * p.W[5] * 16 * p.C[4], 0, st);
-      ASN_CUDA(cudaMemsetAsync(dparams_host[8], 0, (size_t)16 * p.C[4] * sizeof(float), st));
-      fcd_cls_wgrad_kernel<<<dim3(CLS_SLICES, cdiv(p.C[4], 64)), 256, 0, st>>>(dout, A[4], dparams_host[8], N, p.H[4],
-                                                                                   p.W[4], p.C[4], p.H[5], p.W[5]);
+      float* clspart = reinterpret_cast<float*>(ws + p.clspart_off);
+      fcd_cls_wgrad_kernel<<<dim3(CLS_SLICES, cdiv(p.C[4], 64)), 256, 0, st>>>(dout, A[4], clspart, N, p.H[4], p.W[4],
+                                                                                   p.C[4], p.H[5], p.W[5]);
       ASN_LAUNCH_CHECK();
+      R.cls_part = clspart;          // summed over the slices by the merged reduce at the end of the backward
+      R.cls_dw = dparams_host[8];
+      R.cls_C = p.C[4];
     }
     if ((rc = channel_sum_nchw(dout, dparams_host[9], N, 1, p.H[5] * p.W[5], st))) return rc;
   }

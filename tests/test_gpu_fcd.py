@@ -129,3 +129,17 @@ def test_fcd_oracle(mode, N, H, W):
     assert rel_err(out_l, oref) < tol
     dxl, _ = O.fcd_bwd(O.bf16_round(x) if mode == "bf16" else x, params, [a.astype(np.float64) for a in acts_l], dout)
     assert rel_err(dz, O.softmax_c_bwd(O.softmax_c(z), dxl)) < tol
+
+
+def test_backward_is_bit_reproducible():
+    """every gradient of the tensor-core path comes out of fixed-order reductions (split-K partials, bias partials, and --
+    since round 2 -- the classifier's weight gradient, which used fp32 atomics before): two runs are bit-identical"""
+    rng = np.random.default_rng(21)
+    x = rng.random((1, 19, 96, 160)).astype(np.float32)
+    params = seeded_params(5, 19, 64)
+    dout = rng.standard_normal((1, 1, 3, 5)).astype(np.float32)
+    a = run_fcd("bf16", x, params, dout)
+    b = run_fcd("bf16", x, params, dout)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for ga, gb in zip(a[2], b[2]):
+        assert np.array_equal(ga, gb)
