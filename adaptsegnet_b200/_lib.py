@@ -23,6 +23,7 @@ SIGNATURES = {
     "asn_launch_count": (c_int64, []),
     "asn_prof_enable": (c_int, [c_int]),
     "asn_prof_report": (c_int64, [C.c_char_p, c_int64]),
+    "asn_prof_sequence": (c_int64, [C.c_char_p, c_int64]),
     "asn_fast_hist": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "asn_fast_hist_lut": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "asn_upsample_bilinear_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

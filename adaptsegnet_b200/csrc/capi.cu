@@ -136,6 +136,24 @@ extern "C" int64_t asn_prof_report(char* buf, int64_t cap) {
 #define ASN_BUILD_ID "unknown"
 #endif
 extern "C" const char* asn_build_id(void) { return ASN_BUILD_ID; }
+// names of the recorded scopes in launch order, '\n'-separated (profiling tools: lines up ncu's launch list with the
+// library's own kernel names); returns the length needed
+extern "C" int64_t asn_prof_sequence(char* buf, int64_t cap) {
+  using namespace asn::prof;
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::string out;
+  for (auto& r : g_recs) {
+    out += r.name;
+    out += '\n';
+  }
+  if (buf && cap > 0) {
+    size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
+
 extern "C" int asn_abi_version(void) { return ASN_ABI_VERSION; }
 extern "C" const char* asn_last_error(void) { return asn::g_err; }
 extern "C" int asn_sm_count(int* out_host) {

@@ -23,3 +23,12 @@ def report() -> dict:
     buf = C.create_string_buffer(int(need) + 64)
     lib.asn_prof_report(buf, len(buf))
     return json.loads(buf.value.decode())
+
+
+def sequence() -> list:
+    """names of the recorded kernel scopes in launch order"""
+    lib = _lib.load()
+    need = lib.asn_prof_sequence(None, 0)
+    buf = C.create_string_buffer(int(need) + 64)
+    lib.asn_prof_sequence(buf, len(buf))
+    return [ln for ln in buf.value.decode().split("\n") if ln]

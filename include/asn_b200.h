@@ -69,6 +69,8 @@ ASN_API int asn_sm_count(int* out_host);
 ASN_API int64_t asn_launch_count(void);
 ASN_API int asn_prof_enable(int on);
 ASN_API int64_t asn_prof_report(char* buf_host, int64_t capacity);
+/* the recorded scope names in launch order, one per line (same buffer convention as asn_prof_report) */
+ASN_API int64_t asn_prof_sequence(char* buf_host, int64_t capacity);
 
 /* ------------------------------------------------------------------------------------
  * K7  confusion matrix.  replaces: compute_iou.py:15-17 (fast_hist), accumulate :57
