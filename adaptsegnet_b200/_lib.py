@@ -36,6 +36,8 @@ SIGNATURES = {
     "asn_upsample2_argmax_hist": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                           c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "asn_per_class_iu": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "asn_image_u8_to_bgr_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "asn_label_u8_to_trainid_i64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "asn_softmax_ce_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p]),
     "asn_softmax_ce_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,

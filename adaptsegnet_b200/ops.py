@@ -104,6 +104,43 @@ def fast_hist(label: torch.Tensor, pred: torch.Tensor, n_cls: int, hist: torch.T
 
 
 # --------------------------------------------------------------------------------------
+# input pipeline: dataset/gta5_dataset.py:58-71 on the raw 8-bit buffers
+# --------------------------------------------------------------------------------------
+GTA5_ID_TO_TRAINID = {7: 0, 8: 1, 11: 2, 12: 3, 13: 4, 17: 5, 19: 6, 20: 7, 21: 8, 22: 9, 23: 10, 24: 11, 25: 12, 26: 13,
+                      27: 14, 28: 15, 31: 16, 32: 17, 33: 18}   # dataset/gta5_dataset.py:28-30
+
+
+def image_to_tensor(rgb_u8: torch.Tensor, mean_bgr) -> torch.Tensor:
+    """(N, H, W, 3) uint8 RGB on the device -> (N, 3, H, W) fp32, BGR, mean-subtracted: `image[:, :, ::-1] - mean` then
+    `transpose((2, 0, 1))` of dataset/gta5_dataset.py:66-69, bit-exact (8-bit values and fp32 means subtract exactly)."""
+    rgb_u8 = _req(rgb_u8, torch.uint8, "image")
+    N, H, W, c3 = rgb_u8.shape
+    if c3 != 3:
+        raise ValueError("image must be (N, H, W, 3) uint8")
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=rgb_u8.device)
+    check(_lib.load().asn_image_u8_to_bgr_f32(rgb_u8.data_ptr(), out.data_ptr(), N, H, W, float(mean_bgr[0]),
+                                              float(mean_bgr[1]), float(mean_bgr[2]), _stream()), "asn_image_u8_to_bgr_f32")
+    _count()
+    return out
+
+
+def label_to_trainid(ids_u8: torch.Tensor, id_to_trainid=None, ignore_label=255) -> torch.Tensor:
+    """uint8 label ids -> int64 train ids (ignore_label where the table has no entry): dataset/gta5_dataset.py:61-64 + the
+    `.long()` of train...:595 in one pass."""
+    ids_u8 = _req(ids_u8, torch.uint8, "label")
+    table = GTA5_ID_TO_TRAINID if id_to_trainid is None else id_to_trainid
+    lut = torch.full((256,), int(ignore_label), dtype=torch.uint8)
+    for k, v in table.items():
+        lut[int(k)] = int(v)
+    lut = lut.to(ids_u8.device)
+    out = torch.empty(ids_u8.shape, dtype=torch.int64, device=ids_u8.device)
+    check(_lib.load().asn_label_u8_to_trainid_i64(ids_u8.data_ptr(), lut.data_ptr(), out.data_ptr(), ids_u8.numel(), _stream()),
+          "asn_label_u8_to_trainid_i64")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # K2 upsample
 # --------------------------------------------------------------------------------------
 def upsample_fwd_raw(x: torch.Tensor, H: int, W: int) -> torch.Tensor:

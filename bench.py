@@ -708,18 +708,19 @@ def run_b200(args):
                 "peak_source": peaks["source"] + " (sustained bf16 / copy bandwidth: kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": rec["flops"] / rec["launches"],
                 "algorithmic_bytes_per_launch": rec["bytes"] / rec["launches"]}
-        # measured DRAM traffic of that kernel from the committed ncu --set full capture (per launch, source-image shape)
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")) as f:
-                tr = json.load(f)["kernels"].get(name)
+        # measured DRAM traffic of that kernel from the committed ncu --set full capture (per launch; newest round first)
+        for tag in ("r02", "r01"):
+            try:
+                with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_traffic.json")) as f:
+                    tr = json.load(f)["kernels"].get(name)
+            except (OSError, ValueError, KeyError):
+                tr = None
             if tr:
                 roof["traffic"] = tr["dram_bytes_per_launch"]
-                roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch at the " + tr["shape"] +
-                                        " (ncu --set full, profiles/r01_hot_kernels_ncu_full.json); the step mixes source and "
-                                        "target shapes, algorithmic_bytes_per_launch is their average; outputs that stay in the "
+                roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, " + tr["shape"] +
+                                        f" (ncu --set full, profiles/{tag}_hot_kernels_ncu_full.json); outputs that stay in the "
                                         "126 MB L2 do not show up as DRAM writes")
-        except (OSError, ValueError, KeyError):
-            pass
+                break
         roof["launches_in_timed_region"] = rec["launches"]
         roof["avg_launch_ms"] = per_launch_ms
         hot_ms = sum(r["ms"] for r in kernels.values()) / args.steps

@@ -94,6 +94,16 @@ ASN_API int asn_fast_hist_lut(const void* label, int label_dtype, const uint8_t*
 ASN_API int asn_per_class_iu(const int64_t* hist, int n_cls, double* iu, double* miou, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Input pipeline, the tensor-forming tail of dataset/gta5_dataset.py:58-71 on the raw 8-bit
+ * buffers: RGB HWC uint8 -> fp32 CHW in BGR order with the per-channel mean subtracted (:66-69; mean_b/g/r = the script's
+ * IMG_MEAN), and label ids -> train ids through a 256-entry table (:61-64: the 19 pairs, 255 elsewhere) as int64 (the dtype
+ * the loss wants, train...:595).  The PIL resize in front (:51-52) stays on the host.
+ * ---------------------------------------------------------------------------------- */
+ASN_API int asn_image_u8_to_bgr_f32(const uint8_t* rgb_hwc, float* out_chw, int N, int H, int W, float mean_b, float mean_g,
+                            float mean_r, void* stream);
+ASN_API int asn_label_u8_to_trainid_i64(const uint8_t* ids, const uint8_t* lut256, int64_t* out, int64_t n_px, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K2 / K2b / K9  bilinear resize, align_corners=True.
  *   replaces: model/deeplab_multi.py:188-189, evaluate_cityscapes.py:153 (nn.Upsample)
  *   and its autograd; asn_upsample_argmax_u8 replaces evaluate_cityscapes.py:163,168-169

@@ -295,6 +295,32 @@ def gold_eval2():
     save("eval2", **out)
 
 
+def gold_preprocess():
+    """dataset/gta5_dataset.py:47-71 run for real on two PNG files of exactly the crop size (so that its PIL resize is the
+    identity): pins the tensor-forming tail -- BGR flip, mean subtraction, CHW transpose, id -> train id remap."""
+    import tempfile
+    import types
+    from PIL import Image
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))          # import-only dependency (SURVEY Q4)
+    sys.modules.setdefault("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot"))
+    from dataset.gta5_dataset import GTA5DataSet
+    rng = np.random.RandomState(SEED)
+    H, W = 32, 48
+    rgb = rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    ids = rng.randint(0, 35, size=(H, W)).astype(np.uint8)
+    mean = np.array((104.00698793, 116.66876762, 122.67891434), dtype=np.float32)   # train...:30
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "images"))
+        os.makedirs(os.path.join(d, "labels"))
+        Image.fromarray(rgb).save(os.path.join(d, "images", "a.png"))
+        Image.fromarray(ids).save(os.path.join(d, "labels", "a.png"))
+        with open(os.path.join(d, "list.txt"), "w") as f:
+            f.write("a.png\n")
+        ds = GTA5DataSet(d, os.path.join(d, "list.txt"), crop_size=(W, H), scale=False, mirror=False, mean=mean)
+        image, label, size, name = ds[0]
+    save("preprocess", rgb=rgb, ids=ids, mean=mean, image=image, label=label, size=size)
+
+
 def gold_step():
     """whole multi-level / single-level iteration (train_gta2cityscapes_multi.py:560-683, :373-464) driven
     through oracle/torch_ref.RefTrainer's restated loop with the REFERENCE's own modules injected."""
@@ -329,6 +355,6 @@ def gold_step():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["aspp", "upsample", "ce", "softmax", "fcd", "ganloss", "hist", "argmax", "eval2", "step"]
+    which = sys.argv[1:] or ["aspp", "upsample", "ce", "softmax", "fcd", "ganloss", "hist", "argmax", "eval2", "preprocess", "step"]
     for name in which:
         globals()["gold_" + name]()

@@ -268,3 +268,21 @@ def test_fast_hist_with_label_mapping(ops, dtype):
     from adaptsegnet_b200 import compute_iou as CI
     assert np.array_equal(CI.fast_hist(raw.astype(dtype), pred, 19, mapping=CITYSCAPES_LABEL2TRAIN), ref)
     assert np.array_equal(CI.label_mapping(raw, CITYSCAPES_LABEL2TRAIN), O.label_mapping(raw, CITYSCAPES_LABEL2TRAIN))
+
+
+# ---------------------------------------------------------------- input pipeline tail
+def test_input_pipeline_kernels(ops, golden):
+    g = golden("preprocess")
+    img = ops.image_to_tensor(cuda(g["rgb"][None]), g["mean"])
+    assert np.array_equal(host(img)[0], g["image"])                      # bit exact vs the reference's dataset class
+    lab = ops.label_to_trainid(cuda(g["ids"][None]))
+    assert lab.dtype == torch.int64 and np.array_equal(host(lab)[0], g["label"].astype(np.int64))
+    rng = np.random.default_rng(9)                                       # a batch at the real size
+    rgb = rng.integers(0, 256, (2, 720, 1280, 3)).astype(np.uint8)
+    ids = rng.integers(0, 256, (2, 720, 1280)).astype(np.uint8)
+    mean = np.array((104.00698793, 116.66876762, 122.67891434), dtype=np.float32)
+    out = host(ops.image_to_tensor(cuda(rgb), mean))
+    lab = host(ops.label_to_trainid(cuda(ids)))
+    for n in range(2):
+        assert np.array_equal(out[n], O.gta5_image_to_tensor(rgb[n], mean))
+        assert np.array_equal(lab[n], O.gta5_label_to_trainid(ids[n]).astype(np.int64))

@@ -134,3 +134,12 @@ def test_two_stage_eval_chain_bit_exact(golden):
     assert np.array_equal(pred, g["mid_pred"])
     # a single-stage resize is NOT the reference's arithmetic at these shapes
     assert (O.upsample_argmax(g["mid_x"], 518, 1030) != g["mid_pred"]).any()
+
+
+def test_input_pipeline_tail(golden):
+    """dataset/gta5_dataset.py:58-71 (BGR flip, mean, CHW, id -> train id) against the reference's own dataset class run on
+    PNG files of the crop size"""
+    g = golden("preprocess")
+    assert np.array_equal(O.gta5_image_to_tensor(g["rgb"], g["mean"]), g["image"])
+    assert np.array_equal(O.gta5_label_to_trainid(g["ids"]), g["label"])
+    assert tuple(g["size"]) == g["rgb"].shape

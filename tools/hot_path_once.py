@@ -26,11 +26,16 @@ head5 = Classifier_Module(1024, [6, 12, 18, 24], [6, 12, 18, 24], 19).to(dev)
 f3 = (torch.randn(1, 1024, h, w, device=dev).abs() * 4.4).requires_grad_(True)
 f4cl = f4.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
 from adaptsegnet_b200.optim import FlatParams, FusedAdam, FusedSGD
-flatD = FlatParams(D.parameters())
+from adaptsegnet_b200.model.deeplab_multi import DeeplabMulti
+from adaptsegnet_b200.train_step import TrainConfig
+D_b = FCDiscriminator(19).to(dev)
+flatD = FlatParams(list(D.parameters()) + list(D_b.parameters()))       # both discriminators: one buffer, one Adam launch
 adam = FusedAdam(flatD, lr=1e-4, betas=(0.9, 0.99))
-flatH = FlatParams(list(head.parameters()) + list(head5.parameters()))
-sgd = FusedSGD(flatH, [{"params": list(head.parameters()) + list(head5.parameters()), "lr": 2.5e-3}], lr=2.5e-3,
-               momentum=0.9, weight_decay=5e-4)
+# the generator's optimizer at its real size (44.5 M parameters, the reference's duplicated groups): what bench.py times
+G_full = DeeplabMulti(19).to(dev)
+flatG = FlatParams(G_full.parameters())
+sgd = FusedSGD(flatG, G_full.optim_parameters(TrainConfig()), lr=2.5e-4, momentum=0.9, weight_decay=5e-4)
+flatG.flat.normal_(0, 1e-3)
 
 
 tier_b_only = "--tier-b" in sys.argv
@@ -42,6 +47,8 @@ ovf_eval = torch.zeros(1, dtype=torch.int64, device=dev)
 
 def one_pass():
     loss = None
+    head._pack.invalidate()      # weight packing is part of every pass (in training the optimizer step invalidates it)
+    head5._pack.invalidate()
     if not tier_b_only:
         # Tier-A chain (full-resolution logits materialised) on the layer4 head
         logits = head(f4)
