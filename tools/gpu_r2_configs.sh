@@ -21,7 +21,8 @@ PY
 }
 EXTRA=""
 if [ "$N" -gt 1 ]; then EXTRA="--no-cpu-baseline"; fi
-run multi --steps 20 --warmup 5 --also-trunk-bf16 0 $EXTRA
-run singleLS --level single-level --gan LS --steps 20 --warmup 5 --also-trunk-bf16 0 $EXTRA
-run vgg --model VGG --gan LS --steps 20 --warmup 5 --also-trunk-bf16 0 $EXTRA
-run eval --mode eval --frames 500 $EXTRA
+WHICH=${3:-multi,singleLS,vgg,eval}
+case ",$WHICH," in *,multi,*) run multi --steps 20 --warmup 5 --also-trunk-bf16 0 $EXTRA;; esac
+case ",$WHICH," in *,singleLS,*) run singleLS --level single-level --gan LS --steps 20 --warmup 5 --also-trunk-bf16 0 $EXTRA;; esac
+case ",$WHICH," in *,vgg,*) run vgg --model VGG --gan LS --steps 20 --warmup 5 --also-trunk-bf16 0 $EXTRA;; esac
+case ",$WHICH," in *,eval,*) run eval --mode eval --frames 500 $EXTRA;; esac

@@ -25,7 +25,7 @@ def main():
         except (KeyError, ValueError):
             return None
 
-    launches = [r for r in rows[2:] if OURS.search(r[idx["Kernel Name"]])]
+    launches = rows[2:]   # (the capture's -k regex already restricts it to the library's kernels)
     names = []
     for n in seq:
         names += [n] * MULTI.get(n, 1)
