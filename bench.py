@@ -613,19 +613,36 @@ def run_b200(args):
     n_losses = 6 if args.level == "multi-level" else 3
     losses_host = torch.empty(n_losses, dtype=torch.float32).pin_memory()
 
-    def step_e2e(_):
-        # host -> device copies of this step's inputs from pinned memory (straight into the graph's static
-        # input buffers when replaying a CUDA graph), the step, and the losses back on the host
+    # e2e input pipeline: what a DataLoader with pinned memory and one batch of prefetch does -- the NEXT step's images and
+    # labels travel host -> device on a copy stream into a staging set while the current step computes; the step itself
+    # starts with a device-to-device copy of its (already resident) staging set into the graph's static input buffers.
+    # Every step's 24.7 MB still cross PCIe inside the timed region, the losses still come back and are waited for.
+    copy_stream = torch.cuda.Stream()
+    staging = [tuple(torch.empty_like(t) for t in (src, lab, tgt)) for _ in range(2)]
+    staged = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"primed": False}
+
+    def prefetch(k):
+        copy_stream.wait_stream(torch.cuda.current_stream())   # the staging set's previous reader is done
+        with torch.cuda.stream(copy_stream):
+            for d, h in zip(staging[k], (src_h, lab_h, tgt_h)):
+                d.copy_(h, non_blocking=True)
+            staged[k].record(copy_stream)
+
+    def step_e2e(i):
+        cur = it[0] & 1
+        if not e2e_state["primed"]:          # the very first step has nothing prefetched: its copy is exposed
+            prefetch(cur)
+            e2e_state["primed"] = True
+        torch.cuda.current_stream().wait_event(staged[cur])
         if trainer.use_cuda_graph and trainer._graph is not None:
-            s, l, t = trainer._static_in
-            s.copy_(src_h, non_blocking=True)
-            l.copy_(lab_h, non_blocking=True)
-            t.copy_(tgt_h, non_blocking=True)
+            ins = trainer._static_in
+            for d, s_ in zip(ins, staging[cur]):
+                d.copy_(s_, non_blocking=True)
         else:
-            s = src_h.to(dev, non_blocking=True)
-            l = lab_h.to(dev, non_blocking=True)
-            t = tgt_h.to(dev, non_blocking=True)
-        out = trainer.step(s, l, t, i_iter=it[0])
+            ins = staging[cur]
+        prefetch(cur ^ 1)                    # next step's inputs: host -> device beside this step's compute
+        out = trainer.step(*ins, i_iter=it[0])
         vals = torch.stack([v.float() for v in out.values()])
         losses_host.copy_(vals, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the losses every iteration
