@@ -442,6 +442,7 @@ def run_eval(args):
     ms_e2e = None if args.no_e2e else timed(run_e2e)
     # ---- per-kernel events over a few eager frames (events cannot be recorded inside a captured graph) ----
     kernels = {}
+    launches_per_frame = None
     if not args.no_kernel_events:
         ev3 = Evaluator(model, 19, EVAL_LABEL_HW, mapping=CITYSCAPES_LABEL2TRAIN, use_cuda_graph=False,
                         channels_last=bool(args.channels_last))
@@ -449,9 +450,11 @@ def run_eval(args):
             ev3.step(*pool_d[f % 8])
         prof.enable(True)
         n_ev = 16
+        l0 = prof.launch_count()
         for f in range(n_ev):
             ev3.step(*pool_d[f % 8])
         torch.cuda.synchronize()
+        launches_per_frame = (prof.launch_count() - l0) / n_ev   # the graph replays of the timed region launch the same kernels
         kernels = prof.report()
         prof.enable(False)
     if rank == 0:
@@ -464,7 +467,9 @@ def run_eval(args):
                 "e2e": {"value": (n * 1000.0 / ms_e2e) if ms_e2e else None, "unit": "frames/s",
                         "h2d_bytes_per_step": int(pool_h[0][0].numel() * 4 + pool_h[0][1].numel()),
                         "d2h_bytes_per_step": int(pred_h.numel())},
-                "gpu_launches": int(launches) * world, "miou": float(miou.item()),
+                # kernels of this library per frame (counted in the eager pass; the captured frames replay the same ones)
+                "gpu_launches": int(round(launches_per_frame * n)) if launches_per_frame else int(launches) * world,
+                "gpu_launches_per_frame": launches_per_frame, "miou": float(miou.item()),
                 "e2e_hist_equals_resident": bool(torch.equal(ev2.hist, hist_all)) if ms_e2e else None}
         if kernels:
             def frac_of(rec):
