@@ -402,8 +402,8 @@ class AdaptSegTrainer:
         (AccumulateGrad nodes run before anything else that is ready)."""
         import torch.distributed as dist
 
-        if self.single_head or not self.fused_optimizers or not (dist.is_available() and dist.is_initialized()
-                                                                 and dist.get_world_size() > 1):
+        if not self.bucketed_allreduce or self.single_head or not self.fused_optimizers or \
+                not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return False
         plan = self._bucket_plan()
 

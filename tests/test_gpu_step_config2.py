@@ -1,7 +1,8 @@
 """-m gpu: the whole hot path of one multi-level iteration at BASELINE config-2 shapes (720x1280 source, 512x1024
 target) in the BENCHMARKED configuration -- channels_last trunk, Tier-B (lazy upsample: fused upsample+softmax+CE and
 upsample+softmax inside the discriminators' input pack), fused softmax, the D step's target forward replayed from the G
-step's activations, everything captured as CUDA graphs -- gated per backward pass at the north star's 1e-2.
+step's activations, the two-stream schedule (source pipeline, target pipeline and discriminator step overlapped), everything
+captured as ONE CUDA graph -- gated per backward pass at the north star's 1e-2.
 
 Why per backward pass: a gradient compared across two DIFFERENT forwards (bf16 tensor cores here, fp32 on the host
 there) measures the discontinuities of the network (LeakyReLU sign flips, softmax amplification of the logit error) and
@@ -17,7 +18,7 @@ this run produced.  Gates for every head and discriminator gradient: L2-relative
               logits (through the LeakyReLU masks of the saved activations), head backward
   C  discriminator step: parameter gradients of the source pass and of the (replayed) target pass, separately
   D  the sum of the separately checked pieces == what AdaptSegTrainer.step() leaves in its flat gradient buffers when it
-     runs the same iteration as two captured CUDA graphs (ties A-C to the configuration bench.py times)
+     runs the same iteration as the captured two-stream CUDA graph (ties A-C to the configuration bench.py times)
 """
 import numpy as np
 import pytest
@@ -81,7 +82,7 @@ def test_whole_hot_path_config2_per_backward_gates():
     torch.manual_seed(SEED)
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = TrainConfig(level="multi-level", gan="Vanilla", lazy_upsample=True)
-    tr = AdaptSegTrainer(cfg, device="cuda", use_cuda_graph=True, channels_last=True)
+    tr = AdaptSegTrainer(cfg, device="cuda", use_cuda_graph=True, channels_last=True, overlap=True)   # as bench.py runs it
     src, lab, tgt = (t.cuda() for t in TR.synthetic_batch(SEED, SRC_HW, TGT_HW))
     report = {}
 

@@ -23,7 +23,7 @@ trainers = {}
 for mode in ("bucketed", "single"):
     torch.manual_seed(1338)
     tr = AdaptSegTrainer(TrainConfig(lazy_upsample=True), device=dev, use_cuda_graph=True, channels_last=True, overlap=True)
-    tr.bucketed_allreduce = mode == "bucketed"      # (the default is the single all-reduce; this is the opt-in path)
+    tr.bucketed_allreduce = mode == "bucketed"      # (set before the first step: the default is the single all-reduce)
     trainers[mode] = tr
 hw_s, hw_t = (264, 520), (200, 392)
 ok = True
