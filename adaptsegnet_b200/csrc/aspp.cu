@@ -152,6 +152,43 @@ aspp_gather_kernel(const float* __restrict__ Z, const float* __restrict__ bias_s
   }
 }
 
+// Round-2 form of the gather: warp = ONE pixel, lane = class.  All (up to 36) taps of the pixel are independent 76-byte
+// loads issued back to back (fully unrolled, the bounds test is warp-uniform), so an SM keeps 32 warps x 36 loads in
+// flight instead of 24 warps x 6; a CTA owns 8 consecutive pixels and writes 32-byte runs of the NCHW rows.  The sum runs
+// over the taps in the same order as before (bit-identical results).
+constexpr int GATHER_PX = 8;
+__global__ void __launch_bounds__(32 * GATHER_PX, 4)
+aspp_gather_px_kernel(const float* __restrict__ Z, const float* __restrict__ bias_sum, float* __restrict__ y, int N,
+                      int H, int W, int n_cls, int NP, const AsppTaps taps) {
+  __shared__ float stage[32][GATHER_PX + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = H * W;
+  const int groups_per_img = (P + GATHER_PX - 1) / GATHER_PX;
+  const int n = blockIdx.x / groups_per_img;
+  const int p0 = (blockIdx.x - n * groups_per_img) * GATHER_PX;
+  const int p = p0 + warp;
+  if (p < P && lane < n_cls) {
+    const int h = p / W, w = p - h * W;
+    const float* Zn = Z + (int64_t)n * P * NP + lane;
+    float v[36];
+#pragma unroll
+    for (int t = 0; t < 36; ++t) {
+      const int hh = h + taps.dh[t], ww = w + taps.dw[t];
+      const bool ok = t < taps.n_taps && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+      v[t] = ok ? __ldg(Zn + (int64_t)(hh * W + ww) * NP + t * n_cls) : 0.f;
+    }
+    float acc = __ldg(bias_sum + lane);
+#pragma unroll
+    for (int t = 0; t < 36; ++t) acc += v[t];
+    stage[lane][warp] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n_cls * GATHER_PX; idx += 32 * GATHER_PX) {
+    const int c = idx / GATHER_PX, pl = idx - c * GATHER_PX;
+    if (p0 + pl < P) y[((int64_t)n * n_cls + c) * P + p0 + pl] = stage[c][pl];
+  }
+}
+
 // dYcol[n*P + q][t*n_cls + c] = dy[n][c][q - shift_t] (0 outside).  One CTA per 32 pixels; the [32][NP] tile is
 // staged in shared memory so the rows are written with coalesced 16-byte stores.
 __global__ void __launch_bounds__(256)
@@ -191,6 +228,54 @@ aspp_dycols_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYc
     const int r = i / wpr, w = i - r * wpr;
     dst[i] = srcw[r * (TP / 2) + w];
   }
+}
+
+// Round-2 form of dYcol: no shared-memory tile.  A warp owns 32 consecutive pixels x one 32-byte chunk (16 columns
+// j = t*n_cls + c) of their dYcol rows: lane = pixel, so each of the 16 reads of dy[c][q - shift_t] is a coalesced
+// 128-byte row segment (dy is 1.1 MB and stays in L1/L2), all 16 are independent, and the lane writes its 32 bytes with
+// one 256-bit store (a full sector; rows are NP*2 = 32-byte multiples apart).  The first `extra_blocks` blocks compute the bias
+// gradient db[c] = sum_p dy[c][p] (what used to be a separate 19-CTA launch) beside the rest.
+__global__ void __launch_bounds__(256)
+aspp_dycols_chunk_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dYcol, float* __restrict__ db, int N,
+                         int H, int W, int n_cls, int NP, int extra_blocks, const AsppTaps taps) {
+  const int P = H * W;
+  if ((int)blockIdx.x < extra_blocks) {   // the (longer, latency-bound) channel sums start first and run beside the rest
+    block_channel_sum(dy, db, N, n_cls, P, blockIdx.x);
+    return;
+  }
+  const int chunks = NP / 16;
+  const int groups_per_img = (P + 31) / 32;
+  const int64_t gw = (int64_t)(blockIdx.x - extra_blocks) * 8 + (threadIdx.x >> 5);   // global warp = (image, pixel group, chunk)
+  if (gw >= (int64_t)N * groups_per_img * chunks) return;
+  const int ck = (int)(gw % chunks);
+  const int grp = (int)(gw / chunks);
+  const int n = grp / groups_per_img;
+  const int q = (grp - n * groups_per_img) * 32 + (threadIdx.x & 31);
+  if (q >= P) return;
+  const int qh = q / W, qw = q - qh * W;
+  const float* dyn = dy + (int64_t)n * n_cls * P;
+  int t = (ck * 16) / n_cls, c = ck * 16 - t * n_cls;                  // warp-uniform
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x = 0.f;
+    if (t < taps.n_taps) {
+      const int h = qh - taps.dh[t], w = qw - taps.dw[t];
+      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) x = __ldg(dyn + (int64_t)c * P + h * W + w);
+    }
+    v[i] = x;
+    if (++c == n_cls) { c = 0; ++t; }
+  }
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    pk[i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  __nv_bfloat16* dst = dYcol + ((int64_t)n * P + q) * NP + ck * 16;
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+               "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+               : "memory");
 }
 
 // Wp[j][ci] (bf16, j = t*n_cls + c, rows >= J zero) and WpT[ci][j] from the fp32 OIHW branch weights
@@ -248,33 +333,85 @@ aspp_unpack_dw_kernel(const float* __restrict__ part, int S, GradPtrs gp, int n_
   }
 }
 
+// Round-2 form of the unpack: one CTA per input channel.  Its NP-float row of every split-K partial is read with 16-byte
+// loads, all splits of a thread's four columns in flight at once; the 9-float runs of dW_b[c][ci][:] leave from shared memory.
+__global__ void __launch_bounds__(192)
+aspp_unpack_dw_row_kernel(const float* __restrict__ part, int S, GradPtrs gp, int n_active, int n_cls, int Cin, int NP) {
+  extern __shared__ float t[];  // [NP]
+  const int ci = blockIdx.x;
+  const int64_t zs = (int64_t)Cin * NP;
+  for (int e = threadIdx.x; e < NP / 4; e += 192) {
+    const float4* src = reinterpret_cast<const float4*>(part + (int64_t)ci * NP) + e;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int s = 0; s < S; ++s) {
+      const float4 v = ld_stream(src + s * (zs / 4));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(t)[e] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_active * n_cls * 9; e += 192) {
+    const int bc = e / 9, k = e - bc * 9;
+    const int b = bc / n_cls, c = bc - b * n_cls;
+    float* wb = b == 0 ? gp.w[0] : b == 1 ? gp.w[1] : b == 2 ? gp.w[2] : gp.w[3];   // (no dynamic index into the parameters)
+    if (wb) wb[((int64_t)c * Cin + ci) * 9 + k] = t[(b * 9 + k) * n_cls + c];
+  }
+}
+
+// Round-2 form of the weight pack: one CTA per PKW_CI input channels owns ALL their packed columns.  Reads: for every
+// (branch, class) the PKW_CI*9 contiguous floats of w_b[c][ci0..][:]; writes: whole rows of WpT (16-byte stores) and 16-byte
+// pieces of the Wp rows -- no 2-byte scattered stores (the old kernel wrote WpT one bf16 at a time, 1376 bytes apart).
+constexpr int PKW_CI = 8;
+__global__ void __launch_bounds__(256)
+aspp_pack_rows_kernel(WeightPtrs wp, __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* __restrict__ WpT, int n_active,
+                      int n_cls, int Cin, int NP) {
+  extern __shared__ __align__(16) unsigned char pk_raw[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(pk_raw);  // [PKW_CI][NP]
+  const int ci0 = blockIdx.x * PKW_CI;
+  const int J = n_active * 9 * n_cls;
+  for (int e = threadIdx.x; e < PKW_CI * (NP - J); e += 256)      // padding columns
+    tile[(e / (NP - J)) * NP + J + e % (NP - J)] = __float2bfloat16(0.f);
+  // per (branch, class): PKW_CI * 9 = 72 contiguous floats = 18 float4 (288-byte aligned runs)
+  constexpr int RUN4 = PKW_CI * 9 / 4;
+#pragma unroll 6
+  for (int e = threadIdx.x; e < n_active * n_cls * RUN4; e += 256) {
+    const int bc = e / RUN4, r4 = e - bc * RUN4;
+    const int b = bc / n_cls, c = bc - b * n_cls;
+    const float* wb = b == 0 ? wp.w[0] : b == 1 ? wp.w[1] : b == 2 ? wp.w[2] : wp.w[3];
+    const float4 v = ld_stream(reinterpret_cast<const float4*>(wb + ((int64_t)c * Cin + ci0) * 9) + r4);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r4 * 4 + i;
+      const int cl = r / 9, k = r - cl * 9;
+      tile[cl * NP + (b * 9 + k) * n_cls + c] = __float2bfloat16(f[i]);
+    }
+  }
+  __syncthreads();
+  if (WpT) {   // rows ci0 .. ci0+PKW_CI-1 of WpT are the tile itself
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+    uint4* dst = reinterpret_cast<uint4*>(WpT + (int64_t)ci0 * NP);
+    for (int e = threadIdx.x; e < PKW_CI * NP / 8; e += 256) dst[e] = src[e];
+  }
+  if (Wp) {    // Wp[j][ci0 .. ci0+7]: one 16-byte store per packed row
+    for (int j = threadIdx.x; j < NP; j += 256) {
+      uint32_t w4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = *reinterpret_cast<const unsigned short*>(tile + (2 * i) * NP + j);
+        const uint32_t hi = *reinterpret_cast<const unsigned short*>(tile + (2 * i + 1) * NP + j);
+        w4[i] = lo | (hi << 16);
+      }
+      *reinterpret_cast<uint4*>(Wp + (int64_t)j * Cin + ci0) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  }
+}
+
 // column sums over pixels of an NCHW tensor: out[o] = sum_{n,p} src[n][o][p]
 __global__ void __launch_bounds__(256)
 nchw_channel_sum_kernel(const float* __restrict__ src, float* __restrict__ out, int N, int O, int P) {
-  __shared__ double part[8];
-  const int o = blockIdx.x;
-  double acc = 0.0;
-  for (int n = 0; n < N; ++n) {
-    const float* s = src + ((int64_t)n * O + o) * P;
-    if ((P & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
-      // 16-byte loads, four independent fp32 partial sums per thread folded into the double accumulator per load
-#pragma unroll 4
-      for (int i = threadIdx.x; i < P / 4; i += 256) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
-        acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
-      }
-    } else {
-      for (int i = threadIdx.x; i < P; i += 256) acc += (double)s[i];
-    }
-  }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = threadIdx.x < 8 ? part[threadIdx.x] : 0.0;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) out[o] = (float)v;
-  }
+  block_channel_sum(src, out, N, O, P, blockIdx.x);
 }
 
 int channel_sum_nchw(const float* src, float* out, int N, int O, int P, cudaStream_t st) {
@@ -317,6 +454,12 @@ static int make_taps(AsppTaps& t, const int* dil, int n_active, int W) {
         t.dw[b * 9 + kh * 3 + kw] = (kw - 1) * dil[b];
       }
   return ASN_OK;
+}
+
+// ASN_GLUE=0 selects the round-1 forms of the layout kernels (gather, dYcol, unpack, pack) for A/B measurements
+static bool glue_v2() {
+  static const bool on = !(getenv("ASN_GLUE") != nullptr && getenv("ASN_GLUE")[0] == '0');
+  return on;
 }
 
 struct AsppWs {
@@ -374,8 +517,17 @@ extern "C" int asn_aspp_pack_weights(const float* const* w_oihw, int n_active, i
   }
   const int NP = asn_aspp_np(n_cls, n_active);
   prof::Scope ps("aspp_pack_weights", 0, (36.0 * n_active / 4 + 4.0) * NP * Cin, static_cast<cudaStream_t>(stream));
-  aspp_pack_kernel<<<full_grid((int64_t)NP * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      wp, static_cast<__nv_bfloat16*>(wp_bf16), static_cast<__nv_bfloat16*>(wpt_bf16), n_active, n_cls, Cin, NP);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(wp_bf16) | reinterpret_cast<uintptr_t>(wpt_bf16)) & 15) == 0;
+  bool w_aligned = true;
+  for (int b = 0; b < n_active; ++b) w_aligned = w_aligned && (reinterpret_cast<uintptr_t>(w_oihw[b]) & 15) == 0;
+  if (glue_v2() && Cin % PKW_CI == 0 && aligned && w_aligned) {
+    const size_t smem = (size_t)PKW_CI * NP * sizeof(__nv_bfloat16);
+    aspp_pack_rows_kernel<<<Cin / PKW_CI, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        wp, static_cast<__nv_bfloat16*>(wp_bf16), static_cast<__nv_bfloat16*>(wpt_bf16), n_active, n_cls, Cin, NP);
+  } else {
+    aspp_pack_kernel<<<full_grid((int64_t)NP * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        wp, static_cast<__nv_bfloat16*>(wp_bf16), static_cast<__nv_bfloat16*>(wpt_bf16), n_active, n_cls, Cin, NP);
+  }
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -429,7 +581,10 @@ extern "C" int asn_aspp_fwd(const float* x_nchw, int x_channels_last, void* x_bf
   make_taps(taps, dil_host, n_active, W);
   const int groups = N * cdiv(P, 32);
   prof::Scope ps("aspp_gather", 0, 4.0 * N * P * (9.0 * n_active * n_cls + n_cls), st);
-  aspp_gather_kernel<32><<<groups, 256, 0, st>>>(Z, bias_sum, y_nchw, N, H, W, n_cls, ws.NP, taps);
+  if (glue_v2())
+    aspp_gather_px_kernel<<<N * cdiv(P, GATHER_PX), 32 * GATHER_PX, 0, st>>>(Z, bias_sum, y_nchw, N, H, W, n_cls, ws.NP, taps);
+  else
+    aspp_gather_kernel<32><<<groups, 256, 0, st>>>(Z, bias_sum, y_nchw, N, H, W, n_cls, ws.NP, taps);
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -455,12 +610,21 @@ extern "C" int asn_aspp_bwd(const void* x_bf16, int dx_channels_last, const void
   AsppTaps taps;
   make_taps(taps, dil_host, n_active, W);
   const double flops = 2.0 * N * P * (9.0 * n_active * n_cls) * Cin;
+  bool db_done = false;
   if (dx_nchw || dw_oihw) {
-    const size_t smem = (size_t)32 * (ws.NP + 2) * 2;
-    if (smem > 48 * 1024)
-      ASN_CUDA(cudaFuncSetAttribute(aspp_dycols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof::Scope ps("aspp_dy_cols", 0, 2.0 * N * P * ws.NP + 4.0 * N * P * n_cls, st);
-    aspp_dycols_kernel<<<N * cdiv(P, 32), 256, smem, st>>>(dy_nchw, dycol, N, H, W, n_cls, ws.NP, taps);
+    if (glue_v2() && (reinterpret_cast<uintptr_t>(dycol) & 31) == 0) {
+      // the bias gradient rides along as n_cls extra CTAs of the same launch
+      const int main_blocks = cdiv((int64_t)N * cdiv(P, 32) * (ws.NP / 16), 8);
+      const int extra = db ? n_cls : 0;
+      aspp_dycols_chunk_kernel<<<main_blocks + extra, 256, 0, st>>>(dy_nchw, dycol, db, N, H, W, n_cls, ws.NP, extra, taps);
+      db_done = db != nullptr;
+    } else {
+      const size_t smem = (size_t)32 * (ws.NP + 2) * 2;
+      if (smem > 48 * 1024)
+        ASN_CUDA(cudaFuncSetAttribute(aspp_dycols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      aspp_dycols_kernel<<<N * cdiv(P, 32), 256, smem, st>>>(dy_nchw, dycol, N, H, W, n_cls, ws.NP, taps);
+    }
     ASN_LAUNCH_CHECK();
   }
   if (dx_nchw && dx_channels_last) {
@@ -485,11 +649,14 @@ extern "C" int asn_aspp_bwd(const void* x_bf16, int dx_channels_last, const void
     GradPtrs gp{};
     for (int b = 0; b < n_active; ++b) gp.w[b] = dw_oihw[b];
     prof::Scope ps("aspp_unpack_dw", 0, 4.0 * Cin * ws.NP * (ws.S + 1), st);
-    aspp_unpack_dw_kernel<<<cdiv(Cin, UDW_CI), 256, (size_t)UDW_CI * ws.NP * sizeof(float), st>>>(
-        part, ws.S, gp, n_active, n_cls, Cin, ws.NP);
+    if (glue_v2() && (reinterpret_cast<uintptr_t>(part) & 15) == 0)
+      aspp_unpack_dw_row_kernel<<<Cin, 192, (size_t)ws.NP * sizeof(float), st>>>(part, ws.S, gp, n_active, n_cls, Cin, ws.NP);
+    else
+      aspp_unpack_dw_kernel<<<cdiv(Cin, UDW_CI), 256, (size_t)UDW_CI * ws.NP * sizeof(float), st>>>(
+          part, ws.S, gp, n_active, n_cls, Cin, ws.NP);
     ASN_LAUNCH_CHECK();
   }
-  if (db) {
+  if (db && !db_done) {
     rc = channel_sum_nchw(dy_nchw, db, N, n_cls, P, st);
     if (rc) return rc;
   }

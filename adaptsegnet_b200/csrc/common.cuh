@@ -99,6 +99,34 @@ __device__ __forceinline__ long long warp_sum(long long v) {
   return v;
 }
 
+// out[o] = sum_{n,p} src[n][o][p] by ONE CTA of 256 threads (fp64 accumulation, fixed order -> deterministic)
+__device__ __forceinline__ void block_channel_sum(const float* __restrict__ src, float* __restrict__ out, int N, int O,
+                                                  int P, int o) {
+  __shared__ double cs_part[8];
+  double acc = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const float* s = src + ((int64_t)n * O + o) * P;
+    if ((P & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+      // 16-byte loads, eight in flight per thread; four fp32 values folded pairwise into the double accumulator per load
+#pragma unroll 8
+      for (int i = threadIdx.x; i < P / 4; i += 256) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+        acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < P; i += 256) acc += (double)s[i];
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) cs_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? cs_part[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[o] = (float)v;
+  }
+}
+
 // streaming 128-bit accesses (read-once / write-once tensors)
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 r;

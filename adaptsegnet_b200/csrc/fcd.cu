@@ -364,6 +364,121 @@ __global__ void __launch_bounds__(256) fcd_pack_all_kernel(const PackArgs a) {
   }
 }
 
+// Round-2 form of the pack: a flat block table (no empty CTAs) and 16-byte accesses on both sides for conv2..conv4.
+// A CTA owns the same (32 output channels x 16 input channels) block: its 8192 fp32 weights arrive as eight independent
+// float4 loads per thread, and leave as 16-byte stores -- 8 consecutive input channels of one (co, tap) of Wf, 8 consecutive
+// output channels of one (parity class, tap, ci) of Wd -- gathered from shared memory (pitch 260 floats: the gathers of a
+// warp hit 32 different banks).  conv1 (19 -> 32 padded channels, 64 x 19 x 16 weights) and the classifier keep the scalar code.
+constexpr int PK_PITCH = PK_CI * 16 + 4;
+struct PackTable {
+  int seg_end[5];   // conv1..conv4 blocks, classifier blocks
+};
+__global__ void __launch_bounds__(256) fcd_pack_vec_kernel(const PackArgs a, const PackTable tb) {
+  int li = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) li += (int)blockIdx.x >= tb.seg_end[i] ? 1 : 0;
+  int blk = blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) blk = (li == i + 1) ? (int)blockIdx.x - tb.seg_end[i] : blk;
+  if (li == 4) {  // classifier weights [1][C][4][4] -> fp32 [16][C]
+    const int i = blk * 256 + threadIdx.x;
+    if (i < 16 * a.C4) {
+      const int t = i / a.C4, c = i % a.C4;
+      a.wc[i] = __ldg(a.w[4] + (int64_t)c * 16 + t);
+    }
+    if (blk == 0 && threadIdx.x == 0) a.bc[0] = __ldg(a.b[4]);
+    return;
+  }
+  const int l = li + 1;
+  const float* __restrict__ w = a.w[li];
+  __nv_bfloat16* __restrict__ wf = a.wf[li];
+  __nv_bfloat16* __restrict__ wd = a.wd[li];
+  const int Cout = a.Cout[li], Cin_real = a.Cin_real[li], Cin_rows = a.Cin_rows[li];
+  const int ci_blocks = (Cin_rows + PK_CI - 1) / PK_CI;
+  const int co0 = (blk / ci_blocks) * PK_CO, ci0 = (blk % ci_blocks) * PK_CI;
+  __shared__ float t[PK_CO][PK_PITCH];  // [co][ci * 16 + kh * 4 + kw]
+  if (blk % ci_blocks == 0 && threadIdx.x < PK_CO) a.bias[li][co0 + threadIdx.x] = __ldg(a.b[li] + co0 + threadIdx.x);
+  if (l == 1) {   // scalar path (padded channels: 0)
+    for (int e = threadIdx.x; e < PK_CO * PK_CI * 16; e += 256) {
+      const int col = e % (PK_CI * 16), co = e / (PK_CI * 16);
+      const int ci = ci0 + col / 16;
+      t[co][col] = ci < Cin_real ? __ldg(w + ((int64_t)(co0 + co) * Cin_real + ci0) * 16 + col) : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < PK_CO * 16 * PK_CI; e += 256) {
+      const int cil = e % PK_CI, tap = (e / PK_CI) % 16, co = e / (PK_CI * 16);
+      const int kh = tap >> 2, kw = tap & 3;
+      const int ci = ci0 + cil;
+      if (ci >= Cin_rows) continue;
+      wf[(int64_t)(co0 + co) * 512 + (kh * 2 + (kw >> 1)) * 64 + (kw & 1) * 32 + ci] = __float2bfloat16(t[co][cil * 16 + tap]);
+    }
+    const int Kd1 = 4 * Cout;
+    for (int e = threadIdx.x; e < 16 * PK_CI * PK_CO; e += 256) {
+      const int col = e % PK_CO, cil = (e / PK_CO) % PK_CI, zt = e / (PK_CO * PK_CI);
+      const int z = zt >> 2, tt = zt & 3;
+      const int rh = z >> 1, rw = z & 1, th = tt >> 1, tw = tt & 1;
+      const int kh = rh == 0 ? (th == 0 ? 1 : 3) : (th == 0 ? 0 : 2);
+      const int kw = rw == 0 ? (tw == 0 ? 1 : 3) : (tw == 0 ? 0 : 2);
+      const int ci = ci0 + cil;
+      if (ci >= Cin_rows) continue;
+      wd[((int64_t)z * Cin_rows + ci) * Kd1 + tt * Cout + co0 + col] = __float2bfloat16(t[col][cil * 16 + kh * 4 + kw]);
+    }
+    return;
+  }
+  // conv2..conv4: Cin_real == Cin_rows, a multiple of 16; every block is full
+  {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e4 = threadIdx.x + 256 * k;                 // float4 index in the [32][256] block
+      const int co = e4 >> 6, col = (e4 & 63) * 4;
+      v[k] = ld_stream(reinterpret_cast<const float4*>(w + ((int64_t)(co0 + co) * Cin_real + ci0) * 16 + col));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e4 = threadIdx.x + 256 * k;
+      const int co = e4 >> 6, col = (e4 & 63) * 4;
+      *reinterpret_cast<float4*>(&t[co][col]) = v[k];
+    }
+  }
+  __syncthreads();
+  auto pack8 = [](const float (&f)[8]) {
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      r[i] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
+  };
+  // forward pack Wf[co][tap * Cin + ci]: thread = (co, tap, half of the 16 input channels)
+  const int Kf = 16 * Cin_real;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = threadIdx.x + 256 * k;
+    const int half = e & 1, tap = (e >> 1) & 15, co = e >> 5;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = t[co][(half * 8 + i) * 16 + tap];
+    *reinterpret_cast<uint4*>(wf + (int64_t)(co0 + co) * Kf + tap * Cin_real + ci0 + half * 8) = pack8(f);
+  }
+  // dgrad pack Wd[z = (rh,rw)][ci][(th*2 + tw)*Cout + co]: thread = (kh*4+kw, ci, 8 output channels)
+  const int Kd = 4 * Cout;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = threadIdx.x + 256 * k;
+    const int khkw = e & 15, cil = (e >> 4) & 15, g = e >> 8;
+    const int kh = khkw >> 2, kw = khkw & 3;
+    // kh = 1,3 belong to row parity rh = 0 (th = 0,1); kh = 0,2 to rh = 1 (th = 0,1); the same for kw
+    const int rh = (kh & 1) ? 0 : 1, th = kh >> 1, rw = (kw & 1) ? 0 : 1, tw = kw >> 1;
+    const int z = rh * 2 + rw, tt = th * 2 + tw;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = t[g * 8 + i][cil * 16 + khkw];
+    *reinterpret_cast<uint4*>(wd + ((int64_t)z * Cin_rows + ci0 + cil) * Kd + tt * Cout + co0 + g * 8) = pack8(f);
+  }
+}
+
 // ---- classifier (N = 1 output channel): CUDA-core reductions ------------------------------------
 // out[n][oh][ow] = bc + sum_{kh,kw,c} A4[n][2oh-1+kh][2ow-1+kw][c] * wc[kh*4+kw][c].
 // One 128-thread CTA per output pixel: warp = kernel row kh, lanes stride the channels with 16-byte loads.
@@ -461,25 +576,39 @@ fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __rest
 #pragma unroll
   for (int t = 0; t < 16; ++t) acc[t] = 0.f;
   if (c < C) {
-    for (int i = blockIdx.x * 4 + ph; i < n_in; i += 4 * CLS_SLICES) {
-      const int iw = i % W4, ih = (i / W4) % H4, n = i / (W4 * H4);
-      const float v = __bfloat162float(a4[(int64_t)i * C + c]);
-      // kh = ih + 1 (mod 2), kw = iw + 1 (mod 2)
-      if (ih & 1) {
-        if (iw & 1) {
-          cls_tap<0, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<0, 2>(acc, v, dout, n, ih, iw, H5, W5);
-          cls_tap<2, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<2, 2>(acc, v, dout, n, ih, iw, H5, W5);
+    // the activations of up to CLS_UNR pixels of this thread are loaded first (independent 2-byte loads, one DRAM round trip
+    // instead of one per pixel), then folded into the taps in pixel order
+    constexpr int CLS_UNR = 8;
+    for (int i0 = blockIdx.x * 4 + ph; i0 < n_in; i0 += 4 * CLS_SLICES * CLS_UNR) {
+      float vv[CLS_UNR];
+#pragma unroll
+      for (int u = 0; u < CLS_UNR; ++u) {
+        const int i = i0 + u * 4 * CLS_SLICES;
+        vv[u] = i < n_in ? __bfloat162float(a4[(int64_t)i * C + c]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < CLS_UNR; ++u) {
+        const int i = i0 + u * 4 * CLS_SLICES;
+        if (i >= n_in) break;
+        const int iw = i % W4, ih = (i / W4) % H4, n = i / (W4 * H4);
+        const float v = vv[u];
+        // kh = ih + 1 (mod 2), kw = iw + 1 (mod 2)
+        if (ih & 1) {
+          if (iw & 1) {
+            cls_tap<0, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<0, 2>(acc, v, dout, n, ih, iw, H5, W5);
+            cls_tap<2, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<2, 2>(acc, v, dout, n, ih, iw, H5, W5);
+          } else {
+            cls_tap<0, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<0, 3>(acc, v, dout, n, ih, iw, H5, W5);
+            cls_tap<2, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<2, 3>(acc, v, dout, n, ih, iw, H5, W5);
+          }
         } else {
-          cls_tap<0, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<0, 3>(acc, v, dout, n, ih, iw, H5, W5);
-          cls_tap<2, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<2, 3>(acc, v, dout, n, ih, iw, H5, W5);
-        }
-      } else {
-        if (iw & 1) {
-          cls_tap<1, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<1, 2>(acc, v, dout, n, ih, iw, H5, W5);
-          cls_tap<3, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<3, 2>(acc, v, dout, n, ih, iw, H5, W5);
-        } else {
-          cls_tap<1, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<1, 3>(acc, v, dout, n, ih, iw, H5, W5);
-          cls_tap<3, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<3, 3>(acc, v, dout, n, ih, iw, H5, W5);
+          if (iw & 1) {
+            cls_tap<1, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<1, 2>(acc, v, dout, n, ih, iw, H5, W5);
+            cls_tap<3, 0>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<3, 2>(acc, v, dout, n, ih, iw, H5, W5);
+          } else {
+            cls_tap<1, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<1, 3>(acc, v, dout, n, ih, iw, H5, W5);
+            cls_tap<3, 1>(acc, v, dout, n, ih, iw, H5, W5); cls_tap<3, 3>(acc, v, dout, n, ih, iw, H5, W5);
+          }
         }
       }
     }
@@ -493,6 +622,75 @@ fcd_cls_wgrad_kernel(const float* __restrict__ dout, const __nv_bfloat16* __rest
     if (blockIdx.y * 64 + ch < C)
       part[((int64_t)blockIdx.x * 16 + t) * C + blockIdx.y * 64 + ch] = red[0][t][ch] + red[1][t][ch] + red[2][t][ch] + red[3][t][ch];
   }
+}
+
+// Round-2 form: thread = (8 consecutive channels, ONE parity class of input pixels).  The four taps an input pixel feeds are a
+// function of its (row, column) parity alone, so a thread that only visits pixels of one class keeps 4 x 8 accumulators
+// (not 16 per channel), reads 16 bytes per pixel and amortises the index arithmetic over 8 channels (the per-channel form
+// above spends ~170 instructions per pixel and channel on it: instruction-bound at 21 us).  No shared memory: the thread
+// owns its (slice, 4 taps, 8 channels) outputs.  blockDim = C/8 groups x 4 classes; grid = CLS_SLICES.
+__global__ void __launch_bounds__(256)
+fcd_cls_wgrad_par_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a4, float* __restrict__ part,
+                         int N, int H4, int W4, int C, int H5, int W5) {
+  const int groups = C / 8;
+  const int g = threadIdx.x % groups, pc = threadIdx.x / groups;     // pc = (ih & 1) * 2 + (iw & 1)
+  const int pa = pc >> 1, pb = pc & 1;
+  const int nh = (H4 - pa + 1) / 2, nw = (W4 - pb + 1) / 2;           // pixels of this class: ih = 2*mh + pa, iw = 2*mw + pb
+  const int total = N * nh * nw;
+  float acc[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  constexpr int UNR = 8;
+  for (int q0 = blockIdx.x; q0 < total; q0 += CLS_SLICES * UNR) {
+    uint4 u[UNR];
+    int on[UNR], om[UNR], ow_[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int q = q0 + k * CLS_SLICES;
+      u[k] = make_uint4(0u, 0u, 0u, 0u);
+      on[k] = -1;
+      if (q < total) {
+        const int n = q / (nh * nw), rem = q - n * (nh * nw);
+        const int mh = rem / nw, mw = rem - mh * nw;
+        on[k] = n; om[k] = mh; ow_[k] = mw;
+        u[k] = __ldg(reinterpret_cast<const uint4*>(a4 + (((int64_t)n * H4 + 2 * mh + pa) * W4 + 2 * mw + pb) * C) + g);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      if (on[k] < 0) break;
+      float v[8];
+      const uint32_t pk[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+        v[2 * j] = __low2float(hh);
+        v[2 * j + 1] = __high2float(hh);
+      }
+      // tap (kh, kw) = (1 - pa + 2i, 1 - pb + 2j) sees this pixel from output (mh + pa - i, mw + pb - j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int oh = om[k] + pa - i, ow = ow_[k] + pb - j;
+          const bool ok = oh >= 0 && oh < H5 && ow >= 0 && ow < W5;
+          const float d = ok ? __ldg(dout + ((int64_t)on[k] * H5 + oh) * W5 + ow) : 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[i * 2 + j][e] = fmaf(d, v[e], acc[i * 2 + j][e]);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tap = (1 - pa + 2 * i) * 4 + (1 - pb + 2 * j);
+      float4* dst = reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 16 + tap) * C + g * 8);
+      dst[0] = make_float4(acc[i * 2 + j][0], acc[i * 2 + j][1], acc[i * 2 + j][2], acc[i * 2 + j][3]);
+      dst[1] = make_float4(acc[i * 2 + j][4], acc[i * 2 + j][5], acc[i * 2 + j][6], acc[i * 2 + j][7]);
+    }
 }
 
 // ---- reductions at the end of the backward: one launch each for the four conv layers (blockIdx.y = layer) ----
@@ -511,6 +709,13 @@ struct LayerReduce {
   const float* cls_part;
   float* cls_dw;
   int cls_C;
+  // classifier bias gradient: cls_db[0] = sum of dout (cls_n values); merged launch only
+  const float* cls_dout;
+  float* cls_db;
+  int cls_n;
+  // merged launch (fcd_reduce_tail_kernel): block ranges  [0..3] final bias sums of conv1..4, [4] classifier bias gradient,
+  // [5..8] weight gradient of conv1..4, [9] classifier weight gradient; seg_end[i] = first block past segment i
+  int seg_end[10];
 };
 
 // partial[cta][c] = sum of this CTA's row slice (fixed order -> deterministic).  Thread = 8 consecutive channels (one 16-byte
@@ -616,6 +821,90 @@ __global__ void __launch_bounds__(256) fcd_wgrad_reduce_kernel(LayerReduce R) {
   __syncthreads();
   if (l == 0) {
     // conv1: a k-step holds two horizontally adjacent taps x 32 (padded) channels: tap = kh*2 + kw/2, col = (kw%2)*32 + ci
+    for (int e = threadIdx.x; e < Cin_real * 16; e += 256) {
+      const int ci = e >> 4, kh = (e >> 2) & 3, kw = e & 3;
+      R.dw[l][((long long)co * Cin_real + ci) * 16 + (e & 15)] = t[kh * 2 + (kw >> 1)][(kw & 1) * 32 + ci];
+    }
+  } else {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int cl = e >> 4, k = e & 15;
+      const int ci = chunk * 64 + cl;
+      if (ci < Cin_real) R.dw[l][((long long)co * Cin_real + ci) * 16 + k] = t[k][cl];
+    }
+  }
+}
+
+// Round-2 tail of the backward pass: ONE launch with a flat block table (no empty CTAs) that (a) sums the split-K partials of
+// the four weight gradients with 16-byte loads -- a CTA owns (co, 64 columns): thread = (tap, four columns), all S splits of
+// its float4 in flight at once, summed in split order, transposed through shared memory into one contiguous 4 KB run of dW --
+// (b) sums the classifier's slices, (c) finishes the four bias gradients from their per-CTA partials and (d) sums dout for the
+// classifier's bias gradient.  Same summation orders as the separate kernels above (bit-identical results).
+__global__ void __launch_bounds__(256) fcd_reduce_tail_kernel(const LayerReduce R) {
+  int seg = 0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) seg += (int)blockIdx.x >= R.seg_end[i] ? 1 : 0;
+  int blk = blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) blk = (seg == i + 1) ? (int)blockIdx.x - R.seg_end[i] : blk;
+  // the short latency-bound segments come first so that they run beside the bandwidth-bound ones instead of after them
+  if (seg == 4) {
+    block_channel_sum(R.cls_dout, R.cls_db, 1, 1, R.cls_n, 0);
+    return;
+  }
+  if (seg < 4) {                       // bias gradient of conv layer l: 32 channels per CTA, 8 warps split the partial rows
+    __shared__ float red[8][32];
+    const int l = seg;
+    const int C = R.C[l], rows = R.ctas[l];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blk * 32 + lane;
+    float acc = 0.f;
+    if (c < C) {
+#pragma unroll 8
+      for (int r = warp; r < rows; r += 8) acc += R.db_partial[l][(long long)r * C + c];
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][lane];
+      R.db[l][c] = t;
+    }
+    return;
+  }
+  if (seg == 9) {                      // classifier: thread = (tap, channel), slices summed in order
+    const int i = blk * 256 + threadIdx.x;
+    if (i >= 16 * R.cls_C) return;
+    const int t = i / R.cls_C, c = i - t * R.cls_C;
+    float acc = 0.f;
+#pragma unroll 16
+    for (int s = 0; s < CLS_SLICES; ++s) acc += __ldg(R.cls_part + (int64_t)s * 16 * R.cls_C + i);
+    R.cls_dw[(int64_t)c * 16 + t] = acc;
+    return;
+  }
+  const int l = seg - 5;               // 0..3 <-> conv1..conv4
+  const int Cout = R.Cout[l], Cin_real = R.Cin_real[l], Ncols = R.Ncols[l], S = R.S[l];
+  const int taps = l == 0 ? 8 : 16;
+  const int chunks = (Ncols + 63) / 64;
+  const int co = blk / chunks, chunk = blk - co * chunks;
+  __shared__ float t[16][65];
+  if ((int)threadIdx.x < taps * 16) {
+    const int tap = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
+    const int col = chunk * 64 + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < Ncols) {                 // Ncols is a multiple of 4 (64 .. 256)
+      const float4* src = reinterpret_cast<const float4*>(R.part[l] + ((long long)tap * Cout + co) * Ncols + col);
+      const long long zs4 = (long long)taps * Cout * Ncols / 4;  // float4s between split-K partials
+#pragma unroll 8
+      for (int s = 0; s < S; ++s) {
+        const float4 v = ld_stream(src + s * zs4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    t[tap][c4] = acc.x; t[tap][c4 + 1] = acc.y; t[tap][c4 + 2] = acc.z; t[tap][c4 + 3] = acc.w;
+  }
+  __syncthreads();
+  if (l == 0) {
     for (int e = threadIdx.x; e < Cin_real * 16; e += 256) {
       const int ci = e >> 4, kh = (e >> 2) & 3, kw = e & 3;
       R.dw[l][((long long)co * Cin_real + ci) * 16 + (e & 15)] = t[kh * 2 + (kw >> 1)][(kw & 1) * 32 + ci];
@@ -969,6 +1258,20 @@ static int reduce_all(const FcdPlan& p, LayerReduce& R, cudaStream_t st) {
     fcd_colsum_partial_kernel<<<dim3(max_ctas, 4), 256, 0, st>>>(R);
     ASN_LAUNCH_CHECK();
   }
+  static const bool merged = !(getenv("ASN_GLUE") != nullptr && getenv("ASN_GLUE")[0] == '0');
+  bool aligned = true;
+  for (int i = 0; i < 4; ++i) aligned = aligned && (reinterpret_cast<uintptr_t>(R.part[i]) & 15) == 0 && R.Ncols[i] % 4 == 0;
+  if (merged && aligned) {
+    int end = 0;
+    for (int i = 0; i < 4; ++i) { end += cdiv(R.C[i], 32); R.seg_end[i] = end; }
+    end += R.cls_dout ? 1 : 0; R.seg_end[4] = end;
+    for (int i = 0; i < 4; ++i) { end += R.Cout[i] * cdiv(R.Ncols[i], 64); R.seg_end[5 + i] = end; }
+    end += R.cls_part ? cdiv(16 * R.cls_C, 256) : 0; R.seg_end[9] = end;
+    prof::Scope ps("fcd_wgrad_reduce", 0, dw_bytes, st);
+    fcd_reduce_tail_kernel<<<end, 256, 0, st>>>(R);
+    ASN_LAUNCH_CHECK();
+    return ASN_OK;
+  }
   {
     prof::Scope ps("fcd_bias_grad_final", 0, 0, st);
     fcd_colsum_final_kernel<<<dim3(cdiv(max_c, 32), 4), 256, 0, st>>>(R);
@@ -982,6 +1285,7 @@ static int reduce_all(const FcdPlan& p, LayerReduce& R, cudaStream_t st) {
     fcd_wgrad_reduce_kernel<<<dim3((unsigned)blocks, R.cls_part ? 5 : 4), 256, 0, st>>>(R);
     ASN_LAUNCH_CHECK();
   }
+  if (R.cls_dout) return channel_sum_nchw(R.cls_dout, R.cls_db, 1, 1, R.cls_n, st);
   return ASN_OK;
 }
 
@@ -1058,7 +1362,20 @@ extern "C" int asn_fcd_pack_weights(const float* const* params_host, int n_cls, 
   (void)max_total;
   int blocks = 1;
   for (int i = 0; i < 4; ++i) blocks = max(blocks, (a.Cout[i] / PK_CO) * cdiv(a.Cin_rows[i], PK_CI));
-  fcd_pack_all_kernel<<<dim3((unsigned)blocks, 5), 256, 0, st>>>(a);
+  static const bool vec = !(getenv("ASN_GLUE") != nullptr && getenv("ASN_GLUE")[0] == '0');
+  bool ok = vec;
+  for (int i = 1; i < 4; ++i)   // conv2..4: whole 16-channel blocks, 16-byte aligned rows
+    ok = ok && a.Cin_real[i] == a.Cin_rows[i] && a.Cin_rows[i] % PK_CI == 0 && a.Cout[i] % PK_CO == 0 &&
+         ((reinterpret_cast<uintptr_t>(a.w[i]) | reinterpret_cast<uintptr_t>(a.wf[i]) | reinterpret_cast<uintptr_t>(a.wd[i])) & 15) == 0;
+  if (ok) {
+    PackTable tb;
+    int end = 0;
+    for (int i = 0; i < 4; ++i) { end += (a.Cout[i] / PK_CO) * cdiv(a.Cin_rows[i], PK_CI); tb.seg_end[i] = end; }
+    end += cdiv(16 * a.C4, 256); tb.seg_end[4] = end;
+    fcd_pack_vec_kernel<<<end, 256, 0, st>>>(a, tb);
+  } else {
+    fcd_pack_all_kernel<<<dim3((unsigned)blocks, 5), 256, 0, st>>>(a);
+  }
   ASN_LAUNCH_CHECK();
   return ASN_OK;
 }
@@ -1164,14 +1481,21 @@ static int fcd_bwd_impl(const float* dout, const float* x_logits, int x_h, int x
     {
       prof::Scope ps("fcd_classifier_wgrad", 2.0 * N * p.H[5] * p.W[5] * 16 * p.C[4], 0, st);
       float* clspart = reinterpret_cast<float*>(ws + p.clspart_off);
-      fcd_cls_wgrad_kernel<<<dim3(CLS_SLICES, cdiv(p.C[4], 64)), 256, 0, st>>>(dout, A[4], clspart, N, p.H[4], p.W[4],
-                                                                                   p.C[4], p.H[5], p.W[5]);
+      static const bool par = !(getenv("ASN_GLUE") != nullptr && getenv("ASN_GLUE")[0] == '0');
+      if (par && p.C[4] % 8 == 0 && p.C[4] / 2 <= 256 && (reinterpret_cast<uintptr_t>(clspart) & 15) == 0)
+        fcd_cls_wgrad_par_kernel<<<CLS_SLICES, p.C[4] / 2, 0, st>>>(dout, A[4], clspart, N, p.H[4], p.W[4], p.C[4], p.H[5],
+                                                                    p.W[5]);
+      else
+        fcd_cls_wgrad_kernel<<<dim3(CLS_SLICES, cdiv(p.C[4], 64)), 256, 0, st>>>(dout, A[4], clspart, N, p.H[4], p.W[4],
+                                                                                     p.C[4], p.H[5], p.W[5]);
       ASN_LAUNCH_CHECK();
       R.cls_part = clspart;          // summed over the slices by the merged reduce at the end of the backward
       R.cls_dw = dparams_host[8];
       R.cls_C = p.C[4];
     }
-    if ((rc = channel_sum_nchw(dout, dparams_host[9], N, 1, p.H[5] * p.W[5], st))) return rc;
+    R.cls_dout = dout;               // db = sum(dout): part of the merged tail launch
+    R.cls_db = dparams_host[9];
+    R.cls_n = N * p.H[5] * p.W[5];
   }
   for (int l = 4; l >= 1; --l) {
     if (dparams_host) {

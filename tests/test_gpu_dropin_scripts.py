@@ -64,10 +64,15 @@ def test_train_script_multi_level_runs_unchanged(tmp_path, lazy):
     if lazy == "1":
         test_train_script_multi_level_runs_unchanged.lazy_lines = lines
     elif hasattr(test_train_script_multi_level_runs_unchanged, "lazy_lines"):
-        # Tier-B handles and materialised tensors print the same losses (to 2e-3: different kernels, same mathematics)
+        # Tier-B handles and materialised tensors print the same losses.  The two runs are two PROCESSES of a script that
+        # sets cudnn.benchmark = True (train...:228): cuDNN's autotuner may pick different TF32 algorithms for the trunk in
+        # each, and the random-init trunk (segmentation loss ~9, logits of order 10) amplifies that to a few 1e-3 relative --
+        # measured 5.5e-3 once in four runs on the pool's boxes, while libasn_b200 itself is bitwise run-to-run
+        # deterministic (tools/determinism_check.py).  Hence 2e-2 here; the lazy-vs-materialised equality of the library's
+        # own kernels is gated in-process, bit for bit, by tests/test_gpu_lazy.py.
         a = re.findall(r"= ([0-9.]+)", test_train_script_multi_level_runs_unchanged.lazy_lines[0].split(",", 1)[1])
         b = re.findall(r"= ([0-9.]+)", lines[0].split(",", 1)[1])
-        assert np.allclose([float(x) for x in a], [float(x) for x in b], rtol=2e-3, atol=2e-3)
+        assert np.allclose([float(x) for x in a], [float(x) for x in b], rtol=2e-2, atol=2e-3)
 
 
 def test_evaluate_script_runs_unchanged(tmp_path):
