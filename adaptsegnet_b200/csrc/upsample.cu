@@ -125,13 +125,18 @@ upsample_bwd_w_kernel(const float* __restrict__ dy, float* __restrict__ T, int n
 // by the magnification hit distinct banks.  Per output: <= UPB_MAXT x (LDS + FMA).
 constexpr int UPB_MAXT = 24;
 __device__ __forceinline__ int skew(int X) { return X + (X >> 5); }
-__global__ void __launch_bounds__(1024)
+// BOUND = 256 (w <= 256, every training shape): registers to spare, so the skewed offsets of the candidate columns are
+// computed once per thread and a tap is LDS + FFMA; BOUND = 1024: 64 registers, the offsets are recomputed per tap.
+template <int BOUND>
+__global__ void __launch_bounds__(BOUND)
 upsample_bwd_w_fast_kernel(const float* __restrict__ dy, float* __restrict__ T, int n_rows, int w, int W,
                            float sw, int vec_ok) {
+  constexpr bool OFFS = BOUND <= 256;
   extern __shared__ float rows_sh[];  // [UPB_ROWS][skew(W) + 1]
   const int pitch = skew(W) + 1;
   const int j = threadIdx.x;
   float wgt[UPB_MAXT];
+  int off[OFFS ? UPB_MAXT : 1];   // skewed shared-memory offset of candidate column k
   int lo = 0;
   if (j < w) {
     const float inv = 1.f / sw;
@@ -146,6 +151,7 @@ upsample_bwd_w_fast_kernel(const float* __restrict__ dy, float* __restrict__ T, 
         f = (lx.i0 == j ? lx.l0 : 0.f) + (lx.i1 == j ? lx.l1 : 0.f);
       }
       wgt[k] = f;
+      if (OFFS) off[k] = skew(min(X, W - 1));
     }
   }
   for (int row0 = blockIdx.x * UPB_ROWS; row0 < n_rows; row0 += gridDim.x * UPB_ROWS) {
@@ -183,7 +189,7 @@ upsample_bwd_w_fast_kernel(const float* __restrict__ dy, float* __restrict__ T, 
         const float* row = rows_sh + rl * pitch;
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < UPB_MAXT; ++k) acc = fmaf(wgt[k], row[skew(min(lo + k, W - 1))], acc);
+        for (int k = 0; k < UPB_MAXT; ++k) acc = fmaf(wgt[k], row[OFFS ? off[k] : skew(min(lo + k, W - 1))], acc);
         T[(int64_t)(row0 + rl) * w + j] = acc;
       }
     }
@@ -439,9 +445,15 @@ extern "C" int asn_upsample_bilinear_bwd(const float* dy, int N, int C, int H, i
     const bool fast = sw > 0.f && w <= 1024 && (int)ceilf(2.f / sw) + 7 <= UPB_MAXT;
     if (fast) {
       const size_t smem_f = (size_t)UPB_ROWS * (W + (W >> 5) + 1) * 4;
-      if (smem_f > 48 * 1024)
-        ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-      upsample_bwd_w_fast_kernel<<<grid_w, (unsigned)round_up(w, 32), smem_f, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
+      if (w <= 256) {
+        if (smem_f > 48 * 1024)
+          ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_fast_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        upsample_bwd_w_fast_kernel<256><<<grid_w, (unsigned)round_up(w, 32), smem_f, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
+      } else {
+        if (smem_f > 48 * 1024)
+          ASN_CUDA(cudaFuncSetAttribute(upsample_bwd_w_fast_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        upsample_bwd_w_fast_kernel<1024><<<grid_w, (unsigned)round_up(w, 32), smem_f, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
+      }
     } else {
       upsample_bwd_w_kernel<<<grid_w, UP_THREADS, smem, st>>>(dy, T, n_rows, w, W, sw, vec_ok);
     }

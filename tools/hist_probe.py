@@ -1,0 +1,71 @@
+"""A/B of asn_fast_hist on one box with one method: the library's kernel against the round-1 form (tools/probes/hist_round1.cu,
+built here into tools/probes/libhist_round1.so).  50 frames of 1024x2048 per launch; i.i.d. and segmentation-like (blocky)
+maps; u8 and i64 labels; CUDA events around each launch; L2 evicted by READING 512 MB before every launch.
+  python tools/hist_probe.py [--build-only]"""
+import ctypes as C
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OLD = os.path.join(ROOT, "tools", "probes", "libhist_round1.so")
+CSRC = os.path.join(ROOT, "adaptsegnet_b200", "csrc")
+if not os.path.exists(OLD) or "--build-only" in sys.argv:
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                    "-I", CSRC, "-DASN_BUILD_ID=\"probe\"", "-o", OLD, os.path.join(ROOT, "tools", "probes", "hist_round1.cu"),
+                    os.path.join(CSRC, "capi.cu")], check=True)
+if "--build-only" in sys.argv:
+    sys.exit(0)
+import torch
+from adaptsegnet_b200 import _lib
+
+dev = "cuda"
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+copy_gbs = float(peaks.get("hbm_gbs", 6557.1))
+libs = {"round2": _lib.load(), "round1": C.CDLL(OLD)}
+sig = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+for l in libs.values():
+    l.asn_fast_hist.argtypes = sig
+    l.asn_fast_hist.restype = C.c_int
+flush = torch.ones(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+torch.manual_seed(0)
+F, H, W = 50, 1024, 2048
+n_px = F * H * W
+iid = torch.randint(0, 19, (n_px,), device=dev)
+iid[torch.rand(n_px, device=dev) < 0.1] = 255
+pred_iid = torch.randint(0, 19, (n_px,), device=dev, dtype=torch.uint8)
+lab = torch.randint(0, 19, (F, H // 16, W // 16), device=dev).repeat_interleave(16, 1).repeat_interleave(16, 2).contiguous()
+lab[:, :100] = 255
+agree = (torch.rand(F, H // 8, W // 8, device=dev) < 0.85).repeat_interleave(8, 1).repeat_interleave(8, 2)
+other = torch.randint(0, 19, (F, H // 8, W // 8), device=dev, dtype=torch.uint8).repeat_interleave(8, 1).repeat_interleave(8, 2)
+pred_blk = torch.where(agree, (lab % 19).to(torch.uint8), other).reshape(-1).contiguous()
+del agree, other
+cases = {"iid": (iid, pred_iid), "blocky": (lab.reshape(-1), pred_blk)}
+DT = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}
+res = {}
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for cname, (l64, p) in cases.items():
+    for dt in (torch.uint8, torch.int64):
+        l = l64.to(dt).contiguous()
+        ref = None
+        for lname, lib in libs.items():
+            hist = torch.zeros(19 * 19, dtype=torch.int64, device=dev)
+            ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+            ts = []
+            for rep in range(7):
+                hist.zero_()
+                flush.sum()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = lib.asn_fast_hist(l.data_ptr(), DT[dt], p.data_ptr(), n_px, 19, hist.data_ptr(), ovf.data_ptr(), st)
+                e1.record()
+                torch.cuda.synchronize()
+                assert rc == 0
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            us = ts[len(ts) // 2] * 1e3
+            gbs = n_px * (l.element_size() + 1) / (us * 1e-6) / 1e9
+            if ref is None:
+                ref = hist.clone()
+            same = bool(torch.equal(ref, hist))
+            res[f"{cname}_{str(dt).split('.')[-1]}_{lname}"] = {"us": round(us, 1), "GBps": round(gbs, 1), "frac_of_copy": round(gbs / copy_gbs, 3),
+                                                             "identical_counts": same}
+print(json.dumps(res, indent=1))

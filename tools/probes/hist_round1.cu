@@ -1,11 +1,12 @@
+// PROBE ONLY: the fast_hist kernel as it was before the group-uniform rewrite, built into tools/probes/libhist_round1.so by
+// tools/hist_probe.py for a same-box, same-method A/B.  Not part of the library.
 // K7: 19x19 confusion matrix (compute_iou.py:15-17) -- HBM-bound integer kernel.
 //
 // Layout: label (u8 | i32 | i64) and pred (u8) are flat arrays of n_px pixels.
 // Each thread streams 16 consecutive pixels per iteration with 128-bit loads
-// (1 load of pred, 1/4/8 loads of labels).  Groups of four identical (a,b) pairs
-// -- recognised on the raw words -- extend a run kept in registers (labels are
-// blocky, so most shared-memory atomics vanish); mixed groups add pixel by pixel
-// into a warp-private shared-memory histogram.  One 64-bit global
+// (1 load of pred, 1/4/8 loads of labels), run-length-aggregates equal (a,b)
+// pairs in registers (labels are blocky, so most shared-memory atomics vanish),
+// and adds into a warp-private shared-memory histogram.  One 64-bit global
 // atomic per non-zero bin per CTA at the end.  Algorithmic bytes: 2 B/px (u8
 // labels) or 9 B/px (i64 labels, as the reference holds them).
 // Optional 256-entry LUT applied to the labels on the way in: compute_iou.py:24-28 (label_mapping, one full pass over
@@ -17,23 +18,20 @@ namespace asn {
 constexpr int HIST_THREADS = 256;
 constexpr int HIST_WARPS = HIST_THREADS / 32;
 
-// A chunk of 16 consecutive labels as loaded (raw words), decoded lazily: class index or -1 for anything outside [0, n).
-// uniform4(g): the four labels of group g (pixels 4g .. 4g+3) are bit-identical -- decided on the raw words.
 template <typename T>
-struct RawLabels;
+struct LabelLoad;  // loads 16 consecutive labels as int (-1 = invalid for any out-of-range)
 
 template <>
-struct RawLabels<uint8_t> {
-  uint32_t w[4];
-  __device__ __forceinline__ void load(const uint8_t* p) {
-    const uint4 v = ld_stream(reinterpret_cast<const uint4*>(p));
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-  }
-  __device__ __forceinline__ bool uniform4(int g) const { return w[g] == (w[g] & 0xffu) * 0x01010101u; }
-  __device__ __forceinline__ int decode(int i, int n, const uint8_t* lut) const {
-    int x = (w[i >> 2] >> ((i & 3) * 8)) & 0xff;
-    if (lut) x = lut[x];
-    return x < n ? x : -1;
+struct LabelLoad<uint8_t> {
+  static __device__ __forceinline__ void load16(const uint8_t* p, int n, int* a, const uint8_t* lut) {
+    uint4 v = ld_stream(reinterpret_cast<const uint4*>(p));
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int x = (w[i >> 2] >> ((i & 3) * 8)) & 0xff;
+      if (lut) x = lut[x];
+      a[i] = x < n ? x : -1;
+    }
   }
   static __device__ __forceinline__ int load1(const uint8_t* p, int n, const uint8_t* lut) {
     int x = *p;
@@ -42,67 +40,58 @@ struct RawLabels<uint8_t> {
   }
 };
 template <>
-struct RawLabels<int32_t> {
-  uint32_t w[16];
+struct LabelLoad<int32_t> {
   // labels outside [0, 256) are not in the LUT: label_mapping leaves them unchanged (and they are invalid anyway)
   static __device__ __forceinline__ int map1(uint32_t x, int n, const uint8_t* lut) {
     if (lut && x < 256u) x = lut[x];
     return x < (uint32_t)n ? (int)x : -1;
   }
-  __device__ __forceinline__ void load(const int32_t* p) {
+  static __device__ __forceinline__ void load16(const int32_t* p, int n, int* a, const uint8_t* lut) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
-      w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+      uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[j * 4 + i] = map1(w[i], n, lut);
     }
   }
-  __device__ __forceinline__ bool uniform4(int g) const {
-    return w[4 * g] == w[4 * g + 1] && w[4 * g + 2] == w[4 * g + 3] && w[4 * g] == w[4 * g + 2];
-  }
-  __device__ __forceinline__ int decode(int i, int n, const uint8_t* lut) const { return map1(w[i], n, lut); }
   static __device__ __forceinline__ int load1(const int32_t* p, int n, const uint8_t* lut) {
     return map1((uint32_t)*p, n, lut);
   }
 };
 template <>
-struct RawLabels<int64_t> {
-  uint32_t lo[16], hi[16];
-  static __device__ __forceinline__ int map1(uint32_t l, uint32_t h, int n, const uint8_t* lut) {
-    if (h != 0u) return -1;  // negative or >= 2^32: never valid, never in the LUT
-    if (lut && l < 256u) l = lut[l];
-    return l < (uint32_t)n ? (int)l : -1;
+struct LabelLoad<int64_t> {
+  static __device__ __forceinline__ int map1(uint32_t lo, uint32_t hi, int n, const uint8_t* lut) {
+    if (hi != 0u) return -1;  // negative or >= 2^32: never valid, never in the LUT
+    if (lut && lo < 256u) lo = lut[lo];
+    return lo < (uint32_t)n ? (int)lo : -1;
   }
-  __device__ __forceinline__ void load(const int64_t* p) {
+  static __device__ __forceinline__ void load16(const int64_t* p, int n, int* a, const uint8_t* lut) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      // little endian: (x,y) = first int64, (z,w) = second
-      const uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
-      lo[2 * j] = v.x; hi[2 * j] = v.y; lo[2 * j + 1] = v.z; hi[2 * j + 1] = v.w;
+      uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
+      // little endian: (x,y) = first int64, (z,w) = second; valid iff high word 0 and (mapped) low word < n
+      a[j * 2 + 0] = map1(v.x, v.y, n, lut);
+      a[j * 2 + 1] = map1(v.z, v.w, n, lut);
     }
   }
-  __device__ __forceinline__ bool uniform4(int g) const {
-    return lo[4 * g] == lo[4 * g + 1] && lo[4 * g + 2] == lo[4 * g + 3] && lo[4 * g] == lo[4 * g + 2] &&
-           (hi[4 * g] | hi[4 * g + 1] | hi[4 * g + 2] | hi[4 * g + 3]) == 0u;   // (a non-zero high word: slow path, all invalid)
-  }
-  __device__ __forceinline__ int decode(int i, int n, const uint8_t* lut) const { return map1(lo[i], hi[i], n, lut); }
   static __device__ __forceinline__ int load1(const int64_t* p, int n, const uint8_t* lut) {
     const unsigned long long x = (unsigned long long)*p;
     return map1((uint32_t)x, (uint32_t)(x >> 32), n, lut);
   }
 };
 
-// run-length aggregation in registers: equal flat indices that follow each other cost one compare and one add
 struct RunAgg {
   int cur;
   uint32_t cnt;
   uint32_t ovf;
-  __device__ __forceinline__ void push(int idx, uint32_t k, uint32_t* h, int nbins) {
+  __device__ __forceinline__ void push(int idx, uint32_t* h, int nbins) {
     if (idx == cur) {
-      cnt += k;
+      ++cnt;
     } else {
       flush(h, nbins);
       cur = idx;
-      cnt = k;
+      cnt = 1;
     }
   }
   __device__ __forceinline__ void flush(uint32_t* h, int nbins) {
@@ -116,41 +105,8 @@ struct RunAgg {
   }
 };
 
-// 16 pixels in four groups of four.  A group whose four (label, prediction) pairs are identical -- the common case in
-// segmentation maps, decided with two compares on the raw words -- decodes ONE label and extends the current run by 4;
-// any other group goes pixel by pixel straight to the shared-memory histogram (decode, index, one ATOMS each: no run
-// bookkeeping, no data-dependent branch per pixel).
 template <typename LabelT>
-__device__ __forceinline__ void hist_chunk(const RawLabels<LabelT>& L, const uint4& pv, int n_cls, const uint8_t* lut,
-                                           RunAgg& agg, uint32_t* myh, int nbins) {
-  const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint32_t w = pw[g];
-    const uint32_t b0 = w & 0xffu;
-    if (w == b0 * 0x01010101u && L.uniform4(g)) {
-      const int a = L.decode(4 * g, n_cls, lut);
-      agg.push(a >= 0 ? a * n_cls + (int)b0 : -1, 4u, myh, nbins);
-    } else {
-      agg.flush(myh, nbins);
-      agg.cur = -1;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int a = L.decode(4 * g + i, n_cls, lut);
-        const int idx = a * n_cls + (int)((w >> (8 * i)) & 0xffu);
-        if (a >= 0) {
-          if (idx < nbins)
-            atomicAdd(&myh[idx], 1u);
-          else
-            ++agg.ovf;
-        }
-      }
-    }
-  }
-}
-
-template <typename LabelT>
-__global__ void __launch_bounds__(HIST_THREADS, 4)
+__global__ void __launch_bounds__(HIST_THREADS)
 fast_hist_kernel(const LabelT* __restrict__ label, const uint8_t* __restrict__ pred, int64_t n_px,
                  int n_cls, int n_sub, unsigned long long* __restrict__ hist,
                  unsigned long long* __restrict__ overflow, int vec_ok, const uint8_t* __restrict__ lut_g) {
@@ -166,42 +122,23 @@ fast_hist_kernel(const LabelT* __restrict__ label, const uint8_t* __restrict__ p
   RunAgg agg{-1, 0, 0};
   const int64_t tid = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * HIST_THREADS;
-  const int64_t n_vec = vec_ok ? (n_px >> 4) : 0;  // chunks of 16 pixels
-  // u8 labels move only 32 bytes per thread and chunk: the next chunk is requested before the current one is counted, so
-  // every thread always has a pair of 16-byte loads in flight (the wider label types carry 80 / 144 bytes per chunk already)
-  constexpr bool PREFETCH = sizeof(LabelT) == 1;
-  if (PREFETCH) {
-    RawLabels<LabelT> L;
-    uint4 pv = make_uint4(0u, 0u, 0u, 0u);
-    int64_t c = tid;
-    if (c < n_vec) {
-      L.load(label + c * 16);
-      pv = ld_stream(reinterpret_cast<const uint4*>(pred + c * 16));
-    }
-    while (c < n_vec) {
-      const int64_t cn = c + nthreads;
-      RawLabels<LabelT> Ln = L;
-      uint4 pn = pv;
-      if (cn < n_vec) {
-        Ln.load(label + cn * 16);
-        pn = ld_stream(reinterpret_cast<const uint4*>(pred + cn * 16));
-      }
-      hist_chunk<LabelT>(L, pv, n_cls, lut, agg, myh, nbins);
-      L = Ln;
-      pv = pn;
-      c = cn;
-    }
-  } else {
-    for (int64_t c = tid; c < n_vec; c += nthreads) {
-      RawLabels<LabelT> L;
-      L.load(label + c * 16);
-      const uint4 pv = ld_stream(reinterpret_cast<const uint4*>(pred + c * 16));
-      hist_chunk<LabelT>(L, pv, n_cls, lut, agg, myh, nbins);
+  int64_t n_vec = vec_ok ? (n_px >> 4) : 0;  // chunks of 16 pixels
+  for (int64_t c = tid; c < n_vec; c += nthreads) {
+    int a[16];
+    LabelLoad<LabelT>::load16(label + c * 16, n_cls, a, lut);
+    uint4 pv = ld_stream(reinterpret_cast<const uint4*>(pred + c * 16));
+    uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int b = (pw[i >> 2] >> ((i & 3) * 8)) & 0xff;
+      int idx = a[i] >= 0 ? a[i] * n_cls + b : -1;
+      agg.push(idx, myh, nbins);
     }
   }
   for (int64_t i = n_vec * 16 + tid; i < n_px; i += nthreads) {
-    const int a = RawLabels<LabelT>::load1(label + i, n_cls, lut);
-    agg.push(a >= 0 ? a * n_cls + (int)pred[i] : -1, 1u, myh, nbins);
+    int a = LabelLoad<LabelT>::load1(label + i, n_cls, lut);
+    int idx = a >= 0 ? a * n_cls + (int)pred[i] : -1;
+    agg.push(idx, myh, nbins);
   }
   agg.flush(myh, nbins);
   if (agg.ovf) atomicAdd(overflow, (unsigned long long)agg.ovf);
@@ -222,9 +159,8 @@ static int launch_hist(const void* label, const uint8_t* pred, int64_t n_px, int
   if (n_sub > HIST_WARPS) n_sub = HIST_WARPS;
   ASN_CHECK_ARG(n_sub >= 1, "asn_fast_hist: n_cls=%d too large for the shared-memory histogram", n_cls);
   int vec_ok = ((reinterpret_cast<uintptr_t>(label) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0;
-  // 16 px per thread-iteration; at least 4 iterations per thread before adding CTAs; a persistent grid of exactly the
-  // 4 CTAs per SM the launch bounds guarantee (one wave: no second, partly filled round of the grid-stride loop)
-  int grid = wave_grid((n_px + 63) / 64, HIST_THREADS, 4);
+  // 16 px per thread-iteration; at least 4 iterations per thread before adding CTAs
+  int grid = wave_grid((n_px + 63) / 64, HIST_THREADS, 8);
   // 32-bit shared counters: keep every CTA below 2^31 pixels
   while ((n_px + grid - 1) / grid > (int64_t)1 << 31) grid *= 2;
   prof::Scope ps("fast_hist", 0, (double)n_px * (sizeof(LabelT) + 1), st);
