@@ -255,16 +255,25 @@ aspp_dycols_chunk_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict
   const int qh = q / W, qw = q - qh * W;
   const float* dyn = dy + (int64_t)n * n_cls * P;
   int t = (ck * 16) / n_cls, c = ck * 16 - t * n_cls;                  // warp-uniform
+  // the source pixel and its bounds test depend on the tap only: computed when the tap changes (a chunk spans <= 2 taps at
+  // 19 classes), the class steps the pointer by one plane
+  const float* src = dyn;
+  bool ok = false;
+  auto set_tap = [&]() {
+    ok = false;
+    if (t < taps.n_taps) {
+      const int h = qh - taps.dh[t], w = qw - taps.dw[t];
+      ok = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+      src = dyn + (int64_t)c * P + (ok ? h * W + w : 0);
+    }
+  };
+  set_tap();
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float x = 0.f;
-    if (t < taps.n_taps) {
-      const int h = qh - taps.dh[t], w = qw - taps.dw[t];
-      if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) x = __ldg(dyn + (int64_t)c * P + h * W + w);
-    }
-    v[i] = x;
-    if (++c == n_cls) { c = 0; ++t; }
+    v[i] = ok ? __ldg(src) : 0.f;
+    src += P;
+    if (++c == n_cls) { c = 0; ++t; set_tap(); }
   }
   uint32_t pk[8];
 #pragma unroll

@@ -547,6 +547,49 @@ fcd_cls_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w
   }
 }
 
+// Same gradient, thread = 8 consecutive channels of one pixel (16-byte accesses of A4, dPre4 and the fp32 tap weights; the pixel's
+// index arithmetic and its <= 4 dout values are shared by 8 channels instead of 2).  Same fmaf order per channel: bit-identical.
+__global__ void __launch_bounds__(256)
+fcd_cls_dgrad8_kernel(const float* __restrict__ dout, const float* __restrict__ wc,
+                      const __nv_bfloat16* __restrict__ a4, __nv_bfloat16* __restrict__ dpre4, int N, int H4, int W4,
+                      int C, int H5, int W5) {
+  const int groups = C / 8;
+  const int64_t total = (int64_t)N * H4 * W4 * groups;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % groups) * 8;
+  const int64_t px = i / groups;
+  const int iw = (int)(px % W4), ih = (int)((px / W4) % H4), n = (int)(px / ((int64_t)W4 * H4));
+  const uint4 av = __ldg(reinterpret_cast<const uint4*>(a4 + px * C + c));
+  float g[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) g[e] = 0.f;
+  for (int kh = (ih + 1) & 1; kh < 4; kh += 2) {
+    const int oh = (ih + 1 - kh) / 2;
+    if (ih + 1 - kh < 0 || oh >= H5) continue;
+    for (int kw = (iw + 1) & 1; kw < 4; kw += 2) {
+      const int ow = (iw + 1 - kw) / 2;
+      if (iw + 1 - kw < 0 || ow >= W5) continue;
+      const float d = __ldg(dout + ((int64_t)n * H5 + oh) * W5 + ow);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + (kh * 4 + kw) * C + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + (kh * 4 + kw) * C + c + 4));
+      g[0] = fmaf(d, w0.x, g[0]); g[1] = fmaf(d, w0.y, g[1]); g[2] = fmaf(d, w0.z, g[2]); g[3] = fmaf(d, w0.w, g[3]);
+      g[4] = fmaf(d, w1.x, g[4]); g[5] = fmaf(d, w1.y, g[5]); g[6] = fmaf(d, w1.z, g[6]); g[7] = fmaf(d, w1.w, g[7]);
+    }
+  }
+  const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+  uint32_t ow4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+    const float g0 = g[2 * j] * (__low2float(a) > 0.f ? 1.f : FCD_SLOPE);
+    const float g1 = g[2 * j + 1] * (__high2float(a) > 0.f ? 1.f : FCD_SLOPE);
+    const __nv_bfloat162 o = __floats2bfloat162_rn(g0, g1);
+    ow4[j] = *reinterpret_cast<const uint32_t*>(&o);
+  }
+  *reinterpret_cast<uint4*>(dpre4 + px * C + c) = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
+}
+
 // dwc[0][c][kh][kw] = sum_{n,oh,ow} dout * A4[n][2oh-1+kh][2ow-1+kw][c].
 // grid (CLS_SLICES, C/64): thread = (channel, 1 of 4 pixel phases).  Every INPUT pixel of the slice is read once
 // (coalesced 128-byte rows along the channels) and feeds the <= 4 taps whose stride-2 footprint contains it -- which
@@ -1472,10 +1515,18 @@ static int fcd_bwd_impl(const float* dout, const float* x_logits, int x_h, int x
   const float* wc = reinterpret_cast<const float*>(wb + p.wc_off);
 
   // classifier
-  prof::Scope ps_cls("fcd_classifier_dgrad", 0, 4.0 * N * p.H[4] * p.W[4] * p.C[4], st);
-  fcd_cls_dgrad_kernel<<<full_grid((int64_t)N * p.H[4] * p.W[4] * (p.C[4] / 2), 256), 256, 0, st>>>(
-      dout, wc, A[4], dPre[4], N, p.H[4], p.W[4], p.C[4], p.H[5], p.W[5]);
-  ASN_LAUNCH_CHECK();
+  static const bool cls8 = !(getenv("ASN_GLUE") != nullptr && getenv("ASN_GLUE")[0] == '0');
+  {
+    prof::Scope ps_cls("fcd_classifier_dgrad", 0, 4.0 * N * p.H[4] * p.W[4] * p.C[4], st);
+    if (cls8 && p.C[4] % 8 == 0 && ((reinterpret_cast<uintptr_t>(A[4]) | reinterpret_cast<uintptr_t>(dPre[4]) |
+                                      reinterpret_cast<uintptr_t>(wc)) & 15) == 0)
+      fcd_cls_dgrad8_kernel<<<full_grid((int64_t)N * p.H[4] * p.W[4] * (p.C[4] / 8), 256), 256, 0, st>>>(
+          dout, wc, A[4], dPre[4], N, p.H[4], p.W[4], p.C[4], p.H[5], p.W[5]);
+    else
+      fcd_cls_dgrad_kernel<<<full_grid((int64_t)N * p.H[4] * p.W[4] * (p.C[4] / 2), 256), 256, 0, st>>>(
+          dout, wc, A[4], dPre[4], N, p.H[4], p.W[4], p.C[4], p.H[5], p.W[5]);
+    ASN_LAUNCH_CHECK();
+  }
   if (dparams_host) {
     ASN_CHECK_ARG(dparams_host[8] && dparams_host[9], "asn_fcd_bwd: null classifier gradient");
     {

@@ -246,7 +246,10 @@ def gpu_eager_reference(dev, args, steps=5, warmup=3):
                                        "median of 5 after 2 warm-ups, L2 flushed between repetitions: heads = 2 ASPP heads x "
                                        "(source, target) fwd+bwd; seg_loss = upsample+CE fwd+bwd (source, 2 heads); adversarial = "
                                        "all discriminator passes of both levels incl. target upsample+softmax and the GAN "
-                                       "losses; optimizers = SGD + 2 x Adam")
+                                       "losses; optimizers = SGD + 2 x Adam.  ours_ms and aten_*_ms: both launched eagerly from "
+                                       "Python, kernel by kernel (the speed-ups are computed from these); ours_graph_ms: the same "
+                                       "group of libasn_b200 launches replayed as one CUDA graph, which is how the product runs them "
+                                       "(AdaptSegTrainer captures the iteration) -- the device time without the host launch path")
     return out
 
 

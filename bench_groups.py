@@ -172,6 +172,28 @@ def measure_ours(dev, tier="B", reps=5, warm=2):
     from adaptsegnet_b200.train_step import TrainConfig
 
     T = _Timer(dev, reps, warm)
+
+    def graphed(fn):
+        """the same group replayed as ONE CUDA graph (how the product runs it: AdaptSegTrainer captures the iteration), i.e.
+        without the Python / ctypes launch path between its 20-60 small kernels; None if the group cannot be captured"""
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return T(g.replay)
+        except Exception as e:   # noqa: BLE001 -- an informational extra: never let it take the bench line down
+            import sys
+            print(f"[bench_groups] graph replay of a group not measured: {type(e).__name__}: {e}", file=sys.stderr)
+            torch.cuda.synchronize(dev)
+            return None
+
     torch.manual_seed(1338)
     rates = [6, 12, 18, 24]
     l5, l6 = Classifier_Module(1024, rates, rates, 19).to(dev), Classifier_Module(2048, rates, rates, 19).to(dev)
@@ -190,6 +212,7 @@ def measure_ours(dev, tier="B", reps=5, warm=2):
                 torch.autograd.grad(y, [x] + list(head.parameters()), dz)
 
     out["heads"] = T(heads)
+    gout = {"heads": graphed(heads)}
     z_s = [torch.randn((1, 19) + SRC_F, device=dev).mul_(3).requires_grad_(True) for _ in range(2)]
     z_t = [torch.randn((1, 19) + TGT_F, device=dev).mul_(3).requires_grad_(True) for _ in range(2)]
     lazy = tier == "B"
@@ -204,6 +227,7 @@ def measure_ours(dev, tier="B", reps=5, warm=2):
         torch.autograd.grad(loss, z_s)
 
     out["seg_loss"] = T(seg_loss)
+    gout["seg_loss"] = graphed(seg_loss)
     with torch.no_grad():
         pred_s = None if lazy else [ops.upsample_bilinear(z, SRC_HW) for z in z_s]
 
@@ -234,6 +258,7 @@ def measure_ours(dev, tier="B", reps=5, warm=2):
             torch.autograd.grad(ops.gan_loss(d, 1.0) / 2, list(D.parameters()))
 
     out["adversarial"] = T(adversarial)
+    gout["adversarial"] = graphed(adversarial)
     G = DeeplabMulti(19).to(dev)
     cfg = TrainConfig()
     flat_g, flat_d = FlatParams(G.parameters()), [FlatParams(D.parameters()) for D in (D1, D2)]
@@ -248,7 +273,10 @@ def measure_ours(dev, tier="B", reps=5, warm=2):
             a.step()
 
     out["optimizers"] = T(optimizers)
+    gout["optimizers"] = graphed(optimizers)
     out["total"] = sum(out.values())
+    gout["total"] = sum(gout.values()) if all(v is not None for v in gout.values()) else None
+    out["_graph"] = gout
     return out
 
 
@@ -261,8 +289,11 @@ def compare(dev, tier="B", reps=5, warm=2):
     ref_fp32 = measure_reference(dev, False, reps, warm)
     torch.cuda.empty_cache()
     groups = {}
+    ours_graph = ours.pop("_graph", {})
     for k in ours:
-        groups[k] = {"ours_ms": round(ours[k], 4), "aten_tf32_ms": round(ref_tf32[k], 4),
+        groups[k] = {"ours_ms": round(ours[k], 4),
+                     "ours_graph_ms": None if ours_graph.get(k) is None else round(ours_graph[k], 4),
+                     "aten_tf32_ms": round(ref_tf32[k], 4),
                      "aten_fp32_ms": round(ref_fp32[k], 4),
                      "speedup_vs_tf32": round(ref_tf32[k] / ours[k], 2), "speedup_vs_fp32": round(ref_fp32[k] / ours[k], 2)}
     return groups
