@@ -52,7 +52,7 @@ struct RawLabels<int32_t> {
   __device__ __forceinline__ void load(const int32_t* p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + j);   // (L1-allocating: see the int64 loader)
       w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
     }
   }
@@ -75,8 +75,10 @@ struct RawLabels<int64_t> {
   __device__ __forceinline__ void load(const int64_t* p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      // little endian: (x,y) = first int64, (z,w) = second
-      const uint4 v = ld_stream(reinterpret_cast<const uint4*>(p) + j);
+      // little endian: (x,y) = first int64, (z,w) = second.  A thread's 128 bytes are one cache line and a warp instruction
+      // touches 32 different lines, 16 bytes each: the loads allocate in L1 (plain __ldg, not the streaming form), so the
+      // line comes from L2 once and the other seven loads hit L1 instead of requesting the same sectors again
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + j);
       lo[2 * j] = v.x; hi[2 * j] = v.y; lo[2 * j + 1] = v.z; hi[2 * j + 1] = v.w;
     }
   }

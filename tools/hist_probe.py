@@ -50,7 +50,7 @@ for cname, (l64, p) in cases.items():
             hist = torch.zeros(19 * 19, dtype=torch.int64, device=dev)
             ovf = torch.zeros(1, dtype=torch.int64, device=dev)
             ts = []
-            for rep in range(7):
+            for rep in range(int(os.environ.get("HIST_PROBE_REPS", "7"))):
                 hist.zero_()
                 flush.sum()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
